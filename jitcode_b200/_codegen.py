@@ -1,0 +1,178 @@
+"""
+CUDA code generator: the B200 counterpart of generate_f_C / generate_helpers_C
+(_jitcode.py:186-249, 332-360) and of the container jitced_template.c.
+
+The reference prints one `set_dy(i, <expr>)` statement per component into f.c and wraps it in a
+CPython extension; here the same statements (`dy.set(i, <expr>);`, reading `y(i)`, `t`,
+`par.v[k]` and helper temporaries) become the body of `jb_generated::Sys::rhs`, a device
+function template that the hand-written Runge–Kutta kernels of csrc/jb_rk.cuh inline into their
+stage loop (register storage) or call out of line (global storage).  The vector types behind
+`y` and `dy` decide where the state lives; the printed text is the same for both — the role the
+accessor macros play in jitced_template.c:38-55.
+"""
+
+import sympy
+from sympy.core.function import AppliedUndef
+from sympy.printing.c import C99CodePrinter
+
+from ._symbolic import t as TIME
+
+JB_DP5, JB_DOP853 = 0, 1
+JB_DRV_ODE, JB_DRV_IVP_DENSE, JB_DRV_IVP_LAND = 0, 1, 2
+JB_STORE_REGISTERS, JB_STORE_GLOBAL = 0, 1
+
+METHOD_NAMES = {JB_DP5: "JB_DP5", JB_DOP853: "JB_DOP853"}
+DRIVER_NAMES = {JB_DRV_ODE: "JB_DRV_ODE", JB_DRV_IVP_DENSE: "JB_DRV_IVP_DENSE", JB_DRV_IVP_LAND: "JB_DRV_IVP_LAND"}
+STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL"}
+
+
+class CudaPrinter(C99CodePrinter):
+	"""FP64 CUDA C++: small integer powers become products (no pow() call on the FP64 pipe),
+	everything else is the C99 text the reference's generated code would contain."""
+
+	MAX_PRODUCT_POWER = 8
+
+	def __init__(self):
+		super().__init__({"allow_unknown_functions": True})
+
+	def _print_Pow(self, expr):
+		base, exponent = expr.base, expr.exp
+		if exponent.is_Integer and 2 <= abs(int(exponent)) <= self.MAX_PRODUCT_POWER:
+			text = self._print(base)
+			if not (base.is_Symbol or isinstance(base, AppliedUndef) or (base.is_Number and base >= 0)):
+				text = f"({text})"
+			product = "*".join([text] * abs(int(exponent)))
+			return product if exponent > 0 else f"1.0/({product})"
+		return super()._print_Pow(expr)
+
+	def _print_Integer(self, expr):
+		# keep every literal a double: no integer arithmetic, no integer division
+		return f"{int(expr)}.0"
+
+	def _print_AppliedUndef(self, expr):
+		# y(3): the index stays an integer literal
+		return f"{expr.func.__name__}({', '.join(str(int(arg)) if arg.is_Integer else self._print(arg) for arg in expr.args)})"
+
+	def _print_Function(self, expr):
+		if isinstance(expr, AppliedUndef):
+			return self._print_AppliedUndef(expr)
+		return super()._print_Function(expr)
+
+
+def _repeated_function_calls(expressions):
+	"""transcendental calls (sin(t), exp(y(0)) …) that occur in more than one place, innermost first."""
+	counts = {}
+	for expr in expressions:
+		for atom in expr.atoms(sympy.Function):
+			if not isinstance(atom, AppliedUndef):
+				counts[atom] = counts.get(atom, 0) + expr.count(atom)
+	repeated = [atom for atom, count in counts.items() if count > 1]
+	repeated.sort(key=lambda atom: (sympy.count_ops(atom), sympy.default_sort_key(atom)))
+	return repeated
+
+
+def rhs_statements(f, helpers, control_pars, do_cse=False):
+	"""
+	f            : list of expressions in y(i), t, helper symbols, control parameters
+	helpers      : sorted list of (symbol, definition)
+	control_pars : list of symbols
+	returns the lines of the body of Sys::rhs.
+	"""
+	subs = {par: sympy.Symbol(f"par.v[{k}]") for k, par in enumerate(control_pars)}
+	for k, (symbol, _) in enumerate(helpers):
+		subs[symbol] = sympy.Symbol(f"jb_helper_{k}")
+	helper_defs = [definition.xreplace(subs) for _, definition in helpers]
+	f = [entry.xreplace(subs) for entry in f]
+
+	printer = CudaPrinter()
+	lines = []
+
+	# shared temporaries: repeated function calls always; full common-subexpression elimination on request
+	everything = helper_defs + f
+	temporaries = []
+	if do_cse:
+		replacements, everything = sympy.cse(everything, symbols=(sympy.Symbol(f"jb_cse_{k}") for k in range(10**9)), order="none")
+		temporaries = list(replacements)
+	else:
+		for k, call in enumerate(_repeated_function_calls(everything)):
+			symbol = sympy.Symbol(f"jb_call_{k}")
+			everything = [expr.xreplace({call: symbol}) for expr in everything]
+			temporaries = [(s, d.xreplace({call: symbol})) for s, d in temporaries]
+			temporaries.append((symbol, call))
+	helper_defs, f = everything[:len(helpers)], everything[len(helpers):]
+
+	# temporaries may use helpers and vice versa: emit each as soon as its inputs exist
+	helper_symbols = {sympy.Symbol(f"jb_helper_{k}"): k for k in range(len(helpers))}
+	emitted = set()
+	pending_tmp = list(temporaries)
+	def flush_temporaries():
+		progress = True
+		while progress:
+			progress = False
+			for item in list(pending_tmp):
+				needs = {s for s in item[1].free_symbols if s in helper_symbols or s.name.startswith(("jb_cse_", "jb_call_"))}
+				if needs <= emitted:
+					lines.append(f"const double {item[0].name} = {printer.doprint(item[1])};")
+					emitted.add(item[0])
+					pending_tmp.remove(item)
+					progress = True
+	flush_temporaries()
+	for k, definition in enumerate(helper_defs):
+		lines.append(f"const double jb_helper_{k} = {printer.doprint(definition)};")
+		emitted.add(sympy.Symbol(f"jb_helper_{k}"))
+		flush_temporaries()
+	assert not pending_tmp, "unresolvable temporaries"
+	for i, entry in enumerate(f):
+		lines.append(f"dy.set({i}, {printer.doprint(entry)});")
+	return lines
+
+
+def uses_time(f, helpers):
+	return any(TIME in expr.free_symbols for expr in list(f) + [d for _, d in helpers])
+
+
+def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, chunk_size=None):
+	"""the complete translation unit of one module (what _render_template produces from
+	jitced_template.c in the reference, _jitcode.py:397-406)."""
+	tangent_indices = list(tangent_indices or [])
+	if tangent_indices:
+		table = ", ".join(str(int(k)) for k in tangent_indices)
+		tangent = (
+			f"\tstatic __device__ __forceinline__ int tangent_index(int k)\n"
+			f"\t{{\n\t\tconstexpr int table[{len(tangent_indices)}] = {{ {table} }};\n\t\treturn table[k];\n\t}}\n"
+		)
+	else:
+		tangent = "\tstatic __device__ __forceinline__ int tangent_index(int) { return 0; }\n"
+
+	# large right-hand sides are cut into chunks (the role of chunk_size in render_and_write_code,
+	# _jitcode.py:198-200): temporaries first, then groups of statements in their own scope
+	body = "\n".join("\t\t" + line for line in statements)
+	return f"""// generated by jitcode_b200._codegen — one ODE system fused into the ensemble Runge–Kutta kernels
+#include "jb_rk.cuh"
+
+namespace jb_generated {{
+
+struct Sys {{
+	static constexpr int N = {n};      // dimension of the integrated system
+	static constexpr int NP = {n_params};     // control parameters per trajectory
+	static constexpr int NB = {n_basic};     // dimension of the underlying system
+	static constexpr int NL = {n_lyap};     // tangent vectors
+	static constexpr int NT = {len(tangent_indices)};     // transversal tangent coordinates
+	struct Par {{ double v[NP > 0 ? NP : 1]; }};
+{tangent}
+	template <class VI, class VO>
+	static __device__ __forceinline__ void rhs(const double t, const VI &y, VO &dy, const Par &par)
+	{{
+{body}
+		(void) t; (void) par;
+	}}
+}};
+
+}}  // namespace jb_generated
+
+#define JB_MODULE_METHOD {METHOD_NAMES[method]}
+#define JB_MODULE_DRIVER {DRIVER_NAMES[driver]}
+#define JB_MODULE_STORAGE {STORAGE_NAMES[storage]}
+#define JB_MODULE_THREADS {int(threads)}
+#include "jb_module.cuh"
+"""

@@ -1,0 +1,634 @@
+"""
+The JiTCODE classes on top of the B200 ensemble engine.
+
+Same public surface as the reference (jitcode/_jitcode.py): `jitcode` (:49-669), `jitcode_lyap`
+(:671-779), `jitcode_transversal_lyap` (:782-919), `jitcode_restricted_lyap` (:922-946), `test`
+(:948-965); SymPy input instead of SymEngine.  What differs is what happens below the surface
+and that every state has a batch axis:
+
+  * `set_initial_value` takes one state (n,) like the reference or an ensemble (B, n);
+    `set_parameters` takes scalars or one value per trajectory; `integrate(t)` advances all B
+    trajectories with ONE kernel launch and returns (B, n) (or (n,) for a single state);
+  * the code generator emits CUDA (generate_f_cuda, alias generate_f_C), nvcc compiles it for
+    sm_100a into a cached shared object (compile_cuda, alias compile_C) that is loaded through
+    ctypes (include/jitcode_b200.h); the Runge–Kutta steppers are part of that module;
+  * only the explicit Dormand–Prince pairs exist: "dopri5"/"dop853" (Hairer's controller, the
+    reference's `ode` back end) and "RK45"/"DOP853" (SciPy's solve_ivp controller, with or
+    without interpolation); no lambdified fallback, no Python callbacks, no implicit solvers.
+"""
+
+import shutil
+from pathlib import Path
+from warnings import warn
+
+import numpy as np
+import sympy
+import torch
+
+from . import _build, _codegen
+from ._integrator import (
+	JB_POST_LYAP_QR, JB_POST_LYAP_RESTRICTED, JB_POST_LYAP_TRANSVERSAL, JB_POST_NONE,
+	CudaEnsembleIntegrator, UnsuccessfulIntegration, empty_integrator, require_cuda,
+)
+from ._symbolic import dynvar_arguments, handle_input, jacobian_rows, lyapunov_system, sort_helpers, t, y
+from ._transversal import GroupHandler
+
+# name → (method, backend); the reference resolves names in integrator_info (integrator_tools.py:15-37)
+INTEGRATORS = {
+	"dopri5": (_codegen.JB_DP5, "ode"),
+	"dop853": (_codegen.JB_DOP853, "ode"),
+	"RK45": (_codegen.JB_DP5, "ivp"),
+	"DOP853": (_codegen.JB_DOP853, "ivp"),
+}
+NOT_REBUILT = ("RK23", "Radau", "BDF", "LSODA", "vode", "lsoda", "zvode")
+
+_used_module_names = set()
+
+
+def _storage_for(n, method, driver):
+	"""registers while state + stages fit a thread's register file, else the tiled global workspace."""
+	rows = (7 if method == _codegen.JB_DP5 else (16 if driver == _codegen.JB_DRV_IVP_DENSE else 13)) + 3
+	return _codegen.JB_STORE_REGISTERS if rows * n <= 88 else _codegen.JB_STORE_GLOBAL
+
+
+class jitcode:
+	"""
+	Parameters (as in the reference, _jitcode.py:49-95)
+	----------
+	f_sym : iterable of SymPy expressions, generator function, or dictionary {y(i): expression}
+	helpers : list of (symbol, expression) pairs evaluated before the derivative
+	wants_jacobian : accepted for compatibility; the explicit methods never use a Jacobian
+	n : length of f_sym (checked)
+	control_pars : symbols that are set after compilation with `set_parameters` — per trajectory here
+	callback_functions : not supported on a GPU (must be empty)
+	verbose : progress reports
+	module_location : path of a module saved with `save_compiled`; then f_sym may be omitted but n must be given
+	"""
+
+	dynvar = y
+
+	def __init__(self, f_sym=(), *, helpers=None, wants_jacobian=False, n=None, control_pars=(),
+			callback_functions=(), verbose=True, module_location=None):
+		if callback_functions:
+			raise NotImplementedError("Python callbacks cannot run inside a CUDA kernel.")
+		self.verbose = verbose
+		self._f_list, self.n = self._handle_input(f_sym, n, module_location)
+		self.helpers = sort_helpers(helpers)
+		self.control_pars = list(control_pars)
+		self.control_par_values = None
+		self._wants_jacobian = wants_jacobian
+		self.integrator = empty_integrator()
+		self._statements = None
+		self._compile_options = {"extra_compile_args": (), "extra_link_args": (), "verbose": False}
+		self._modules = {}
+		self._integrator_config = None
+		self._module_location = module_location
+		self._f_module = None
+		if module_location is not None:
+			module = _build.CudaModule(module_location)
+			if module.info.n != self.n:
+				raise ValueError("The module at module_location was compiled for a different dimension.")
+			self._modules[(module.info.method, module.info.driver, module.info.storage)] = module
+		# layout constants of the module; the Lyapunov subclasses overwrite them
+		self._n_basic_module = self.n
+		self._n_lyap_module = 0
+		self._tangent_indices_module = []
+
+	# ------------------------------------------------------------------ input handling and checks
+
+	def _handle_input(self, f_sym, n, module_location=None):
+		if module_location is not None and not f_sym:
+			if n is None:
+				raise ValueError("If no f_sym is given, n must be given.")
+			return [], n
+		return handle_input(f_sym, n)
+
+	def f_sym(self):
+		return iter(self._f_list)
+
+	def report(self, message):
+		if self.verbose:
+			print(message)
+
+	def _check_assert(self, condition, message):
+		if not condition:
+			self._check_failures.append(message)
+
+	def check(self, fail_fast=True):
+		"""Runs the consistency checks of the reference (_jitcode.py:128-154); raises ValueError on the first
+		(fail_fast) or on all collected problems."""
+		self._check_failures = []
+		checks = (self._check_non_empty, self._check_valid_arguments, self._check_valid_symbols)
+		for checker in checks:
+			checker()
+			if self._check_failures and fail_fast:
+				break
+		if self._check_failures:
+			raise ValueError("\n".join(self._check_failures))
+
+	def _check_non_empty(self):
+		self._check_assert(self._f_list, "f_sym is empty.")
+
+	def _check_valid_arguments(self):
+		for i, entry in enumerate(self._f_list):
+			for argument in dynvar_arguments(entry):
+				self._check_assert(len(argument) == 1 and argument[0].is_Integer, f"y is called with invalid arguments {argument} in equation {i}.")
+				if len(argument) == 1 and argument[0].is_Integer:
+					self._check_assert(argument[0] >= 0, f"y is called with a negative argument ({argument[0]}) in equation {i}.")
+					self._check_assert(argument[0] < self.n, f"y is called with an argument ({argument[0]}) higher than the system’s dimension ({self.n}) in equation {i}.")
+
+	def _check_valid_symbols(self):
+		valid = {t} | {helper[0] for helper in self.helpers} | set(self.control_pars)
+		for i, entry in enumerate(self._f_list):
+			for symbol in entry.free_symbols:
+				self._check_assert(symbol in valid, f"Invalid symbol ({symbol.name}) in equation {i}.")
+
+	# ------------------------------------------------------------------ symbolic Jacobian (tangent equations use it)
+
+	@property
+	def jac_sym(self):
+		if not hasattr(self, "_jac_sym"):
+			self._jac_sym = list(jacobian_rows(self._f_list, self.helpers, self.n))
+			self.report("generated symbolic Jacobian")
+		return self._jac_sym
+
+	# ------------------------------------------------------------------ code generation and compilation
+
+	def generate_f_cuda(self, simplify=None, do_cse=False, chunk_size=None):
+		"""
+		Translates the derivative to CUDA statements (counterpart of generate_f_C, _jitcode.py:186-249).
+
+		simplify : apply SymPy's `simplify(ratio=1)` to every component first (default: off — nvcc optimises
+			the arithmetic anyway and SymPy's simplify is slow; the reference defaults to n<=10)
+		do_cse : full common-subexpression elimination with sympy.cse (repeated function calls such as
+			sin(t) are always shared)
+		chunk_size : accepted for compatibility; the global-storage kernels call one out-of-line copy of the
+			right-hand side, which bounds code size the way chunking does for the C compiler
+		"""
+		self.check()
+		f = self._f_list
+		if simplify:
+			f = [entry.simplify(ratio=1.0) for entry in f]
+		self._statements = _codegen.rhs_statements(f, self.helpers, self.control_pars, do_cse=do_cse)
+		self._modules = {}
+		self._f_module = None
+		self.report("generated CUDA code for f")
+
+	generate_f_C = generate_f_cuda
+
+	def generate_helpers_C(self, chunk_size=None):
+		"""helpers are emitted together with f (generate_f_cuda); kept for call compatibility."""
+
+	def generate_jac_C(self, *args, **kwargs):
+		raise NotImplementedError("Only explicit Runge–Kutta methods exist here; none of them uses a Jacobian.")
+
+	def generate_lambdas(self, *args, **kwargs):
+		raise NotImplementedError("There is no CPU fallback: the derivative only exists as CUDA code.")
+
+	def compile_cuda(self, extra_compile_args=None, extra_link_args=None, verbose=False, modulename=None, omp=None,
+			method=_codegen.JB_DP5, driver=_codegen.JB_DRV_ODE, storage=None, threads=None):
+		"""
+		Compiles (or fetches from the cache) and loads the module for one integrator configuration
+		(counterpart of compile_C, _jitcode.py:367-417).  `set_integrator` calls this itself.
+		"""
+		if modulename is not None:
+			if modulename in _used_module_names:
+				raise NameError("Module name has already been used in this instance of Python.")
+			_used_module_names.add(modulename)
+		if extra_compile_args is not None:
+			self._compile_options["extra_compile_args"] = tuple(extra_compile_args)
+		if extra_link_args is not None:
+			self._compile_options["extra_link_args"] = tuple(extra_link_args)
+		self._compile_options["verbose"] = verbose
+		return self._module(method, driver, storage, threads)
+
+	compile_C = compile_cuda
+
+	def _module(self, method, driver, storage=None, threads=None):
+		if storage is None:
+			storage = _storage_for(self.n, method, driver)
+		key = (method, driver, storage) if threads is None else (method, driver, storage, threads)
+		if key not in self._modules:
+			if self._statements is None:
+				if not self._f_list:
+					raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
+				self.generate_f_cuda()
+			if threads is None:
+				threads = 128 if storage == _codegen.JB_STORE_REGISTERS else 64
+			source = _codegen.module_source(
+				self._statements, self.n, len(self.control_pars),
+				self._n_basic_module, self._n_lyap_module, self._tangent_indices_module,
+				method, driver, storage, threads,
+			)
+			path = _build.compile_module(
+				source, self._compile_options["extra_compile_args"], self._compile_options["extra_link_args"],
+				verbose=self._compile_options["verbose"],
+			)
+			self._modules[key] = _build.CudaModule(path)
+			self.report(f"compiled and loaded {path.name}")
+		return self._modules[key]
+
+	def save_compiled(self, destination="", overwrite=False):
+		"""Copies the module of the current integrator (compiling the default one if there is none) to
+		`destination` and returns the path, to be passed as `module_location` (tests/test_jitcode.py:77-84)."""
+		if self._integrator_config is not None:
+			module = self._module(*self._integrator_config)
+		elif self._modules:
+			module = next(iter(self._modules.values()))
+		else:
+			module = self._module(_codegen.JB_DP5, _codegen.JB_DRV_ODE)
+		source = Path(module.path)
+		destination = Path(destination) if destination else Path.cwd()
+		if destination.is_dir() or str(destination).endswith("/"):
+			destination = destination / source.name
+		if destination.exists() and not overwrite:
+			raise OSError(f"Target File already exists and “overwrite” is set to False: {destination}")
+		destination.parent.mkdir(parents=True, exist_ok=True)
+		shutil.copyfile(source, destination)
+		return str(destination)
+
+	# ------------------------------------------------------------------ f(t, y), as the reference exposes jitced.f
+
+	def f(self, time, state):
+		"""Evaluates the compiled derivative on the GPU: state (n,) → (n,), or (B, n) → (B, n)."""
+		module = self._f_module or (next(iter(self._modules.values())) if self._modules else self._module(_codegen.JB_DP5, _codegen.JB_DRV_ODE))
+		self._f_module = module
+		helper = CudaEnsembleIntegrator(module, device=getattr(self.integrator, "device", None))
+		rows, kind, single = helper._to_device_rows(state, self.n, "state")
+		helper._alloc(rows.shape[0])
+		helper._out_kind, helper._single = kind, single
+		if self.control_pars:
+			helper.set_parameters(self._parameter_rows())
+			helper._upload_parameters()
+		helper._pack(rows, helper.Y, self.n)
+		times = np.broadcast_to(np.asarray(time, dtype=float), (helper.B,)).copy()
+		helper.tt[:helper.B].copy_(torch.as_tensor(times))
+		out = torch.empty_like(helper.Y)
+		module.eval_f(helper.tt.data_ptr(), helper.Y.data_ptr(), helper.P.data_ptr(), out.data_ptr(), helper.B, helper.ld, helper.stream)
+		return helper._export(helper._unpack(out, self.n))
+
+	# ------------------------------------------------------------------ state, parameters, integration
+
+	@property
+	def t(self):
+		return self.integrator.t
+
+	@property
+	def _y(self):
+		return self.integrator._y
+
+	@property
+	def y(self):
+		return self.integrator._y
+
+	@property
+	def y_dict(self):
+		state = self.y
+		return {self.dynvar(i): state[..., i] for i in range(self.n)}
+
+	def _list_from_dynvar_dict(self, dictionary, name, n):
+		keys = {}
+		for key, value in dictionary.items():
+			key = sympy.sympify(key)
+			if not (getattr(key.func, "__name__", None) == "y" and len(key.args) == 1):
+				raise ValueError(f"The keys of the {name} dictionary must be y(0), y(1), …")
+			keys[int(key.args[0])] = value
+		if sorted(keys) != list(range(n)):
+			raise ValueError(f"The {name} dictionary must have exactly the keys y(0) … y({n-1}).")
+		return [keys[i] for i in range(n)]
+
+	def set_initial_value(self, initial_value, time=0.0):
+		"""One state (list / array of length n, or dictionary {y(i): value}) or an ensemble: (B, n) NumPy
+		array, torch tensor (CPU or CUDA).  The kind of the input decides the kind of what `integrate` returns."""
+		if isinstance(initial_value, dict):
+			initial_value = self._list_from_dynvar_dict(initial_value, "initial value", self.n)
+		shape = tuple(initial_value.shape) if hasattr(initial_value, "shape") else (len(initial_value),)
+		if shape[-1] != self.n or len(shape) > 2:
+			raise ValueError("The dimension of the initial value does not match the dimension of your differential equations.")
+		self.integrator.set_initial_value(initial_value, time)
+
+	def _parameter_rows(self):
+		"""(1 or B, p) array from whatever set_parameters got: scalars and/or one vector per parameter."""
+		if self.control_par_values is None:
+			raise RuntimeError("Something needs parameters to be set. Try calling `set_parameters` earlier.")
+		values = self.control_par_values
+		if isinstance(values, torch.Tensor) or (isinstance(values, np.ndarray) and values.ndim == 2):
+			return values
+		columns = [v if isinstance(v, torch.Tensor) else np.asarray(v, dtype=float) for v in values]
+		if all(np.ndim(c) == 0 for c in columns):
+			return np.array([[float(c) for c in columns]])
+		if any(isinstance(c, torch.Tensor) for c in columns):
+			B = max(c.shape[0] for c in columns if np.ndim(c))
+			columns = [torch.as_tensor(c, dtype=torch.float64).expand(B) if np.ndim(c) == 0 else c.to(torch.float64) for c in columns]
+			device = next(c.device for c in columns if c.is_cuda) if any(c.is_cuda for c in columns) else "cpu"
+			return torch.stack([c.to(device) for c in columns], dim=1)
+		B = max(c.shape[0] for c in columns if c.ndim)
+		return np.stack([np.broadcast_to(c, (B,)) for c in columns], axis=1)
+
+	def set_parameters(self, *args):
+		"""
+		As in the reference (_jitcode.py:638-655): the values as separate arguments or as one sequence.
+		Each value may be a number (shared by all trajectories) or a vector with one entry per trajectory;
+		a (B, p) array or tensor is taken as is.
+		"""
+		if len(args) == 1 and (isinstance(args[0], torch.Tensor) or isinstance(args[0], np.ndarray)) and np.ndim(args[0]) == 2:
+			values = args[0]
+			count = values.shape[1]
+		else:
+			try:
+				values = tuple(args[0])
+			except (TypeError, IndexError):
+				values = args
+			else:
+				if len(args) > 1:
+					raise TypeError("Argument must either be a single sequence or multiple numbers.")
+			count = len(values)
+		if count != len(self.control_pars):
+			raise ValueError("Number of values does not match number of control parameters.")
+		self.control_par_values = values
+		if isinstance(self.integrator, CudaEnsembleIntegrator):
+			self.integrator.set_parameters(self._parameter_rows())
+
+	def set_f_params(self, *args):
+		warn("This function has been replaced by `set_parameters`", stacklevel=2)
+		self.set_parameters(*args)
+
+	def set_jac_params(self, *args):
+		warn("This function has been replaced by `set_parameters`", stacklevel=2)
+		self.set_parameters(*args)
+
+	_post = JB_POST_NONE
+	_proj = None
+
+	def set_integrator(self, name, nsteps=10**6, interpolate=True, *, device=None, storage=None, threads=None, **integrator_params):
+		"""
+		As in the reference (_jitcode.py:560-626).
+
+		name : "dopri5" | "dop853" (Hairer's codes as scipy.integrate.ode runs them: every `integrate` call is a
+			fresh start that lands exactly on the target time) or "RK45" | "DOP853" (SciPy's solve_ivp stepper,
+			persistent between calls; with `interpolate` the sample is the dense output of the step that passed
+			the target time, without it the last step is clipped to the target time).
+		nsteps : limit of step attempts per `integrate` call for the `ode` names.
+		integrator_params : rtol, atol (scalar or one per component), max_step, first_step, and for the `ode`
+			names safety, ifactor, dfactor, beta — passed to the kernel with SciPy's defaults.
+		device / storage ("registers" | "global") / threads : where and how the kernel runs (engine-specific).
+		"""
+		if name in NOT_REBUILT:
+			raise NotImplementedError(f"The B200 engine only implements the explicit Dormand–Prince pairs (dopri5, dop853, RK45, DOP853), not {name!r}.")
+		if name not in INTEGRATORS:
+			raise RuntimeError("There is no integrator with that name.")
+		method, backend = INTEGRATORS[name]
+		if backend == "ode":
+			driver = _codegen.JB_DRV_ODE
+		else:
+			driver = _codegen.JB_DRV_IVP_DENSE if interpolate else _codegen.JB_DRV_IVP_LAND
+		if isinstance(storage, str):
+			storage = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL}[storage]
+		old_integrator = self.integrator
+		module = self._module(method, driver, storage, threads)   # compiling needs no GPU …
+		require_cuda(device)                                      # … running does
+		self._integrator_config = (method, driver, storage, threads)
+		self._f_module = module
+		integrator_params.pop("verbosity", None)
+		self.integrator = CudaEnsembleIntegrator(
+			module, device=device, nsteps=nsteps if backend == "ode" else 0,
+			post=self._post, proj=self._proj, **integrator_params,
+		)
+		if self.control_pars and self.control_par_values is not None:
+			self.integrator.set_parameters(self._parameter_rows())
+		# restore state and time, if applicable (_jitcode.py:619-626)
+		try:
+			old_y = old_integrator.y_device if isinstance(old_integrator, CudaEnsembleIntegrator) else old_integrator._y
+			old_t = old_integrator.t
+		except (AttributeError, RuntimeError):
+			pass
+		else:
+			if old_y is not None and len(old_y):
+				self.integrator.set_initial_value(old_y, old_t)
+				if isinstance(old_integrator, CudaEnsembleIntegrator):
+					self.integrator._out_kind, self.integrator._single = old_integrator._out_kind, old_integrator._single
+
+	def integrate(self, *args, **kwargs):
+		return self.integrator.integrate(*args, **kwargs)
+
+	def integrate_many(self, times):
+		"""`[integrate(T) for T in times]` in one kernel launch: (len(times), B, n)."""
+		if not isinstance(self.integrator, CudaEnsembleIntegrator):
+			raise RuntimeError("You must call set_integrator first.")
+		return self.integrator.integrate_many(times)
+
+	def successful(self):
+		raise NotImplementedError("JiTCODE doesn’t support ODE’s `successful`. Instead the exception `UnsuccessfulIntegration` is raised in case of an unsuccessful integration (its `indices` attribute names the failing trajectories).")
+
+	def step_counts(self):
+		"""(accepted, rejected) step attempts of the whole ensemble so far — the benchmark's trajectory-steps."""
+		return self.integrator.step_counts()
+
+
+def random_directions(B, n, generator=None, device="cpu"):
+	"""B isotropic unit vectors of dimension n (random_direction of jitcxde_common, _jitcode.py:729,873)."""
+	vectors = torch.randn((B, n), dtype=torch.float64, generator=generator, device=device)
+	return vectors / vectors.norm(dim=1, keepdim=True)
+
+
+class jitcode_lyap(jitcode):
+	"""
+	As `jitcode`, plus (_jitcode.py:671-779):
+
+	n_lyap : number of Lyapunov exponents; negative or larger than the dimension → all
+	simplify : simplify the tangent-vector equations with SymPy (default: off, see generate_f_cuda)
+
+	`integrate(t)` returns (state (B, n), local Lyapunov exponents (B, n_lyap), tangent vectors (B, n_lyap, n));
+	the tangent vectors are integrated alongside the state in the same kernel and re-orthonormalised on the
+	device after every call.  `seed` makes the random initial tangent vectors reproducible.
+	"""
+
+	_post = JB_POST_LYAP_QR
+
+	def __init__(self, f_sym=(), n_lyap=-1, simplify=None, seed=None, **kwargs):
+		n_basic = kwargs.pop("n", None)
+		f_basic, self.n_basic = handle_input(f_sym, n_basic)
+		self._n_lyap = n_lyap if 0 <= n_lyap <= self.n_basic else self.n_basic
+		if self._n_lyap > 10:
+			warn(f"You are about to calculate {self._n_lyap} Lyapunov exponents. This is very likely more than you need and may lead to severe difficulties with compilation and integration.", stacklevel=2)
+		helpers = sort_helpers(kwargs.pop("helpers", None))
+		full = lyapunov_system(f_basic, helpers, self.n_basic, self._n_lyap)
+		if simplify:
+			full = full[:self.n_basic] + [entry.simplify(ratio=1.0) for entry in full[self.n_basic:]]
+		super().__init__(full, helpers=helpers, n=self.n_basic*(self._n_lyap+1), **kwargs)
+		self._n_basic_module = self.n_basic
+		self._n_lyap_module = self._n_lyap
+		self._generator = None if seed is None else torch.Generator().manual_seed(seed)
+
+	def _with_tangent_vectors(self, state):
+		if isinstance(state, dict):
+			state = self._list_from_dynvar_dict(state, "initial value", self.n_basic)
+		is_tensor = isinstance(state, torch.Tensor)
+		rows = state if is_tensor else torch.as_tensor(np.ascontiguousarray(state, dtype=float))
+		single = rows.dim() == 1
+		rows2 = rows.reshape(1, -1) if single else rows
+		if rows2.shape[1] != self.n_basic:
+			raise ValueError("The dimension of the initial value does not match the dimension of your differential equations.")
+		B = rows2.shape[0]
+		tangents = torch.cat([random_directions(B, self.n_basic, self._generator) for _ in range(self._n_lyap)], dim=1)
+		full = torch.cat([rows2.to(torch.float64), tangents.to(rows2.device)], dim=1)
+		if single:
+			full = full[0]
+		return full if is_tensor else full.numpy()
+
+	def set_initial_value(self, y, time=0.0):
+		super().set_initial_value(self._with_tangent_vectors(y), time)
+
+	def set_integrator(self, name, interpolate=None, **kwargs):
+		"""
+		As for `jitcode`.  The reference passes `interpolate` on positionally into the `nsteps` slot
+		(_jitcode.py:741 vs :560), so that in effect the `ode` names run with SciPy's default step limit and the
+		solve_ivp names always interpolate; that effective behaviour is kept (SURVEY.md §7 "reference quirks").
+		"""
+		kwargs.setdefault("nsteps", 0)
+		super().set_integrator(name, interpolate=True, **kwargs)
+
+	def _split(self, state):
+		n, k = self.n_basic, self._n_lyap
+		tangents = state[..., n:].reshape(*state.shape[:-1], k, n)
+		return state[..., :n], tangents
+
+	def integrate(self, *args, **kwargs):
+		integrator = self.integrator
+		state = integrator.integrate(*args, **kwargs)
+		lyaps = integrator._export(integrator.last_lyaps)
+		basic, tangents = self._split(state)
+		return basic, lyaps, tangents
+
+	def integrate_many(self, times, discard=0):
+		"""All calls of `integrate` for `times` in one launch: returns (states (T, B, n), local exponents
+		(T, B, n_lyap)); running sums of the exponents from sample `discard` on are kept on the device
+		(`lyapunov_statistics`)."""
+		integrator = self.integrator
+		integrator.lyap_discard = discard
+		states = integrator.integrate_many(times)
+		lyaps = integrator.last_lyaps
+		if integrator._single:
+			lyaps = lyaps[:, 0]
+		if integrator._out_kind != "cuda":
+			lyaps = lyaps.cpu() if integrator._out_kind == "torch" else lyaps.cpu().numpy()
+		return states[..., :self.n_basic], lyaps
+
+	@property
+	def y_dict(self):
+		state = self.y
+		return {self.dynvar(i): state[..., i] for i in range(self.n_basic)}
+
+
+class jitcode_restricted_lyap(jitcode_lyap):
+	"""
+	Largest Lyapunov exponent orthogonal to a given plane (_jitcode.py:922-946).
+
+	vectors : basis of the plane whose projection is removed from the tangent vector after every call
+	"""
+
+	_post = JB_POST_LYAP_RESTRICTED
+
+	def __init__(self, f_sym=(), vectors=(), **kwargs):
+		kwargs["n_lyap"] = 1
+		super().__init__(f_sym, **kwargs)
+		self.vectors = [np.asarray(vector, dtype=float)/np.linalg.norm(vector) for vector in vectors]
+		self._proj = np.array(self.vectors, dtype=float).reshape(len(self.vectors), self.n_basic) if self.vectors else None
+
+
+class jitcode_transversal_lyap(jitcode, GroupHandler):
+	"""
+	Largest Lyapunov exponent transversal to a synchronisation manifold (_jitcode.py:782-919): the system is
+	transformed to one representative per group of synchronised variables plus difference coordinates of the
+	tangent vector, which shrinks it considerably.
+
+	groups : iterable of iterables of indices of variables that are identical on the manifold
+	simplify : simplify the transformed equations with SymPy (default: off)
+	average_dynamics : average the dynamics over each group instead of taking its first member
+
+	`integrate(t)` returns (one value per group (B, n_groups), local exponent (B,)).
+	"""
+
+	_post = JB_POST_LYAP_TRANSVERSAL
+
+	def __init__(self, f_sym=(), groups=(), simplify=None, average_dynamics=False, seed=None, **kwargs):
+		GroupHandler.__init__(self, groups)
+		n = kwargs.pop("n", None)
+		f_list, n = handle_input(f_sym, n)
+		if n != self.n_members:
+			raise ValueError("Every dynamical variable must belong to exactly one group.")
+		helpers = sort_helpers(kwargs.pop("helpers", None))
+		z = sympy.Function("z")
+		tangent_vector = self.back_transform([z(i) for i in range(n)])
+		tangent_f = [
+			sympy.Add(*[entry * tangent_vector[k] for k, entry in enumerate(row) if entry != 0])
+			for row in jacobian_rows(f_list, helpers, n)
+		]
+		to_main = {y(i): z(self.map_to_main(i)) for i in range(n)}
+
+		def finalise(entry):
+			entry = sympy.sympify(entry).xreplace(to_main)
+			if simplify:
+				entry = entry.simplify(ratio=1.0)
+			return entry.replace(z, y)
+
+		f_lyap = []
+		for entry in self.iterate(tangent_f):
+			if isinstance(entry, int):
+				group = self.groups[entry]
+				if average_dynamics:
+					f_lyap.append(sympy.Add(*[finalise(f_list[i]) for i in group]) / len(group))
+				else:
+					f_lyap.append(finalise(f_list[group[0]]))
+			else:
+				f_lyap.append(finalise(entry[0] - entry[1]))
+		helpers = [(symbol, finalise(definition)) for symbol, definition in helpers]
+		jitcode.__init__(self, f_lyap, helpers=helpers, n=n, **kwargs)
+		self._n_basic_module = n
+		self._n_lyap_module = 1
+		self._tangent_indices_module = list(self.tangent_indices)
+		self._generator = None if seed is None else torch.Generator().manual_seed(seed)
+
+	def set_initial_value(self, y, time=0.0):
+		if isinstance(y, dict):
+			raise NotImplementedError("Dictionary input is not supported for transversal Lyapunov exponents")
+		is_tensor = isinstance(y, torch.Tensor)
+		rows = y if is_tensor else torch.as_tensor(np.ascontiguousarray(y, dtype=float))
+		single = rows.dim() == 1
+		rows2 = (rows.reshape(1, -1) if single else rows).to(torch.float64)
+		if rows2.shape[1] != len(self.groups):
+			raise ValueError("Provide exactly one value per synchronisation group.")
+		B = rows2.shape[0]
+		full = torch.empty((B, self.n), dtype=torch.float64, device=rows2.device)
+		full[:, self.main_indices] = rows2
+		full[:, self.tangent_indices] = random_directions(B, len(self.tangent_indices), self._generator).to(rows2.device)
+		if single:
+			full = full[0]
+		super().set_initial_value(full if is_tensor else full.numpy(), time)
+
+	def set_integrator(self, name, interpolate=False, **kwargs):
+		"""As for `jitcode`; like the reference (_jitcode.py:884) the positional hand-over makes the `ode` names
+		use SciPy's default step limit and the solve_ivp names interpolate."""
+		kwargs.setdefault("nsteps", 0)
+		super().set_integrator(name, interpolate=True, **kwargs)
+
+	def integrate(self, *args, **kwargs):
+		integrator = self.integrator
+		state = integrator.integrate(*args, **kwargs)
+		lyap = integrator._export(integrator.last_lyaps)[..., 0]
+		return state[..., self.main_indices], lyap
+
+	@property
+	def y_dict(self):
+		raise NotImplementedError("Dictionary output is not supported for transversal Lyapunov exponents")
+
+
+def test(omp=True, sympy=True):
+	"""Quick sanity check of the installation (reference :948-965): generate, compile with nvcc, load, and —
+	on a machine with a GPU — integrate a harmonic oscillator."""
+	ODE = jitcode([y(1), -y(0)], verbose=False)
+	ODE.generate_f_cuda(chunk_size=1)
+	ODE.compile_cuda()
+	ODE.set_integrator("dopri5")
+	ODE.set_initial_value([1, 2])
+	ODE.integrate(0.1)

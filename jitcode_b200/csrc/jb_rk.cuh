@@ -1,0 +1,701 @@
+// Ensemble adaptive Runge–Kutta kernels, one thread per trajectory.
+//
+// What is computed follows the reference's integrators exactly:
+//   JB_DRV_ODE        Hairer's DOPRI5 / DOP853 core (HINIT + DOPCOR / DP86CO) as scipy.integrate.ode
+//                     configures it (scipy _ode.py:1112-1236) and as ODE_wrapper.integrate drives it
+//                     (integrator_tools.py:134-144): fresh start per sample time, lands exactly on it.
+//   JB_DRV_IVP_DENSE  scipy solve_ivp's RungeKutta._step_impl (scipy _ivp/rk.py:111-176) with
+//                     select_initial_step (common.py:68-134), driven like IVP_wrapper.integrate
+//                     (integrator_tools.py:98-105): persistent stepper, t_bound = ∞, dense output.
+//   JB_DRV_IVP_LAND   same stepper driven like IVP_wrapper_no_interpolation (:110-128).
+// followed, per sample time, by the optional Lyapunov post-step of _jitcode.py:743-775 / :886-893 /
+// :937-946.  oracle/rk_numpy.py is the line-by-line CPU statement of the same arithmetic.
+//
+// How it is computed is B200-first: the generated right-hand side (Sys::rhs) is fused into the
+// stepper; a trajectory never leaves its thread between the first and the last sample time of a
+// launch; memory is laid out in trajectory-minor tiles of 32 (one tile = one warp), so that every
+// global access of a warp is one contiguous 256-byte segment at a compile-time offset from a
+// per-thread base pointer (no address arithmetic in the generated code).
+//   REG  = true : y and all stages live in registers for the whole launch (small systems, FP64-pipe bound);
+//   REG  = false: they live in a caller-provided workspace (large systems, HBM/L2 bound); buffers are
+//                 rotated by pointer instead of copied.
+#pragma once
+
+#include <cstdint>
+#include <cmath>
+#include <type_traits>
+#include "jb_tableaux.cuh"
+#include "jitcode_b200.h"
+
+namespace jb {
+
+constexpr int TILE = JB_TILE;
+
+// ---------------------------------------------------------------------------------------------
+// vectors: the generated code reads `y(i)` and writes `dy.set(i, v)`
+
+template <int N>
+struct RVec {               // thread-private, scalarised into registers
+	double v[N > 0 ? N : 1];
+	__device__ __forceinline__ double operator()(int i) const { return v[i]; }
+	__device__ __forceinline__ void set(int i, double x) { v[i] = x; }
+};
+
+struct GVec {               // one trajectory's column of a tile: element i at p[i*TILE]
+	double *p;
+	__device__ __forceinline__ double operator()(int i) const { return p[i * TILE]; }
+	__device__ __forceinline__ void set(int i, double x) const { p[i * TILE] = x; }
+};
+
+// dst takes the value of src; src becomes scratch (registers: copy; global: pointer swap)
+template <int N>
+__device__ __forceinline__ void take(RVec<N> &dst, RVec<N> &src)
+{
+#pragma unroll
+	for (int i = 0; i < N; ++i) dst.v[i] = src.v[i];
+}
+__device__ __forceinline__ void take(GVec &dst, GVec &src)
+{
+	double *const p = dst.p;
+	dst.p = src.p;
+	src.p = p;
+}
+
+// position of trajectory b in a tiled array of `rows` rows
+__device__ __forceinline__ int64_t tile_offset(int64_t b, int rows)
+{
+	return (b / TILE) * ((int64_t) rows * TILE) + (b % TILE);
+}
+
+// ---------------------------------------------------------------------------------------------
+
+template <class Tab> struct Coef;
+template <> struct Coef<DP5> {
+	static __host__ __device__ constexpr double a(int s, int j) { return DP5::A[s][j]; }
+	static __host__ __device__ constexpr double c(int s) { return DP5::C[s]; }
+};
+template <> struct Coef<DOP853> {
+	static __host__ __device__ constexpr double a(int s, int j) { return dop853::A[s][j]; }
+	static __host__ __device__ constexpr double c(int s) { return dop853::C[s]; }
+};
+
+struct Params {             // kernel argument block (by value)
+	int64_t B, ld;
+	int32_t n_times, post, n_proj, lyap_discard, hairer_reject_by_dfactor;
+	const double *times;
+	double rtol, atol;
+	const double *atol_vec;
+	double max_step, first_step;
+	int64_t nsteps;
+	double safety, facc1, facc2, beta, expo1;
+	double *t, *Y;
+	const double *P;
+	double *state, *sstate, *work, *Yres, *Yrec, *lyap_rec, *lyap_acc;
+	const double *proj;
+	int32_t *status;
+	int64_t *n_accepted, *n_rejected;
+};
+
+// persistent scalars of the IVP drivers, sstate[k*ld + b]
+enum { SS_H_ABS = 0, SS_T_OLD = 1, SS_H_PREV = 2, SS_FLAGS = 3, SS_COUNT = 4 };
+enum { FLAG_INITIALISED = 1, FLAG_INTERPOLANT = 2 };
+// persistent vectors of the IVP drivers (tiled, n rows each): f(t,y), y_old, interpolant
+enum { SV_F = 0, SV_YOLD = 1, SV_DENSE0 = 2 };
+
+template <class Tab, int DRIVER> struct Layout {
+	static constexpr bool DENSE = DRIVER == JB_DRV_IVP_DENSE;
+	static constexpr bool IVP = DRIVER != JB_DRV_ODE;
+	static constexpr int KR = DENSE ? Tab::KROWS_DENSE : Tab::KROWS;
+	static constexpr int STATE_VECTORS = DENSE ? 2 + Tab::NDENSE : (IVP ? 1 : 0);
+	static constexpr int STATE_SCALARS = IVP ? SS_COUNT : 0;
+	static constexpr int WORK_VECTORS = 1 + KR + (DENSE ? 1 : 0);   // Z, K rows, y_old
+};
+
+template <class Sys, bool REG> struct RhsCall;
+
+// registers: the right-hand side is inlined at every call site
+template <class Sys> struct RhsCall<Sys, true> {
+	template <class VI, class VO>
+	static __device__ __forceinline__ void call(double t, const VI &in, VO &out, const typename Sys::Par &par)
+	{
+		Sys::rhs(t, in, out, par);
+	}
+};
+// global: one out-of-line copy of the (large) right-hand side
+template <class Sys>
+__device__ __noinline__ void rhs_outlined(double t, const double *__restrict__ in, double *__restrict__ out,
+		const typename Sys::Par par)
+{
+	const GVec vi{const_cast<double *>(in)};
+	GVec vo{out};
+	Sys::rhs(t, vi, vo, par);
+}
+template <class Sys> struct RhsCall<Sys, false> {
+	static __device__ __forceinline__ void call(double t, const GVec &in, GVec &out, const typename Sys::Par &par)
+	{
+		rhs_outlined<Sys>(t, in.p, out.p, par);
+	}
+};
+
+template <class Sys, class Tab, int DRIVER, bool REG>
+struct Stepper {
+	static constexpr int N = Sys::N;
+	using L = Layout<Tab, DRIVER>;
+	static constexpr bool DENSE = L::DENSE;
+	static constexpr bool IVP = L::IVP;
+	static constexpr int KR = L::KR;
+	static constexpr int S = Tab::NSTAGE;
+	static constexpr int UNR = REG ? (N > 0 ? N : 1) : 4;   // unroll factor of component loops
+	using Vec = typename std::conditional<REG, RVec<N>, GVec>::type;
+
+	Vec Y, Z, YO, K[KR];
+	typename Sys::Par par;
+	double atol_s, rtol;
+	const double *atol_vec;
+
+	__device__ __forceinline__ double atol(int i) const { return atol_vec ? atol_vec[i] : atol_s; }
+
+	__device__ __forceinline__ void rhs(double t, const Vec &in, Vec &out)
+	{
+		RhsCall<Sys, REG>::call(t, in, out, par);
+	}
+
+	// dst = Y + h * Σ_{j<ROW} a(ROW,j) K[j]   (stage input for ROW < S, solution for ROW == S)
+	template <int ROW>
+	__device__ __forceinline__ void combine(Vec &dst, double h)
+	{
+#pragma unroll UNR
+		for (int i = 0; i < N; ++i) {
+			double acc = 0.0;
+			static_for<0, ROW>([&](auto j) {
+				constexpr double a = Coef<Tab>::a(ROW, j);
+				if constexpr (a != 0.0) acc = fma(a, K[j](i), acc);
+			});
+			dst.set(i, fma(h, acc, Y(i)));
+		}
+	}
+
+	// one step attempt from (t, Y, K[0]) with step h: fills K[1..], Z = y_new; returns the error norm
+	__device__ __forceinline__ double attempt(double t, double h)
+	{
+		static_for<1, S>([&](auto s) {
+			combine<s>(Z, h);
+			constexpr double cs = Coef<Tab>::c(s);
+			rhs(fma(cs, h, t), Z, K[s]);
+		});
+		combine<S>(Z, h);
+		if constexpr (Tab::ERR_NEEDS_FSAL) {
+			rhs(t + h, Z, K[S]);
+			double sum = 0.0;
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) {
+				double e = 0.0;
+				static_for<0, Tab::KROWS>([&](auto j) {
+					constexpr double w = DP5::E[j];
+					if constexpr (w != 0.0) e = fma(w, K[j](i), e);
+				});
+				const double sk = fma(rtol, fmax(fabs(Y(i)), fabs(Z(i))), atol(i));
+				const double q = h * e / sk;
+				sum = fma(q, q, sum);
+			}
+			return sqrt(sum / N);
+		} else {
+			double s5 = 0.0, s3 = 0.0;
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) {
+				double e5 = 0.0, e3 = 0.0;
+				static_for<0, S>([&](auto j) {
+					constexpr double w5 = dop853::E5[j];
+					constexpr double w3 = dop853::E3[j];
+					if constexpr (w5 != 0.0) e5 = fma(w5, K[j](i), e5);
+					if constexpr (w3 != 0.0) e3 = fma(w3, K[j](i), e3);
+				});
+				const double sk = fma(rtol, fmax(fabs(Y(i)), fabs(Z(i))), atol(i));
+				e5 /= sk;
+				e3 /= sk;
+				s5 = fma(e5, e5, s5);
+				s3 = fma(e3, e3, s3);
+			}
+			if (s5 == 0.0 && s3 == 0.0) return 0.0;
+			double deno = fma(0.01, s3, s5);
+			if (deno <= 0.0) deno = 1.0;
+			return fabs(h) * s5 * sqrt(1.0 / (deno * N));
+		}
+	}
+
+	// the 8th-order pair evaluates f(t+h, y_new) only once the step is accepted
+	__device__ __forceinline__ void finish_accepted(double t, double h)
+	{
+		if constexpr (!Tab::ERR_NEEDS_FSAL) rhs(t + h, Z, K[S]);
+	}
+
+	// Σ_i (v_i / (atol_i + rtol |Y_i|))², the weighted norms of both start-up rules
+	template <class F>
+	__device__ __forceinline__ double weighted_sq(F &&value)
+	{
+		double sum = 0.0;
+#pragma unroll UNR
+		for (int i = 0; i < N; ++i) {
+			const double q = value(i) / fma(rtol, fabs(Y(i)), atol(i));
+			sum = fma(q, q, sum);
+		}
+		return sum;
+	}
+
+	__device__ __forceinline__ void euler_probe(const Vec &f0, double h)
+	{
+#pragma unroll UNR
+		for (int i = 0; i < N; ++i) Z.set(i, fma(h, f0(i), Y(i)));
+	}
+};
+
+__device__ __forceinline__ double ulp_above(double t)
+{
+	return fabs(::nextafter(t, (double) INFINITY) - t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lyapunov post-steps on the state of one trajectory (component access through get/set lambdas)
+
+// jitcode_lyap.norms (_jitcode.py:743-749): Gram–Schmidt of the n_lyap tangent blocks;
+// norms_k = |R_kk| of the QR decomposition that orthonormalise_qr computes.
+// U = unroll factor (full for register vectors, whose indices must be compile-time constants).
+template <int NB, int NL, bool REG, class Vec>
+__device__ __forceinline__ void lyap_orthonormalise(Vec &Y, double *norms)
+{
+	constexpr int UK = REG ? (NL > 0 ? NL : 1) : 1;
+	constexpr int UI = REG ? (NB > 0 ? NB : 1) : 4;
+#pragma unroll UK
+	for (int k = 0; k < NL; ++k) {
+		const int ok = NB * (1 + k);
+#pragma unroll UK
+		for (int j = 0; j < k; ++j) {
+			const int oj = NB * (1 + j);
+			double dot = 0.0;
+#pragma unroll UI
+			for (int i = 0; i < NB; ++i) dot = fma(Y(oj + i), Y(ok + i), dot);
+#pragma unroll UI
+			for (int i = 0; i < NB; ++i) Y.set(ok + i, fma(-dot, Y(oj + i), Y(ok + i)));
+		}
+		double sq = 0.0;
+#pragma unroll UI
+		for (int i = 0; i < NB; ++i) sq = fma(Y(ok + i), Y(ok + i), sq);
+		const double norm = sqrt(sq);
+		norms[k] = norm;
+		const double inv = 1.0 / norm;
+#pragma unroll UI
+		for (int i = 0; i < NB; ++i) Y.set(ok + i, Y(ok + i) * inv);
+	}
+}
+
+// jitcode_restricted_lyap.norms (_jitcode.py:937-946): remove the projections onto the given
+// (orthonormalised) vectors from the single tangent vector, then normalise.
+template <int NB, bool REG, class Vec>
+__device__ __forceinline__ double lyap_restricted(Vec &Y, const double *proj, int n_proj)
+{
+	constexpr int UI = REG ? (NB > 0 ? NB : 1) : 4;
+	for (int v = 0; v < n_proj; ++v) {
+		const double *vec = proj + (int64_t) v * NB;
+		double dot = 0.0;
+#pragma unroll UI
+		for (int i = 0; i < NB; ++i) dot = fma(vec[i], Y(NB + i), dot);
+#pragma unroll UI
+		for (int i = 0; i < NB; ++i) Y.set(NB + i, fma(-dot, vec[i], Y(NB + i)));
+	}
+	double sq = 0.0;
+#pragma unroll UI
+	for (int i = 0; i < NB; ++i) sq = fma(Y(NB + i), Y(NB + i), sq);
+	const double norm = sqrt(sq);
+	const double inv = 1.0 / norm;
+#pragma unroll UI
+	for (int i = 0; i < NB; ++i) Y.set(NB + i, Y(NB + i) * inv);
+	return norm;
+}
+
+// jitcode_transversal_lyap.norm (_jitcode.py:886-893): norm over the tangent (difference) coordinates
+template <class Sys, bool REG, class Vec>
+__device__ __forceinline__ double lyap_transversal(Vec &Y)
+{
+	constexpr int UT = REG ? (Sys::NT > 0 ? Sys::NT : 1) : 4;
+	double sq = 0.0;
+#pragma unroll UT
+	for (int k = 0; k < Sys::NT; ++k) {
+		const double v = Y(Sys::tangent_index(k));
+		sq = fma(v, v, sq);
+	}
+	const double norm = sqrt(sq);
+	const double inv = 1.0 / norm;
+#pragma unroll UT
+	for (int k = 0; k < Sys::NT; ++k) Y.set(Sys::tangent_index(k), Y(Sys::tangent_index(k)) * inv);
+	return norm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Everything one trajectory does during one launch.
+
+template <class Sys, class Tab, int DRIVER, bool REG>
+__device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
+{
+	using ST = Stepper<Sys, Tab, DRIVER, REG>;
+	using L = Layout<Tab, DRIVER>;
+	constexpr int N = Sys::N;
+	constexpr int S = Tab::NSTAGE;
+	constexpr bool DENSE = ST::DENSE;
+	constexpr bool IVP = ST::IVP;
+	constexpr int UNR = ST::UNR;
+	constexpr int NLY = Sys::NL > 0 ? Sys::NL : 1;
+	const int64_t ld = a.ld;
+	const int64_t vec = (int64_t) N * ld;              // one tiled vector
+	const int64_t off = tile_offset(b, N);             // this trajectory inside a tiled vector
+
+	ST st;
+	st.rtol = a.rtol;
+	st.atol_s = a.atol;
+	st.atol_vec = a.atol_vec;
+#pragma unroll
+	for (int k = 0; k < Sys::NP; ++k) st.par.v[k] = a.P[tile_offset(b, Sys::NP) + k * TILE];
+
+	int status = a.status[b];
+	double t = a.t[b];
+	int64_t n_acc = 0, n_rej = 0;
+
+	// ---- canonical (caller-visible) locations
+	const GVec Yc{a.Y + off};
+	const GVec Fc{IVP ? a.state + SV_F * vec + off : nullptr};
+	const GVec Oc{DENSE ? a.state + SV_YOLD * vec + off : nullptr};
+	auto Qc = [&](int p) { return GVec{a.state + (SV_DENSE0 + p) * vec + off}; };
+
+	// ---- bind working storage
+	if constexpr (REG) {
+#pragma unroll
+		for (int i = 0; i < N; ++i) st.Y.v[i] = Yc(i);
+	} else {
+		st.Y.p = Yc.p;
+		st.Z.p = a.work + off;
+#pragma unroll
+		for (int j = 0; j < ST::KR; ++j) st.K[j].p = a.work + (int64_t) (1 + j) * vec + off;
+		if constexpr (DENSE) st.YO.p = a.work + (int64_t) (1 + ST::KR) * vec + off;
+	}
+
+	double h_abs = 0.0, t_old = NAN, h_prev = 0.0;
+	bool initialised = false;   // IVP: the persistent stepper exists (f(t,y) and h_abs are valid)
+	bool interpolant = false;   // DENSE: the interpolant of the last step is in the canonical state
+	bool have_f = false;        // IVP: K[0] holds f(t, Y) for the step to come
+	bool pending_f = false;     // IVP: K[S] holds f(t, Y) (fresh from an accepted step), K[0..S] are its stages
+	if constexpr (IVP) {
+		h_abs = a.sstate[SS_H_ABS * ld + b];
+		t_old = a.sstate[SS_T_OLD * ld + b];
+		h_prev = a.sstate[SS_H_PREV * ld + b];
+		const int flags = (int) a.sstate[SS_FLAGS * ld + b];
+		initialised = flags & FLAG_INITIALISED;
+		interpolant = flags & FLAG_INTERPOLANT;
+	}
+
+	double lyap_sum[NLY], lyap_sq[NLY];
+#pragma unroll
+	for (int k = 0; k < NLY; ++k) lyap_sum[k] = lyap_sq[k] = 0.0;
+
+	for (int it = 0; it < a.n_times; ++it) {
+		const double T = a.times[it];
+		const double t_start = t;        // solver time before this sample (Δt of the Lyapunov step for ODE/LAND)
+		if (status != JB_OK) continue;
+
+		if constexpr (DRIVER == JB_DRV_ODE) {
+			// ================= Hairer DOPRI5 / DOP853, fresh start (dopri5.f DOPCOR, dop853.f DP86CO)
+			if (T > t) {
+				st.rhs(t, st.Y, st.K[0]);
+				const double hmax = a.max_step > 0.0 ? a.max_step : fabs(T - t);
+				double h;
+				if (a.first_step > 0.0) {
+					h = a.first_step;
+				} else {
+					// HINIT
+					const double dnf = st.weighted_sq([&](int i) { return st.K[0](i); });
+					const double dny = st.weighted_sq([&](int i) { return st.Y(i); });
+					h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+					h = fmin(h, hmax);
+					st.euler_probe(st.K[0], h);
+					st.rhs(t + h, st.Z, st.K[1]);
+					const double der2 = sqrt(st.weighted_sq([&](int i) { return st.K[1](i) - st.K[0](i); })) / h;
+					const double der12 = fmax(fabs(der2), sqrt(dnf));
+					const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h) * 1e-3)
+							: pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
+					h = fmin(fmin(100.0 * fabs(h), h1), hmax);
+				}
+				double facold = 1e-4;
+				bool reject = false, last = false;
+				int64_t nstep = 0;
+				const int64_t nmax = a.nsteps > 0 ? a.nsteps : 100000;
+				while (true) {
+					if (nstep > nmax) { status = JB_TOO_MANY_STEPS; break; }
+					if (0.1 * fabs(h) <= fabs(t) * 2.3e-16) { status = JB_STEP_TOO_SMALL; break; }
+					if (!(h == h)) { status = JB_NONFINITE; break; }
+					if (t + 1.01 * h - T > 0.0) { h = T - t; last = true; }
+					++nstep;
+					const double err = st.attempt(t, h);
+					const double fac11 = pow(err, a.expo1);
+					double fac = a.beta > 0.0 ? fac11 / pow(facold, a.beta) : fac11;
+					fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
+					double hnew = h / fac;
+					if (err <= 1.0) {
+						facold = fmax(err, 1e-4);
+						++n_acc;
+						st.finish_accepted(t, h);
+						take(st.Y, st.Z);
+						take(st.K[0], st.K[S]);
+						t = last ? T : t + h;
+						if (fabs(hnew) > hmax) hnew = hmax;
+						if (reject) hnew = fmin(fabs(hnew), fabs(h));
+						reject = false;
+						if (last) break;
+					} else {
+						if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
+							hnew = h / fmin(a.facc1, fac11 / a.safety);
+						else
+							hnew = h / a.facc1;
+						reject = true;
+						last = false;
+						++n_rej;
+					}
+					h = hnew;
+				}
+			}
+		} else {
+			// ================= scipy solve_ivp stepper (rk.py RungeKutta), persistent between launches
+			if (!initialised) {
+				// RungeKutta.__init__: f = fun(t, y); select_initial_step with t_bound = ∞
+				st.rhs(t, st.Y, st.K[0]);
+				if (a.first_step > 0.0) {
+					h_abs = a.first_step;
+				} else {
+					const double d0 = sqrt(st.weighted_sq([&](int i) { return st.Y(i); }) / N);
+					const double d1 = sqrt(st.weighted_sq([&](int i) { return st.K[0](i); }) / N);
+					const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+					st.euler_probe(st.K[0], h0);
+					st.rhs(t + h0, st.Z, st.K[1]);
+					const double d2 = sqrt(st.weighted_sq([&](int i) { return st.K[1](i) - st.K[0](i); }) / N) / h0;
+					const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3)
+							: pow(0.01 / fmax(d1, d2), 1.0 / (Tab::ERR_ORDER + 1));
+					h_abs = fmin(fmin(100.0 * h0, h1), a.max_step > 0.0 ? a.max_step : INFINITY);
+				}
+				t_old = NAN;
+				initialised = true;
+				interpolant = false;
+				have_f = true;
+				pending_f = false;
+			}
+			const double max_step = a.max_step > 0.0 ? a.max_step : INFINITY;
+			const double t_bound = DENSE ? INFINITY : T;
+			while (status == JB_OK && (t < T || (DENSE && !(t_old == t_old)))) {
+				// ---- begin a step: K[0] = f(t, Y)
+				if (pending_f) {
+					take(st.K[0], st.K[S]);
+					pending_f = false;
+				} else if (!have_f) {
+#pragma unroll UNR
+					for (int i = 0; i < N; ++i) st.K[0].set(i, Fc(i));
+				}
+				have_f = true;
+				// ---- RungeKutta._step_impl
+				const double min_step = 10.0 * ulp_above(t);
+				if (h_abs > max_step) h_abs = max_step;
+				else if (h_abs < min_step) h_abs = min_step;
+				bool rejected = false;
+				while (true) {
+					if (h_abs < min_step || !(h_abs == h_abs)) { status = JB_STEP_TOO_SMALL; break; }
+					double t_new = t + h_abs;
+					if (t_new - t_bound > 0.0) t_new = t_bound;
+					const double h = t_new - t;
+					h_abs = fabs(h);
+					const double err = st.attempt(t, h);
+					if (err < 1.0) {
+						double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(err, -1.0 / (Tab::ERR_ORDER + 1)));
+						if (rejected) factor = fmin(1.0, factor);
+						h_abs *= factor;
+						++n_acc;
+						st.finish_accepted(t, h);
+						if constexpr (DENSE) take(st.YO, st.Y);
+						take(st.Y, st.Z);
+						t_old = t;
+						h_prev = h;
+						t = t_new;
+						pending_f = true;
+						interpolant = false;
+						break;
+					}
+					h_abs *= fmax(0.2, 0.9 * pow(err, -1.0 / (Tab::ERR_ORDER + 1)));
+					rejected = true;
+					++n_rej;
+				}
+			}
+		}
+
+		// ================= the sample at T
+		if (status != JB_OK) continue;
+		double *const rec = a.Yrec ? a.Yrec + (int64_t) it * vec + off : nullptr;
+		double dt_lyap = T - t_start;
+		if constexpr (DENSE) {
+			if (!interpolant) {
+				// ---- materialise the interpolant of the last step (rk.py:178-180, 693-712)
+				if constexpr (std::is_same<Tab, DP5>::value) {
+#pragma unroll UNR
+					for (int i = 0; i < N; ++i) {
+						static_for<0, 4>([&](auto p) {
+							double q = 0.0;
+							static_for<0, 7>([&](auto j) {
+								constexpr double w = DP5::P[j][p];
+								if constexpr (w != 0.0) q = fma(w, st.K[j](i), q);
+							});
+							Qc(p).set(i, q);
+						});
+						Oc.set(i, st.YO(i));
+					}
+				} else {
+					// three extra stages from (t_old, y_old), then F[0..6]
+					static_for<S + 1, S + 4>([&](auto s) {
+#pragma unroll UNR
+						for (int i = 0; i < N; ++i) {
+							double acc = 0.0;
+							static_for<0, s>([&](auto j) {
+								constexpr double c = dop853::A[s][j];
+								if constexpr (c != 0.0) acc = fma(c, st.K[j](i), acc);
+							});
+							st.Z.set(i, fma(h_prev, acc, st.YO(i)));
+						}
+						constexpr double cs = Coef<DOP853>::c(s);
+						st.rhs(fma(cs, h_prev, t_old), st.Z, st.K[s]);
+					});
+#pragma unroll UNR
+					for (int i = 0; i < N; ++i) {
+						const double delta = st.Y(i) - st.YO(i);
+						const double f_old = st.K[0](i), f_new = st.K[S](i);
+						Qc(0).set(i, delta);
+						Qc(1).set(i, h_prev * f_old - delta);
+						Qc(2).set(i, 2.0 * delta - h_prev * (f_new + f_old));
+						static_for<0, 4>([&](auto r) {
+							double q = 0.0;
+							static_for<0, 16>([&](auto j) {
+								constexpr double w = dop853::D[r][j];
+								if constexpr (w != 0.0) q = fma(w, st.K[j](i), q);
+							});
+							Qc(3 + r).set(i, h_prev * q);
+						});
+						Oc.set(i, st.YO(i));
+					}
+				}
+				interpolant = true;
+			}
+			// ---- evaluate it at T (rk.py:723-737, 747-764)
+			const double hh = t - t_old;
+			const double x = (T - t_old) / hh;
+			const bool restart = a.post != JB_POST_NONE;
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) {
+				double r;
+				if constexpr (std::is_same<Tab, DP5>::value) {
+					r = Qc(3)(i);
+					r = fma(r, x, Qc(2)(i));
+					r = fma(r, x, Qc(1)(i));
+					r = fma(r, x, Qc(0)(i));
+					r = fma(hh * x, r, Oc(i));
+				} else {
+					r = 0.0;
+					static_for<0, 7>([&](auto k) {
+						r += Qc(6 - k)(i);
+						r *= (k % 2 == 0) ? x : 1.0 - x;
+					});
+					r += Oc(i);
+				}
+				if (restart) st.Z.set(i, r);
+				else {
+					a.Yres[off + (int64_t) i * TILE] = r;
+					if (rec) rec[i * TILE] = r;
+				}
+			}
+			if (restart) {
+				// jitcode_lyap.integrate re-creates the stepper at (T, sample) (_jitcode.py:773)
+				take(st.Y, st.Z);
+				t = T;
+				initialised = false;
+				interpolant = false;
+				pending_f = have_f = false;
+			}
+		}
+
+		if (a.post != JB_POST_NONE) {
+			double norms[NLY];
+			if constexpr (Sys::NL > 0) {
+				if (a.post == JB_POST_LYAP_QR)
+					lyap_orthonormalise<Sys::NB, Sys::NL, REG>(st.Y, norms);
+				else if (a.post == JB_POST_LYAP_RESTRICTED)
+					norms[0] = lyap_restricted<Sys::NB, REG>(st.Y, a.proj, a.n_proj);
+				else if (a.post == JB_POST_LYAP_TRANSVERSAL)
+					norms[0] = lyap_transversal<Sys, REG>(st.Y);
+			}
+			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+			for (int k = 0; k < NLY; ++k) {
+				if (k >= n_out) break;
+				const double lyap = log(norms[k]) / dt_lyap;
+				if (a.lyap_rec) a.lyap_rec[(int64_t) it * n_out * ld + tile_offset(b, n_out) + k * TILE] = lyap;
+				if (it >= a.lyap_discard) {
+					lyap_sum[k] += lyap;
+					lyap_sq[k] = fma(lyap, lyap, lyap_sq[k]);
+				}
+			}
+			if constexpr (IVP) {
+				// the tangent vectors changed: the stepper restarts from the new state
+				initialised = false;
+				interpolant = false;
+				pending_f = have_f = false;
+			}
+		}
+		if constexpr (!DENSE) {
+			if (rec) {
+#pragma unroll UNR
+				for (int i = 0; i < N; ++i) rec[i * TILE] = st.Y(i);
+			}
+		} else if (a.post != JB_POST_NONE) {
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) {
+				a.Yres[off + (int64_t) i * TILE] = st.Y(i);
+				if (rec) rec[i * TILE] = st.Y(i);
+			}
+		}
+	}
+
+	// ================= write the solver back
+	if constexpr (REG) {
+#pragma unroll
+		for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
+	} else {
+		if (st.Y.p != Yc.p) {
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) Yc.set(i, st.Y(i));
+		}
+	}
+	if constexpr (IVP) {
+		if (pending_f || have_f) {
+			const auto &F = pending_f ? st.K[S] : st.K[0];
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) Fc.set(i, F(i));
+		}
+		a.sstate[SS_H_ABS * ld + b] = h_abs;
+		a.sstate[SS_T_OLD * ld + b] = t_old;
+		a.sstate[SS_H_PREV * ld + b] = h_prev;
+		a.sstate[SS_FLAGS * ld + b] = (double) ((initialised ? FLAG_INITIALISED : 0) | (interpolant ? FLAG_INTERPOLANT : 0));
+	}
+	a.t[b] = t;
+	a.status[b] = status;
+	if (a.n_accepted) a.n_accepted[b] += n_acc;
+	if (a.n_rejected) a.n_rejected[b] += n_rej;
+	if (a.lyap_acc && a.post != JB_POST_NONE) {
+		const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+		for (int k = 0; k < NLY; ++k) {
+			if (k >= n_out) break;
+			a.lyap_acc[tile_offset(b, n_out) + k * TILE] += lyap_sum[k];
+			a.lyap_acc[(int64_t) n_out * ld + tile_offset(b, n_out) + k * TILE] += lyap_sq[k];
+		}
+	}
+}
+
+}  // namespace jb
