@@ -331,9 +331,13 @@ class jitcode:
 		Each value may be a number (shared by all trajectories) or a vector with one entry per trajectory;
 		a (B, p) array or tensor is taken as is.
 		"""
-		if len(args) == 1 and (isinstance(args[0], torch.Tensor) or isinstance(args[0], np.ndarray)) and np.ndim(args[0]) == 2:
+		p = len(self.control_pars)
+		if len(args) == 1 and isinstance(args[0], (torch.Tensor, np.ndarray)) and np.ndim(args[0]) == 2:
 			values = args[0]
 			count = values.shape[1]
+		elif len(args) == 1 and p == 1 and np.ndim(args[0]) == 1 and len(args[0]) != 1:
+			values = (args[0],)          # one control parameter, one value per trajectory
+			count = 1
 		else:
 			try:
 				values = tuple(args[0])
@@ -341,7 +345,10 @@ class jitcode:
 				values = args
 			else:
 				if len(args) > 1:
-					raise TypeError("Argument must either be a single sequence or multiple numbers.")
+					if len(args) == p:
+						values = args    # one vector per control parameter
+					else:
+						raise TypeError("Argument must either be a single sequence or multiple numbers.")
 			count = len(values)
 		if count != len(self.control_pars):
 			raise ValueError("Number of values does not match number of control parameters.")
