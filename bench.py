@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""
+bench.py — ensemble Dormand–Prince RK45 trajectory-steps/s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload roessler|lv] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
+
+A *step* of the benchmark is one pass of the hot path over one batch: (re)initialise the ensemble and
+integrate every trajectory from t = 0 to the workload's end time with one `integrate` call.  A
+*trajectory-step* is one Runge–Kutta step attempt (accepted or rejected) of one trajectory; they are
+counted on the device (per-trajectory counters of the kernel).
+
+Default workload (the one the north star's ≥100× target is quoted on, BASELINE.json configs[2]):
+small-world network of 100 Rössler oscillators (n = 300), 1 Mi trajectories per GPU with per-trajectory
+coupling strength and initial state, dopri5 semantics (Dormand–Prince 5(4), Hairer's controller — what
+examples/SW_of_Roesslers.py:107 uses), rtol 1e-6, atol 1e-12, t = 0 → 10.  `--workload lv` runs configs[1]
+(1 Mi Lotka–Volterra initial conditions, t = 0 → 100).
+
+Output: ONE JSON line on rank 0 (keys as the driver's contract demands).
+  value        device-timed (CUDA events) with the ensemble already resident in HBM
+  e2e          through jitcode.set_initial_value / integrate with pinned HOST buffers, copies inside the timed region
+  roofline     the integrate kernel against the HBM roofline of MEASURED_PEAKS.json (algorithmic bytes 280·n per
+               trajectory-step)
+  cpu_baseline the reference CPU path (compiled C right-hand side under scipy.integrate.ode, one process per core)
+               on a bounded sample of the same ensemble
+`--impl reference` times only that CPU path.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+import workloads as W  # noqa: E402
+
+METRIC = "ensemble RK45 trajectory-steps/s"
+UNIT = "trajectory-steps/s"
+RTOL, ATOL = 1e-6, 1e-12
+
+
+def workload(name, B, seed_offset=0):
+	if name == "roessler":
+		system = W.roessler_network(100)
+		Y0, pars = W.roessler_ensemble(B, seed=43 + seed_offset)
+		return {"system": system, "Y0": Y0, "pars": pars, "T": 10.0, "integrator": "dopri5",
+				"label": "SW_of_Roesslers N=100 (n=300), per-trajectory k and Y0"}
+	if name == "lv":
+		system = W.lotka_volterra()
+		Y0, pars = W.lotka_volterra_ensemble(B, seed=42 + seed_offset)
+		return {"system": system, "Y0": Y0, "pars": pars, "T": 100.0, "integrator": "dopri5",
+				"label": "Lotka-Volterra ensemble (n=2), random initial conditions"}
+	raise SystemExit(f"unknown workload {name}")
+
+
+# ------------------------------------------------------------------ the reference CPU path (oracle)
+
+def cpu_reference_handle(system, label):
+	"""oracle/_ref (the reference's own jitced_template.c, compiled in the build container) when it is there,
+	else the oracle's port of it."""
+	from oracle import build_ref, c_rhs
+	handle = None
+	try:
+		handle = build_ref.build_ref_rhs(system["f_sym"], system["helpers"], system["control_pars"], system["n"])
+		if handle is not None:
+			handle.f  # noqa: B018  (import check: the file was built for this Python)
+			return handle, "reference"
+	except Exception:
+		handle = None
+	return c_rhs.build_rhs(system["f_sym"], system["helpers"], system["control_pars"], system["n"]), "port"
+
+
+def cpu_run(wl, handle, n_sample):
+	from oracle import ensemble
+	Y0, pars = wl["Y0"][:n_sample], wl["pars"][:n_sample]
+	result = ensemble.run_ensemble(handle, wl["integrator"], Y0, [wl["T"]], pars=pars, rtol=RTOL, atol=ATOL)
+	return result["attempts"], result["seconds"], result["cores"]
+
+
+def cpu_baseline(wl, per_core):
+	handle, kind = cpu_reference_handle(wl["system"], wl["label"])
+	from oracle import ensemble
+	cores = ensemble.available_cores()
+	n_sample = min(len(wl["Y0"]), per_core * cores)
+	cpu_run(wl, handle, min(n_sample, 2 * cores))     # warm the pool and the page cache
+	attempts, seconds, cores = cpu_run(wl, handle, n_sample)
+	return {"value": attempts / seconds, "unit": UNIT, "cores": cores, "kind": kind,
+			"sample": f"{n_sample} trajectories of the same ensemble, {wl['integrator']} via scipy.integrate.ode, t=0..{wl['T']:g}, {seconds:.1f} s"}
+
+
+def run_reference(args):
+	rank = int(os.environ.get("RANK", "0"))
+	if rank != 0:
+		return
+	per_core = args.cpu_sample_per_core
+	from oracle import ensemble
+	cores = ensemble.available_cores()
+	wl = workload(args.workload, per_core * cores)
+	handle, kind = cpu_reference_handle(wl["system"], wl["label"])
+	for _ in range(args.warmup):
+		cpu_run(wl, handle, min(len(wl["Y0"]), 4 * cores))
+	attempts = seconds = 0.0
+	for _ in range(args.steps):
+		a, s, cores = cpu_run(wl, handle, len(wl["Y0"]))
+		attempts += a
+		seconds += s
+	value = attempts / seconds
+	line = {
+		"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+		"warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "weak",
+		"vs_baseline": None, "dtype": "f64", "data": "synthetic",
+		"config": {"workload": wl["label"], "integrator": wl["integrator"], "rtol": RTOL, "atol": ATOL, "t_end": wl["T"],
+				"trajectories_per_step": len(wl["Y0"])},
+		"cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+				"sample": f"{len(wl['Y0'])} trajectories per step, one process per core"},
+		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+		"gpu_launches": 0,
+	}
+	print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ clocks
+
+CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+		"clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+class ClockSampler:
+	def __init__(self, device_index):
+		self.device_index = device_index
+		self.process = None
+
+	def __enter__(self):
+		try:
+			self.process = subprocess.Popen(
+				["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={CLOCK_QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+				stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+		except OSError:
+			self.process = None
+		return self
+
+	def __exit__(self, *exc):
+		self.samples = []
+		if self.process is None:
+			return
+		self.process.terminate()
+		try:
+			out, _ = self.process.communicate(timeout=5)
+		except subprocess.TimeoutExpired:
+			self.process.kill()
+			out, _ = self.process.communicate()
+		for line in out.splitlines():
+			parts = [p.strip() for p in line.split(",")]
+			if len(parts) >= 9:
+				try:
+					self.samples.append({"sm": float(parts[1]), "max": float(parts[2]), "power": float(parts[3]),
+							"hw_slowdown": parts[5], "hw_thermal": parts[6], "sw_thermal": parts[7], "sw_power_cap": parts[8]})
+				except ValueError:
+					pass
+
+	def summary(self):
+		if not getattr(self, "samples", None):
+			return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+		busy = [s for s in self.samples if s["power"] > 200] or self.samples
+		reasons = [key for key in ("hw_slowdown", "hw_thermal", "sw_thermal", "sw_power_cap")
+				if any(s[key].lower().startswith("active") for s in self.samples)]
+		return {"sm_mhz": statistics.median(s["sm"] for s in busy), "sm_max_mhz": max(s["max"] for s in self.samples),
+				"reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------ our arm
+
+def run_ours(args):
+	import torch
+	import torch.distributed as dist
+	from jitcode_b200 import jitcode
+
+	world = int(os.environ.get("WORLD_SIZE", "1"))
+	rank = int(os.environ.get("RANK", "0"))
+	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+	if not torch.cuda.is_available():
+		raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm).")
+	torch.cuda.set_device(local_rank)
+	device = torch.device("cuda", local_rank)
+	if world > 1:
+		dist.init_process_group("nccl", device_id=device)
+
+	B = args.trajectories
+	wl = workload(args.workload, B, seed_offset=1000 * rank)      # every rank integrates its own shard
+	system = wl["system"]
+	n = system["n"]
+	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=n, control_pars=system["control_pars"], verbose=False)
+	ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=ATOL, storage=args.storage)
+	integrator = ODE.integrator
+	module = integrator.module
+
+	Y0_host = torch.as_tensor(wl["Y0"]).pin_memory()
+	pars_host = torch.as_tensor(wl["pars"]).pin_memory() if wl["pars"].shape[1] else None
+	out_host = torch.empty_like(Y0_host).pin_memory()
+	Y0_dev = Y0_host.to(device)
+	pars_dev = pars_host.to(device) if pars_host is not None else None
+
+	def barrier():
+		if world > 1:
+			dist.barrier()
+		torch.cuda.synchronize()
+
+	def device_step():
+		if pars_dev is not None:
+			ODE.set_parameters(pars_dev)
+		ODE.set_initial_value(Y0_dev, 0.0)
+		return ODE.integrate(wl["T"])
+
+	def host_step():
+		if pars_host is not None:
+			ODE.set_parameters(pars_host)
+		ODE.set_initial_value(Y0_host, 0.0)
+		return ODE.integrate(wl["T"], out=out_host)
+
+	# ---- device-resident arm
+	for _ in range(args.warmup):
+		device_step()
+	barrier()
+	integrator.reset_step_counts()
+	integrator.kernel_events = []
+	launches_before = module.launch_count()
+	start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+	with ClockSampler(local_rank) as clocks:
+		barrier()
+		start.record()
+		for _ in range(args.steps):
+			device_step()
+		end.record()
+		barrier()
+	seconds = start.elapsed_time(end) * 1e-3
+	launches = module.launch_count() - launches_before
+	accepted, rejected = integrator.step_counts()
+	attempts = accepted + rejected
+	kernel_ms = [a.elapsed_time(b) for a, b in integrator.kernel_events]
+	integrator.kernel_events = None
+
+	# ---- end-to-end arm: pinned host buffers in and out through the public API
+	for _ in range(min(args.warmup, 2)):
+		host_step()
+	barrier()
+	integrator.reset_step_counts()
+	t0 = time.perf_counter()
+	for _ in range(args.steps):
+		host_step()
+	barrier()
+	e2e_seconds = time.perf_counter() - t0
+	e2e_attempts = sum(integrator.step_counts())
+
+	if world > 1:
+		stats = torch.tensor([seconds, e2e_seconds], dtype=torch.float64, device=device)
+		dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+		seconds, e2e_seconds = stats.tolist()
+		counts = torch.tensor([attempts, e2e_attempts, accepted, launches], dtype=torch.float64, device=device)
+		dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+		attempts, e2e_attempts, accepted, launches = counts.tolist()
+
+	if rank == 0:
+		peaks_path = ROOT / "MEASURED_PEAKS.json"
+		if peaks_path.exists():
+			peak, peak_source = json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+		else:
+			peak, peak_source = 6650.0, "fallback of B200_PROFILING.md"
+		own_attempts = sum(integrator.step_counts()) / max(1, args.steps) if world == 1 else attempts / world / args.steps
+		own_attempts = (attempts / world) / args.steps
+		bytes_per_launch = 280.0 * n * own_attempts           # 35·n·8 B per trajectory-step
+		kernel_s = statistics.mean(kernel_ms) * 1e-3
+		achieved = bytes_per_launch / kernel_s / 1e9
+		traffic_file = ROOT / "profiles" / "traffic.json"
+		traffic = None
+		if traffic_file.exists():
+			traffic = json.loads(traffic_file.read_text()).get(f"{args.workload}:{module.info.storage}")
+		line = {
+			"metric": METRIC, "value": attempts / seconds, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+			"ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+			"dtype": "f64", "data": "synthetic",
+			"config": {"workload": wl["label"], "integrator": wl["integrator"], "rtol": RTOL, "atol": ATOL, "t_end": wl["T"],
+					"trajectories_per_gpu": B, "n": n, "storage": {0: "registers", 1: "global", 2: "warp"}.get(module.info.storage),
+					"parallelism": f"trajectory shards x{world}, no data-path collective",
+					"l2": f"state per GPU {B*n*8/1e6:.0f} MB vs 126 MB L2 (no flush needed)" if B*n*8 > 2.5e8 else "ensemble re-packed from a fresh copy every step",
+					"accepted_fraction": accepted / max(1.0, attempts)},
+			"e2e": {"value": e2e_attempts / e2e_seconds, "unit": UNIT,
+					"h2d_bytes_per_step": int(Y0_host.numel() * 8 + (pars_host.numel() * 8 if pars_host is not None else 0)),
+					"d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": 1e3 * e2e_seconds / args.steps},
+			"gpu_launches": int(launches),
+			"clocks": clocks.summary(),
+			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+					"kernel": "jb_integrate_kernel", "kernel_ms": statistics.mean(kernel_ms), "peak_source": peak_source,
+					"algorithmic_bytes_per_trajectory_step": 280 * n},
+		}
+		if world == 1 and not args.no_cpu_baseline:
+			line["cpu_baseline"] = cpu_baseline(wl, args.cpu_sample_per_core)
+		print(json.dumps(line))
+	if world > 1:
+		dist.destroy_process_group()
+
+
+def main():
+	parser = argparse.ArgumentParser()
+	parser.add_argument("--gpus", type=int, default=1)
+	parser.add_argument("--steps", type=int, default=5)
+	parser.add_argument("--warmup", type=int, default=3)
+	parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+	parser.add_argument("--workload", default="roessler", choices=["roessler", "lv"])
+	parser.add_argument("--trajectories", type=int, default=1 << 20, help="per GPU")
+	parser.add_argument("--storage", default=None, choices=[None, "registers", "global", "warp"])
+	parser.add_argument("--cpu-sample-per-core", type=int, default=None)
+	parser.add_argument("--no-cpu-baseline", action="store_true")
+	args = parser.parse_args()
+	args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+	if args.cpu_sample_per_core is None:
+		args.cpu_sample_per_core = 256 if args.workload == "roessler" else 4096
+	if args.impl == "reference":
+		run_reference(args)
+	else:
+		run_ours(args)
+
+
+if __name__ == "__main__":
+	main()

@@ -119,6 +119,7 @@ class CudaEnsembleIntegrator:
 		self._out_kind = "numpy"
 		self._single = False
 		self.last_lyaps = None
+		self.kernel_events = None   # set to [] to collect (start, end) CUDA events around every integrate launch
 
 	# ------------------------------------------------------------------ plumbing
 
@@ -168,10 +169,15 @@ class CudaEnsembleIntegrator:
 		self.module.unpack(tiled.data_ptr(), rows.data_ptr(), self.B, width, self.ld, self.stream)
 		return rows
 
-	def _export(self, rows):
-		"""device rows → what the caller gets (mirrors the kind of the initial value)."""
+	def _export(self, rows, out=None):
+		"""device rows → what the caller gets (mirrors the kind of the initial value); `out`: a (pinned) CPU
+		tensor of the right shape to receive the copy instead of a fresh array."""
 		if self._single:
 			rows = rows[0]
+		if out is not None:
+			out.copy_(rows, non_blocking=True)
+			torch.cuda.current_stream(self.device).synchronize()
+			return out
 		if self._out_kind == "cuda":
 			return rows
 		host = rows.cpu()
@@ -302,7 +308,15 @@ class CudaEnsembleIntegrator:
 		n_times = len(times)
 		Yrec = torch.empty(n_times * self.n * self.ld, dtype=torch.float64, device=self.device) if record else None
 		lyap_rec = torch.empty(max(1, n_times * self.n_out) * self.ld, dtype=torch.float64, device=self.device) if self.n_out else None
-		self.module.integrate(self._args(times_dev, n_times, Yrec, lyap_rec))
+		args = self._args(times_dev, n_times, Yrec, lyap_rec)
+		if self.kernel_events is not None:
+			start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			start.record()
+			self.module.integrate(args)
+			end.record()
+			self.kernel_events.append((start, end))
+		else:
+			self.module.integrate(args)
 		self.time = times[-1]
 		return Yrec, lyap_rec
 
@@ -310,8 +324,9 @@ class CudaEnsembleIntegrator:
 		source = self.Yres if (self.driver == JB_DRV_IVP_DENSE) else self.Y
 		return self._unpack(source, self.n)
 
-	def integrate(self, T):
-		"""advance every trajectory to T and return the state there: (B, n), or (n,) if the initial value was 1-D."""
+	def integrate(self, T, out=None):
+		"""advance every trajectory to T and return the state there: (B, n), or (n,) if the initial value was 1-D.
+		out: optional CPU tensor (ideally pinned) that receives the result."""
 		T = float(T)
 		if self.B is None:
 			raise RuntimeError("You must call set_initial_value first.")
@@ -322,7 +337,7 @@ class CudaEnsembleIntegrator:
 		if self.n_out:
 			self.last_lyaps = self._unpack(lyap_rec, self.n_out)
 		self._check_failures()
-		return self._export(self._rows)
+		return self._export(self._rows, out)
 
 	def integrate_many(self, times):
 		"""the loop `for T in times: integrate(T)` as ONE launch; returns (len(times), B, n)."""

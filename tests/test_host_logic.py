@@ -1,0 +1,273 @@
+"""
+CPU-side tests of the product (no GPU): symbolic front-end, CUDA code generator, run-time build + C ABI
+export table, and the error behaviour of the reference's API (reference tests/test_jitcode.py:164-205,
+tests/scenarios.py:48-110 input styles).
+"""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import sympy
+
+import workloads as W
+from jitcode_b200 import _build, _codegen, _symbolic, jitcode, jitcode_lyap, jitcode_transversal_lyap, t, y
+from jitcode_b200._transversal import GroupHandler
+
+ROOT = Path(__file__).resolve().parents[1]
+a, b1, b2, c, k = (W.FHN[x] for x in ("a", "b1", "b2", "c", "k"))
+
+
+def fhn_list():
+	return W.fhn()["f_sym"]
+
+def fhn_generator():
+	yield from fhn_list()
+
+def fhn_dict():
+	return {y(i): entry for i, entry in reversed(list(enumerate(fhn_list())))}
+
+def fhn_with_helpers():
+	# reference tests/scenarios.py:70-91: shuffled helpers that depend on each other
+	p, q, r, s = sympy.symbols("p q r s")
+	helpers = [
+		(r, y(2) * q),
+		(p, y(0) * (a - y(0)) * (y(0) - 1.0)),
+		(q, (a - y(2)) * (y(2) - 1.0)),
+		(s, k * (y(2) - y(0))),
+	]
+	f = [p - y(1) + s, b1*y(0) - c*y(1), r - y(3) - s, b2*y(2) - c*y(3)]
+	return f, helpers
+
+
+def evaluate(f, helpers, state, time=0.0):
+	"""plain SymPy evaluation of what the generator would print."""
+	subs = {y(i): v for i, v in enumerate(state)}
+	subs[t] = time
+	values = {}
+	for symbol, definition in _symbolic.sort_helpers(helpers):
+		values[symbol] = float(definition.subs(values).subs(subs))
+	return np.array([float(sympy.sympify(entry).subs(values).subs(subs)) for entry in f])
+
+
+@pytest.mark.parametrize("style", [fhn_list, lambda: fhn_generator, fhn_dict])
+def test_input_styles(style):
+	f, n = _symbolic.handle_input(style())
+	assert n == 4
+	np.testing.assert_allclose(evaluate(f, [], W.FHN_Y0), W.FHN_F_OF_Y0, rtol=1e-5)
+
+
+def test_helpers_sorted_and_equivalent():
+	f, helpers = fhn_with_helpers()
+	ordered = _symbolic.sort_helpers(helpers)
+	seen = set()
+	symbols = {s for s, _ in ordered}
+	for symbol, definition in ordered:
+		assert not ((definition.free_symbols & symbols) - seen)
+		seen.add(symbol)
+	np.testing.assert_allclose(evaluate(f, helpers, W.FHN_Y0), W.FHN_F_OF_Y0, rtol=1e-5)
+	with pytest.raises(ValueError):
+		p, q = sympy.symbols("p q")
+		_symbolic.sort_helpers([(p, q + 1), (q, p + 1)])
+
+
+def test_jacobian_golden_with_and_without_helpers():
+	# reference tests/scenarios.py:24-29, tests/test_generation.py:57-59,66-83
+	subs = {y(i): v for i, v in enumerate(W.FHN_Y0)}
+	plain = sympy.Matrix(list(_symbolic.jacobian_rows(_symbolic.handle_input(fhn_list())[0], [], 4))).subs(subs)
+	np.testing.assert_allclose(np.array(plain, dtype=float), W.FHN_JAC_OF_Y0, rtol=1e-5)
+	f, helpers = fhn_with_helpers()
+	helpers = _symbolic.sort_helpers(helpers)
+	rows = list(_symbolic.jacobian_rows(_symbolic.handle_input(f)[0], helpers, 4))
+	values = {}
+	for symbol, definition in helpers:
+		values[symbol] = definition.subs(values)
+	with_helpers = sympy.Matrix(rows).subs(values).subs(subs)
+	np.testing.assert_allclose(np.array(with_helpers, dtype=float), W.FHN_JAC_OF_Y0, rtol=1e-5)
+
+
+def test_lyapunov_system_matches_golden(golden):
+	# the 20-dimensional system of jitcode_lyap evaluated at the reference's test point (tests/test_generation.py:85-97)
+	g = golden("fhn_lyap_rhs")
+	f, helpers = fhn_with_helpers()
+	helpers = _symbolic.sort_helpers(helpers)
+	for basic, hs in ((_symbolic.handle_input(fhn_list())[0], []), (_symbolic.handle_input(f)[0], helpers)):
+		full = _symbolic.lyapunov_system(basic, hs, 4, 4)
+		assert len(full) == 20
+		np.testing.assert_allclose(evaluate(full, hs, g["x"]), g["fx"], rtol=1e-12)
+
+
+def test_symbol_provenance():
+	# reference tests/test_sympy_input.py: own symbols, SymPy-made symbols, mixtures
+	own = [sympy.cos(t) * y(0)]
+	foreign_y, foreign_t = sympy.Function("y"), sympy.Symbol("t", real=True)
+	plain_t = sympy.Symbol("t")
+	for f in ([sympy.cos(foreign_t) * foreign_y(0)], [sympy.cos(plain_t) * foreign_y(0)], [sympy.cos(t) * foreign_y(0)]):
+		assert _symbolic.handle_input(f)[0] == _symbolic.handle_input(own)[0]
+
+
+def test_cuda_printer():
+	printer = _codegen.CudaPrinter()
+	x = sympy.Symbol("x")
+	assert printer.doprint(y(3)**2) == "y(3)*y(3)"
+	assert printer.doprint((x + 1)**3) == "(x + 1.0)*(x + 1.0)*(x + 1.0)"
+	assert printer.doprint(x**-2) == "1.0/(x*x)"
+	assert "pow" in printer.doprint(x**sympy.Rational(5, 3))
+	assert printer.doprint(sympy.Rational(3, 4) * x) in ("(3.0/4.0)*x", "3.0/4.0*x", "0.75*x")
+	assert printer.doprint(2 * y(0)) == "2.0*y(0)"
+
+
+def test_statements_share_repeated_calls():
+	system = W.roessler_network(20)
+	f, n = _symbolic.handle_input(system["f_sym"], system["n"])
+	lines = _codegen.rhs_statements(f, _symbolic.sort_helpers(system["helpers"]), system["control_pars"])
+	text = "\n".join(lines)
+	assert text.count("sin(t)") == 1            # sin(t) appears in 20 equations but is evaluated once
+	assert len([line for line in lines if line.startswith("dy.set(")]) == n
+	assert "par.v[0]" in text and "jb_helper_0" in text
+
+
+def test_module_builds_loads_and_exports_every_symbol():
+	"""the C ABI: every function declared in include/jitcode_b200.h is exported by a compiled module."""
+	header = (ROOT / "include" / "jitcode_b200.h").read_text()
+	declared = set(re.findall(r"\b(jb_[a-z_]+)\s*\(", header))
+	assert declared == set(_build.EXPORTS)
+	ODE = jitcode(W.lotka_volterra(gamma_as_parameter=True)["f_sym"], n=2, control_pars=W.lotka_volterra(gamma_as_parameter=True)["control_pars"], verbose=False)
+	module = ODE.compile_cuda()
+	lib = ctypes.CDLL(module.path)
+	for name in declared:
+		assert hasattr(lib, name), name
+	assert module.info.abi_version == _build.JB_ABI_VERSION
+	assert (module.info.n, module.info.n_params, module.info.n_basic, module.info.n_lyap) == (2, 1, 2, 0)
+	assert module.info.storage == _codegen.JB_STORE_REGISTERS and module.info.work_vectors == 0
+	assert ctypes.sizeof(_build.IntegrateArgs) % 8 == 0
+	# argument validation happens before any CUDA call
+	assert lib.jb_integrate(None) == -2
+	assert b"ABI" in ctypes.cast(lib.jb_last_error, ctypes.CFUNCTYPE(ctypes.c_char_p))()
+
+
+def test_struct_layout_matches_header():
+	"""ctypes mirror and C struct agree (compiled probe prints sizeof/offsetof)."""
+	import subprocess, tempfile
+	probe = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "jitcode_b200.h"
+int main(void) {
+	printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(jb_integrate_args), offsetof(jb_integrate_args, times), offsetof(jb_integrate_args, nsteps),
+		offsetof(jb_integrate_args, t), offsetof(jb_integrate_args, status), offsetof(jb_integrate_args, stream), sizeof(jb_module_info));
+	return 0;
+}'''
+	with tempfile.TemporaryDirectory() as tmp:
+		src = Path(tmp) / "probe.c"
+		src.write_text(probe)
+		subprocess.run(["gcc", f"-I{ROOT/'include'}", str(src), "-o", str(Path(tmp)/"probe")], check=True)
+		out = subprocess.run([str(Path(tmp)/"probe")], capture_output=True, text=True, check=True).stdout.split()
+	A = _build.IntegrateArgs
+	expected = [ctypes.sizeof(A), A.times.offset, A.nsteps.offset, A.t.offset, A.status.offset, A.stream.offset, ctypes.sizeof(_build.ModuleInfo)]
+	assert [int(v) for v in out] == expected
+
+
+def test_storage_choice():
+	from jitcode_b200._jitcode import _storage_for
+	assert _storage_for(2, _codegen.JB_DP5, _codegen.JB_DRV_ODE) == _codegen.JB_STORE_REGISTERS
+	assert _storage_for(8, _codegen.JB_DP5, _codegen.JB_DRV_IVP_DENSE) == _codegen.JB_STORE_REGISTERS
+	assert _storage_for(20, _codegen.JB_DP5, _codegen.JB_DRV_ODE) == _codegen.JB_STORE_GLOBAL
+	assert _storage_for(4, _codegen.JB_DOP853, _codegen.JB_DRV_IVP_DENSE) == _codegen.JB_STORE_REGISTERS
+	assert _storage_for(300, _codegen.JB_DP5, _codegen.JB_DRV_ODE) != _codegen.JB_STORE_REGISTERS
+
+
+# ------------------------------------------------------------------ error behaviour (reference tests/test_jitcode.py:164-205)
+
+def test_duplicate_module_name():
+	ODE = jitcode(fhn_list(), verbose=False)
+	ODE.compile_cuda(modulename="foo_b200")
+	with pytest.raises(NameError):
+		jitcode(fhn_list(), verbose=False).compile_cuda(modulename="foo_b200")
+
+def test_wrong_n():
+	with pytest.raises(ValueError):
+		jitcode(fhn_list(), n=5, verbose=False)
+
+def test_dimension_mismatch():
+	ODE = jitcode(fhn_list(), verbose=False)
+	with pytest.raises(ValueError):
+		ODE.set_initial_value(np.array([1.0, 2.0, 3.0]), 0.0)
+
+def test_check_index_negative():
+	with pytest.raises(ValueError):
+		jitcode([y(0) - y(-1)], verbose=False).check()
+
+def test_check_index_too_high():
+	with pytest.raises(ValueError):
+		jitcode([y(0) - y(1)], verbose=False).check()
+
+def test_check_undefined_variable():
+	with pytest.raises(ValueError):
+		jitcode([y(0) * sympy.Symbol("x")], verbose=False).check()
+
+def test_no_integrator():
+	ODE = jitcode(fhn_list(), verbose=False)
+	ODE.set_initial_value(W.FHN_Y0, 0.0)
+	with pytest.raises(RuntimeError):
+		ODE.integrate(1.0)
+	with pytest.raises(RuntimeError):
+		jitcode(fhn_list(), verbose=False).t
+
+def test_implicit_methods_are_refused():
+	ODE = jitcode(fhn_list(), verbose=False)
+	for name in ("LSODA", "vode", "BDF", "Radau"):
+		with pytest.raises(NotImplementedError):
+			ODE.set_integrator(name)
+
+def test_callbacks_are_refused():
+	with pytest.raises(NotImplementedError):
+		jitcode(fhn_list(), callback_functions=[(sympy.Function("cb"), lambda state: 0.0, 0)], verbose=False)
+
+def test_wrong_number_of_parameters():
+	system = W.lotka_volterra(gamma_as_parameter=True)
+	ODE = jitcode(system["f_sym"], control_pars=system["control_pars"], verbose=False)
+	with pytest.raises(ValueError):
+		ODE.set_parameters(1.0, 2.0)
+
+def test_save_compiled_and_module_location(tmp_path):
+	ODE = jitcode(fhn_list(), verbose=False)
+	destination = ODE.save_compiled(str(tmp_path / "saved.so"), overwrite=True)
+	with pytest.raises(OSError):
+		ODE.save_compiled(destination)
+	loaded = jitcode(n=4, module_location=destination, verbose=False)
+	assert next(iter(loaded._modules.values())).info.n == 4
+	with pytest.raises(ValueError):
+		jitcode(n=5, module_location=destination, verbose=False)
+
+
+# ------------------------------------------------------------------ transversal bookkeeping
+
+def test_group_handler_round_trip():
+	groups = [[0, 2, 4], [1, 3]]
+	handler = GroupHandler(groups)
+	assert handler.main_indices == [0, 3] and handler.tangent_indices == [1, 2, 4]
+	assert handler.map_to_main(4) == 0 and handler.map_to_main(3) == 3
+	z = sympy.symbols("z0:5")
+	back = handler.back_transform(list(z))
+	# differences of consecutive members reproduce the difference coordinates; group sums vanish
+	assert sympy.simplify(back[0] - back[2] - z[1]) == 0
+	assert sympy.simplify(back[2] - back[4] - z[2]) == 0
+	assert sympy.simplify(back[1] - back[3] - z[4]) == 0
+	assert sympy.simplify(back[0] + back[2] + back[4]) == 0 and sympy.simplify(back[1] + back[3]) == 0
+
+def test_transversal_system_dimension():
+	# two identical, mutually coupled oscillators: one group per component
+	f = [y(1), -y(0) + 0.1*(y(2) - y(0)), y(3), -y(2) + 0.1*(y(0) - y(2))]
+	ODE = jitcode_transversal_lyap(f, groups=[[0, 2], [1, 3]], verbose=False)
+	assert ODE.n == 4 and ODE.main_indices == [0, 2] and ODE.tangent_indices == [1, 3]
+	module = ODE.compile_cuda()
+	assert module.info.n_tangent == 2 and module.info.n_lyap == 1
+
+def test_lyap_module_layout():
+	ODE = jitcode_lyap(fhn_list(), n_lyap=2, verbose=False)
+	assert ODE.n == 12 and ODE.n_basic == 4
+	module = ODE.compile_cuda()
+	assert (module.info.n, module.info.n_basic, module.info.n_lyap) == (12, 4, 2)
