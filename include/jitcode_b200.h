@@ -34,6 +34,10 @@
  *     padded number of trajectories; a "[k][n][ld]" array below is k such tiled vectors back to
  *     back (k * n * ld doubles).  Per-trajectory scalars are plain arrays [ld].  jb_pack /
  *     jb_unpack convert from / to the reference's row-per-trajectory (B, n) layout.
+ *     Modules with storage JB_STORE_WARP (one warp per trajectory, lanes across components) read a
+ *     trajectory's vector as one contiguous row instead: every n-vector, parameter block and
+ *     "[k][n][ld]" array is row-major (k, ld, n) — the reference's own layout, X[b*n + i], ld >= B
+ *     without padding requirement — and jb_pack / jb_unpack are plain copies.
  *   - Every function returns 0 on success, otherwise a cudaError_t value (>0) or a negative
  *     JB_E_* code; jb_last_error() gives the text for the calling thread.
  *   - Per-trajectory outcome is reported in `status[b]` (enum jb_status).
@@ -47,7 +51,7 @@
 extern "C" {
 #endif
 
-#define JB_ABI_VERSION 4
+#define JB_ABI_VERSION 5
 #define JB_TILE 32
 
 enum jb_method  { JB_DP5 = 0, JB_DOP853 = 1 };
@@ -56,7 +60,11 @@ enum jb_driver  {
 	JB_DRV_IVP_DENSE = 1,  /* scipy solve_ivp controller; persistent stepper; dense output at the sample time */
 	JB_DRV_IVP_LAND = 2    /* scipy solve_ivp controller; persistent stepper; last step clipped to the sample time */
 };
-enum jb_storage { JB_STORE_REGISTERS = 0, JB_STORE_GLOBAL = 1 };
+enum jb_storage {
+	JB_STORE_REGISTERS = 0, /* thread per trajectory, state and stages in registers; tiled layout */
+	JB_STORE_GLOBAL = 1,    /* thread per trajectory, stages in the caller's tiled workspace */
+	JB_STORE_WARP = 2       /* warp per trajectory, stages in shared memory; ROW layout (see below) */
+};
 enum jb_status  { JB_OK = 0, JB_STEP_TOO_SMALL = 1, JB_TOO_MANY_STEPS = 2, JB_STIFF = 3, JB_NONFINITE = 4 };
 enum jb_post    {
 	JB_POST_NONE = 0,
@@ -80,7 +88,8 @@ typedef struct jb_module_info {
 	int32_t state_scalars;/* persistent solver scalars per trajectory: sstate[state_scalars][ld] */
 	int32_t work_vectors; /* scratch vectors (global storage only): work[work_vectors][n][ld] */
 	int32_t threads_per_block;
-	int32_t reserved[3];
+	int32_t shared_bytes;  /* dynamic shared memory per block (JB_STORE_WARP: tables + stage vectors of its warps) */
+	int32_t reserved[2];
 } jb_module_info;
 
 typedef struct jb_integrate_args {

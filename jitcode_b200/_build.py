@@ -19,7 +19,7 @@ from pathlib import Path
 PACKAGE_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PACKAGE_DIR / "csrc"
 INCLUDE_DIR = PACKAGE_DIR.parent / "include"
-JB_ABI_VERSION = 4
+JB_ABI_VERSION = 5
 JB_TILE = 32
 
 DEFAULT_COMPILE_ARGS = [
@@ -86,8 +86,8 @@ def compile_module(source, extra_compile_args=(), extra_link_args=(), verbose=Fa
 class ModuleInfo(ctypes.Structure):
 	_fields_ = [(name, ctypes.c_int32) for name in (
 		"abi_version", "n", "n_params", "n_basic", "n_lyap", "n_tangent", "method", "driver", "storage",
-		"state_vectors", "state_scalars", "work_vectors", "threads_per_block",
-	)] + [("reserved", ctypes.c_int32 * 3)]
+		"state_vectors", "state_scalars", "work_vectors", "threads_per_block", "shared_bytes",
+	)] + [("reserved", ctypes.c_int32 * 2)]
 
 class IntegrateArgs(ctypes.Structure):
 	_fields_ = [

@@ -19,11 +19,11 @@ from ._symbolic import t as TIME
 
 JB_DP5, JB_DOP853 = 0, 1
 JB_DRV_ODE, JB_DRV_IVP_DENSE, JB_DRV_IVP_LAND = 0, 1, 2
-JB_STORE_REGISTERS, JB_STORE_GLOBAL = 0, 1
+JB_STORE_REGISTERS, JB_STORE_GLOBAL, JB_STORE_WARP = 0, 1, 2
 
 METHOD_NAMES = {JB_DP5: "JB_DP5", JB_DOP853: "JB_DOP853"}
 DRIVER_NAMES = {JB_DRV_ODE: "JB_DRV_ODE", JB_DRV_IVP_DENSE: "JB_DRV_IVP_DENSE", JB_DRV_IVP_LAND: "JB_DRV_IVP_LAND"}
-STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL"}
+STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL", JB_STORE_WARP: "JB_STORE_WARP"}
 
 
 class CudaPrinter(C99CodePrinter):
@@ -131,9 +131,18 @@ def uses_time(f, helpers):
 	return any(TIME in expr.free_symbols for expr in list(f) + [d for _, d in helpers])
 
 
-def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, chunk_size=None):
+def _c_array(values, per_line=16):
+	values = list(values) or ["0"]
+	return ",\n\t".join(", ".join(values[k:k+per_line]) for k in range(0, len(values), per_line))
+
+
+def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None):
 	"""the complete translation unit of one module (what _render_template produces from
-	jitced_template.c in the reference, _jitcode.py:397-406)."""
+	jitced_template.c in the reference, _jitcode.py:397-406).
+
+	statements : body of the right-hand side — of Sys::rhs (thread storage: `y(i)` / `dy.set(i, …)` on whatever
+		vector type the stepper uses) or of Sys::rhs_warp (warp storage: the vectorised form of _vectorise.py,
+		with `tables` = its _vectorise.Tables)."""
 	tangent_indices = list(tangent_indices or [])
 	if tangent_indices:
 		table = ", ".join(str(int(k)) for k in tangent_indices)
@@ -144,13 +153,39 @@ def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, met
 	else:
 		tangent = "\tstatic __device__ __forceinline__ int tangent_index(int) { return 0; }\n"
 
-	# large right-hand sides are cut into chunks (the role of chunk_size in render_and_write_code,
-	# _jitcode.py:198-200): temporaries first, then groups of statements in their own scope
 	body = "\n".join("\t\t" + line for line in statements)
+	warp = storage == JB_STORE_WARP
+	tf = [repr(float(v)) for v in tables.f64] if warp else []
+	tu = [str(int(v)) for v in tables.u] if warp else []
+	tu_type = "unsigned short" if (not tu or max(int(v) for v in tu) < 65536) else "unsigned int"
+	if warp:
+		function = f"""	template <class VI, class VO>
+	static __device__ __forceinline__ void rhs_warp(const double t, const VI &y, VO &dy, const Par &par, const int lane, const void *jb_tables)
+	{{
+		const double *const JB_TF = static_cast<const double *>(jb_tables);
+		const TU *const JB_TU = reinterpret_cast<const TU *>(JB_TF + TF_COUNT);
+{body}
+		(void) t; (void) par; (void) JB_TF; (void) JB_TU;
+	}}"""
+	else:
+		function = f"""	template <class VI, class VO>
+	static __device__ __forceinline__ void rhs(const double t, const VI &y, VO &dy, const Par &par)
+	{{
+{body}
+		(void) t; (void) par;
+	}}"""
 	return f"""// generated by jitcode_b200._codegen — one ODE system fused into the ensemble Runge–Kutta kernels
 #include "jb_rk.cuh"
 
 namespace jb_generated {{
+
+// tables of the vectorised right-hand side (warp storage); staged in shared memory by the kernels
+__device__ const double jb_tf[{max(1, len(tf))}] = {{
+	{_c_array(tf, 8)}
+}};
+__device__ const {tu_type} jb_tu[{max(1, len(tu))}] = {{
+	{_c_array(tu, 24)}
+}};
 
 struct Sys {{
 	static constexpr int N = {n};      // dimension of the integrated system
@@ -158,14 +193,11 @@ struct Sys {{
 	static constexpr int NB = {n_basic};     // dimension of the underlying system
 	static constexpr int NL = {n_lyap};     // tangent vectors
 	static constexpr int NT = {len(tangent_indices)};     // transversal tangent coordinates
+	static constexpr int TF_COUNT = {len(tf)}, TU_COUNT = {len(tu)};
+	typedef {tu_type} TU;
 	struct Par {{ double v[NP > 0 ? NP : 1]; }};
 {tangent}
-	template <class VI, class VO>
-	static __device__ __forceinline__ void rhs(const double t, const VI &y, VO &dy, const Par &par)
-	{{
-{body}
-		(void) t; (void) par;
-	}}
+{function}
 }};
 
 }}  // namespace jb_generated

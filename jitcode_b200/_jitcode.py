@@ -25,7 +25,7 @@ import numpy as np
 import sympy
 import torch
 
-from . import _build, _codegen
+from . import _build, _codegen, _vectorise
 from ._integrator import (
 	JB_POST_LYAP_QR, JB_POST_LYAP_RESTRICTED, JB_POST_LYAP_TRANSVERSAL, JB_POST_NONE,
 	CudaEnsembleIntegrator, UnsuccessfulIntegration, empty_integrator, require_cuda,
@@ -45,10 +45,25 @@ NOT_REBUILT = ("RK23", "Radau", "BDF", "LSODA", "vode", "lsoda", "zvode")
 _used_module_names = set()
 
 
+SHARED_MEMORY_PER_BLOCK = 227 * 1024      # sm_100a: opt-in maximum of dynamic shared memory per block
+STORAGE_BY_NAME = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL, "warp": _codegen.JB_STORE_WARP}
+
+
+def _stage_rows(method, driver):
+	return 7 if method == _codegen.JB_DP5 else (16 if driver == _codegen.JB_DRV_IVP_DENSE else 13)
+
+
 def _storage_for(n, method, driver):
-	"""registers while state + stages fit a thread's register file, else the tiled global workspace."""
-	rows = (7 if method == _codegen.JB_DP5 else (16 if driver == _codegen.JB_DRV_IVP_DENSE else 13)) + 3
+	"""registers while state + stages fit a thread's register file, else the tiled global workspace
+	(warp storage is chosen on top of this when the system vectorises well, see jitcode._module)."""
+	rows = _stage_rows(method, driver) + 3
 	return _codegen.JB_STORE_REGISTERS if rows * n <= 88 else _codegen.JB_STORE_GLOBAL
+
+
+def _warps_per_block(n, method, driver, table_bytes):
+	"""how many trajectories (warps) of a warp-storage module fit one SM's shared memory."""
+	rows = 2 + _stage_rows(method, driver) + (1 if driver == _codegen.JB_DRV_IVP_DENSE else 0)
+	return min(16, (SHARED_MEMORY_PER_BLOCK - table_bytes - 1024) // (rows * n * 8))
 
 
 class jitcode:
@@ -89,6 +104,7 @@ class jitcode:
 			if module.info.n != self.n:
 				raise ValueError("The module at module_location was compiled for a different dimension.")
 			self._modules[(module.info.method, module.info.driver, module.info.storage)] = module
+			self._modules[(module.info.method, module.info.driver, None)] = module
 		# layout constants of the module; the Lyapunov subclasses overwrite them
 		self._n_basic_module = self.n
 		self._n_lyap_module = 0
@@ -170,7 +186,7 @@ class jitcode:
 		if simplify:
 			f = [entry.simplify(ratio=1.0) for entry in f]
 		self._statements = _codegen.rhs_statements(f, self.helpers, self.control_pars, do_cse=do_cse)
-		self._modules = {}
+		self._modules = {key: module for key, module in self._modules.items() if key[2] == _codegen.JB_STORE_WARP}
 		self._f_module = None
 		self.report("generated CUDA code for f")
 
@@ -187,6 +203,8 @@ class jitcode:
 
 	def compile_cuda(self, extra_compile_args=None, extra_link_args=None, verbose=False, modulename=None, omp=None,
 			method=_codegen.JB_DP5, driver=_codegen.JB_DRV_ODE, storage=None, threads=None):
+		if isinstance(storage, str):
+			storage = STORAGE_BY_NAME[storage]
 		"""
 		Compiles (or fetches from the cache) and loads the module for one integrator configuration
 		(counterpart of compile_C, _jitcode.py:367-417).  `set_integrator` calls this itself.
@@ -204,21 +222,63 @@ class jitcode:
 
 	compile_C = compile_cuda
 
+	def _warp_plan(self):
+		"""the vectorised form of the right-hand side (None if it cannot be vectorised)."""
+		if not hasattr(self, "_plan"):
+			self._plan = None
+			if self._f_list and self._post == JB_POST_NONE:
+				try:
+					plan = _vectorise.make_plan(self._f_list, self.helpers, self.control_pars)
+					lines, tables = _vectorise.warp_statements(plan)
+					self._plan = (plan, lines, tables)
+				except NotImplementedError:
+					pass
+		return self._plan
+
+	def _choose_storage(self, method, driver):
+		storage = _storage_for(self.n, method, driver)
+		if storage == _codegen.JB_STORE_GLOBAL and self.n >= 64:
+			plan = self._warp_plan()
+			if plan is not None and plan[0].efficiency >= 0.5:
+				table_bytes = plan[2].nbytes
+				if _warps_per_block(self.n, method, driver, table_bytes) >= 2:
+					storage = _codegen.JB_STORE_WARP
+		return storage
+
 	def _module(self, method, driver, storage=None, threads=None):
 		if storage is None:
-			storage = _storage_for(self.n, method, driver)
+			if (method, driver, None) in self._modules:
+				return self._modules[(method, driver, None)]
+			storage = self._choose_storage(method, driver) if self._f_list else None
+			if storage is None:
+				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
 		key = (method, driver, storage) if threads is None else (method, driver, storage, threads)
 		if key not in self._modules:
-			if self._statements is None:
-				if not self._f_list:
-					raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
-				self.generate_f_cuda()
-			if threads is None:
-				threads = 128 if storage == _codegen.JB_STORE_REGISTERS else 64
+			if not self._f_list:
+				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
+			tables = None
+			if storage == _codegen.JB_STORE_WARP:
+				plan = self._warp_plan()
+				if plan is None:
+					raise NotImplementedError("This system cannot be vectorised for warp storage (or it has a Lyapunov post-step).")
+				self.check()
+				_, statements, tables = plan
+				if threads is None:
+					table_bytes = tables.nbytes
+					warps = _warps_per_block(self.n, method, driver, table_bytes)
+					if warps < 1:
+						raise ValueError("The system is too large for warp storage: one trajectory does not fit shared memory.")
+					threads = 32 * warps
+			else:
+				if self._statements is None:
+					self.generate_f_cuda()
+				statements = self._statements
+				if threads is None:
+					threads = 128 if storage == _codegen.JB_STORE_REGISTERS else 64
 			source = _codegen.module_source(
-				self._statements, self.n, len(self.control_pars),
+				statements, self.n, len(self.control_pars),
 				self._n_basic_module, self._n_lyap_module, self._tangent_indices_module,
-				method, driver, storage, threads,
+				method, driver, storage, threads, tables=tables,
 			)
 			path = _build.compile_module(
 				source, self._compile_options["extra_compile_args"], self._compile_options["extra_link_args"],
@@ -390,7 +450,7 @@ class jitcode:
 		else:
 			driver = _codegen.JB_DRV_IVP_DENSE if interpolate else _codegen.JB_DRV_IVP_LAND
 		if isinstance(storage, str):
-			storage = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL}[storage]
+			storage = STORAGE_BY_NAME[storage]
 		old_integrator = self.integrator
 		module = self._module(method, driver, storage, threads)   # compiling needs no GPU …
 		require_cuda(device)                                      # … running does

@@ -1,0 +1,400 @@
+"""
+SIMT-vectorising code generator for large systems ("warp" storage: one trajectory per warp, lanes
+across components).
+
+The reference prints one C statement per component (generate_f_C, _jitcode.py:186-249) and, for
+large systems, cuts them into chunks (chunk_size, :198-200) that a CPU executes one after the
+other.  A warp cannot run 32 different statements at once — but the equations of a network of
+identical units differ only in their numbers (ω_i, degree) and in which components they read.
+This module finds that structure:
+
+  1. every statement is brought into a canonical tree in which numeric constants and the indices
+     of dynamical variables are *slots*, the children of commutative operations are ordered by
+     shape, and — in sums — runs of equally shaped terms (neighbour sums Σ_j y(3j), Σ_j sin(y_j−y_i))
+     become a *loop* of variable length;
+  2. statements of equal shape form a group; per group the slot values go into tables (slots whose
+     value is the same for the whole group are printed as literals);
+  3. per group ONE code block is printed; lane ℓ evaluates statements ℓ, ℓ+32, … of the group,
+     fetching its numbers and indices from the tables (staged in shared memory by the kernel).
+
+Helpers (e.g. a mean field Σ_j y(3j+2)) are evaluated cooperatively: their loops are spread over
+the lanes and reduced with shuffles; the scalar rest is computed redundantly by every lane.
+
+`evaluate_plan` is a NumPy interpreter of the same plan, used by the CPU tests to check the
+vectoriser against direct evaluation of the symbolic input.
+"""
+
+from collections import OrderedDict
+
+import numpy as np
+import sympy
+from sympy.core.function import AppliedUndef
+
+from ._codegen import CudaPrinter, _repeated_function_calls
+
+LOOP_MIN = 3        # a run of at least this many equally shaped terms in a sum becomes a loop
+
+
+# ------------------------------------------------------------------ canonical trees
+
+class Node:
+	__slots__ = ("kind", "value", "children", "key", "has_loop")
+
+	def __init__(self, kind, value=None, children=()):
+		self.kind, self.value, self.children = kind, value, list(children)
+		self.has_loop = kind == "loop" or any(child.has_loop for child in self.children)
+		if kind == "const":
+			self.key = "C"
+		elif kind == "y":
+			self.key = "Y"
+		elif kind == "sym":
+			self.key = "S:" + value.name
+		elif kind == "loop":
+			self.key = "Loop[" + self.children[0].key + "]"
+		elif kind == "pow":
+			self.key = f"Pow({self.children[0].key};{sympy.srepr(value)})"
+		else:   # op
+			self.key = f"{value.__name__}(" + ",".join(child.key for child in self.children) + ")"
+
+
+def _is_dynvar(expr):
+	return isinstance(expr, AppliedUndef) and expr.func.__name__ == "y"
+
+
+def analyse(expr, allow_loops=True):
+	"""canonical tree of a SymPy expression."""
+	if expr.is_Number:
+		return Node("const", float(expr))
+	if _is_dynvar(expr):
+		return Node("y", int(expr.args[0]))
+	if expr.is_Symbol:
+		return Node("sym", expr)
+	if expr.is_Pow and expr.exp.is_Number:
+		return Node("pow", expr.exp, [analyse(expr.base, allow_loops)])
+	if expr.is_Add or expr.is_Mul:
+		children = sorted((analyse(arg, allow_loops) for arg in expr.args), key=lambda node: node.key)
+		if expr.is_Add and allow_loops:
+			runs = OrderedDict()
+			for child in children:
+				runs.setdefault(child.key, []).append(child)
+			children = []
+			for key, members in runs.items():
+				varying = "C" in key or "Y" in key
+				if len(members) >= LOOP_MIN and varying and not any(member.has_loop for member in members):
+					children.append(Node("loop", None, members))
+				else:
+					children.extend(members)
+			children.sort(key=lambda node: node.key)
+		return Node("op", expr.func, children)
+	if isinstance(expr, sympy.Function) or isinstance(expr, AppliedUndef):
+		return Node("op", expr.func, [analyse(arg, allow_loops) for arg in expr.args])
+	raise NotImplementedError(f"cannot vectorise {expr!r}")
+
+
+def slots(node, consts, indices, loops):
+	"""collects slot values in canonical order; loops get their own term-local slots."""
+	if node.kind == "const":
+		consts.append(node.value)
+	elif node.kind == "y":
+		indices.append(node.value)
+	elif node.kind == "loop":
+		terms = []
+		for member in node.children:
+			tc, ti = [], []
+			slots(member, tc, ti, None)
+			terms.append((tc, ti))
+		loops.append(terms)
+	else:
+		for child in node.children:
+			slots(child, consts, indices, loops)
+
+
+class SlotNames:
+	"""hands out placeholder symbols while a template expression is rebuilt from a canonical tree."""
+	def __init__(self, prefix):
+		self.prefix = prefix
+		self.n_const = self.n_index = self.n_loop = 0
+
+	def const(self):
+		self.n_const += 1
+		return sympy.Symbol(f"{self.prefix}c{self.n_const-1}")
+
+	def index(self):
+		self.n_index += 1
+		return sympy.Symbol(f"{self.prefix}i{self.n_index-1}", integer=True)
+
+	def loop(self):
+		self.n_loop += 1
+		return sympy.Symbol(f"{self.prefix}l{self.n_loop-1}")
+
+
+Y = sympy.Function("y")
+
+def template(node, names, loop_templates):
+	"""SymPy expression with placeholders for the slots; loop bodies are appended to loop_templates."""
+	if node.kind == "const":
+		return names.const()
+	if node.kind == "y":
+		return Y(names.index())
+	if node.kind == "sym":
+		return node.value
+	if node.kind == "loop":
+		symbol = names.loop()
+		term_names = SlotNames(f"{symbol.name}_t")
+		loop_templates.append((symbol, template(node.children[0], term_names, None), term_names))
+		return symbol
+	if node.kind == "pow":
+		return sympy.Pow(template(node.children[0], names, loop_templates), node.value)
+	return node.value(*[template(child, names, loop_templates) for child in node.children])
+
+
+# ------------------------------------------------------------------ the plan
+
+class Loop:
+	def __init__(self, symbol, body, names):
+		self.symbol, self.body = symbol, body
+		self.n_const, self.n_index = names.n_const, names.n_index
+		self.prefix = names.prefix
+		self.start = [0]                               # prefix sums over the statements of the group
+		self.consts = [[] for _ in range(self.n_const)]    # per slot: one value per term
+		self.indices = [[] for _ in range(self.n_index)]
+
+
+class Group:
+	"""statements of one shape."""
+	def __init__(self, key, node, prefix):
+		self.key = key
+		names = SlotNames(prefix)
+		loop_templates = []
+		self.body = template(node, names, loop_templates)
+		self.prefix = prefix
+		self.n_const, self.n_index = names.n_const, names.n_index
+		self.loops = [Loop(*item) for item in loop_templates]
+		self.outs = []
+		self.consts = [[] for _ in range(self.n_const)]
+		self.indices = [[] for _ in range(self.n_index)]
+
+	def add(self, out, node):
+		consts, indices, loops = [], [], []
+		slots(node, consts, indices, loops)
+		assert len(consts) == self.n_const and len(indices) == self.n_index and len(loops) == len(self.loops)
+		self.outs.append(out)
+		for slot, value in zip(self.consts, consts):
+			slot.append(value)
+		for slot, value in zip(self.indices, indices):
+			slot.append(value)
+		for loop, terms in zip(self.loops, loops):
+			for tc, ti in terms:
+				assert len(tc) == loop.n_const and len(ti) == loop.n_index
+				for slot, value in zip(loop.consts, tc):
+					slot.append(value)
+				for slot, value in zip(loop.indices, ti):
+					slot.append(value)
+			loop.start.append(loop.start[-1] + len(terms))
+
+	@property
+	def size(self):
+		return len(self.outs)
+
+
+class Plan:
+	"""everything the code printer and the NumPy interpreter need."""
+	def __init__(self, n, n_params):
+		self.n, self.n_params = n, n_params
+		self.temporaries = []       # (symbol, expression): repeated function calls, uniform over the warp
+		self.helpers = []           # (symbol, Group of size 1)
+		self.groups = []
+
+	@property
+	def lane_passes(self):
+		return sum((group.size + 31) // 32 for group in self.groups)
+
+	@property
+	def efficiency(self):
+		"""fraction of lane slots doing useful work."""
+		return self.n / (32.0 * max(1, self.lane_passes))
+
+
+def make_plan(f, helpers, control_pars):
+	"""f: list of expressions; helpers: sorted (symbol, definition) pairs; control_pars: symbols."""
+	subs = {par: sympy.Symbol(f"par.v[{k}]") for k, par in enumerate(control_pars)}
+	for k, (symbol, _) in enumerate(helpers):
+		subs[symbol] = sympy.Symbol(f"jb_helper_{k}")
+	helper_defs = [definition.xreplace(subs) for _, definition in helpers]
+	f = [entry.xreplace(subs) for entry in f]
+	everything = helper_defs + f
+	plan = Plan(len(f), len(control_pars))
+	for k, call in enumerate(_repeated_function_calls(everything)):
+		symbol = sympy.Symbol(f"jb_call_{k}")
+		everything = [expr.xreplace({call: symbol}) for expr in everything]
+		plan.temporaries = [(s, d.xreplace({call: symbol})) for s, d in plan.temporaries]
+		plan.temporaries.append((symbol, call))
+	helper_defs, f = everything[:len(helpers)], everything[len(helpers):]
+	for k, definition in enumerate(helper_defs):
+		node = analyse(sympy.sympify(definition))
+		group = Group(node.key, node, f"jb_h{k}_")
+		group.add(-1, node)
+		plan.helpers.append((sympy.Symbol(f"jb_helper_{k}"), group))
+	groups = OrderedDict()
+	for i, entry in enumerate(f):
+		node = analyse(sympy.sympify(entry))
+		if node.key not in groups:
+			groups[node.key] = Group(node.key, node, f"jb_g{len(groups)}_")
+		groups[node.key].add(i, node)
+	plan.groups = list(groups.values())
+	return plan
+
+
+# ------------------------------------------------------------------ NumPy interpreter (test infrastructure for the plan)
+
+def evaluate_plan(plan, t, state, pars=()):
+	"""dY = f(t, state) computed by walking the plan the way the generated kernel does."""
+	state = np.asarray(state, dtype=float)
+	scalars = {sympy.Symbol("t", real=True): float(t)}
+	for k, value in enumerate(pars):
+		scalars[sympy.Symbol(f"par.v[{k}]")] = float(value)
+
+	def run(body, names, consts, indices, loops):
+		values = dict(scalars)
+		for c, value in enumerate(consts):
+			values[sympy.Symbol(f"{names}c{c}")] = value
+		expr = body
+		for i, index in enumerate(indices):
+			expr = expr.xreplace({Y(sympy.Symbol(f"{names}i{i}", integer=True)): sympy.Float(state[index])})
+		for symbol, total in loops:
+			values[symbol] = total
+		return float(expr.xreplace({k: sympy.Float(v) for k, v in values.items()}))
+
+	def run_group(group, m):
+		loops = []
+		for loop in group.loops:
+			total = 0.0
+			for k in range(loop.start[m], loop.start[m+1]):
+				total += run(loop.body, loop.prefix, [slot[k] for slot in loop.consts], [slot[k] for slot in loop.indices], [])
+			loops.append((loop.symbol, total))
+		return run(group.body, group.prefix, [slot[m] for slot in group.consts], [slot[m] for slot in group.indices], loops)
+
+	pending = list(plan.temporaries)
+	def flush():
+		progress = True
+		while progress:
+			progress = False
+			for symbol, definition in list(pending):
+				expr = definition
+				for atom in definition.atoms(AppliedUndef):
+					if _is_dynvar(atom):
+						expr = expr.xreplace({atom: sympy.Float(state[int(atom.args[0])])})
+				expr = expr.xreplace({k: sympy.Float(v) for k, v in scalars.items()})
+				if not expr.free_symbols:
+					scalars[symbol] = float(expr)
+					pending.remove((symbol, definition))
+					progress = True
+	flush()
+	for symbol, group in plan.helpers:
+		scalars[symbol] = run_group(group, 0)
+		flush()
+	out = np.empty(plan.n)
+	for group in plan.groups:
+		for m, i in enumerate(group.outs):
+			out[i] = run_group(group, m)
+	return out
+
+
+# ------------------------------------------------------------------ printing
+
+class Tables:
+	"""two flat tables (doubles, unsigned integers) that the kernel stages in shared memory."""
+	def __init__(self):
+		self.f64, self.u = [], []
+
+	def add_f64(self, values):
+		offset = len(self.f64)
+		self.f64.extend(float(v) for v in values)
+		return offset
+
+	def add_u(self, values):
+		offset = len(self.u)
+		self.u.extend(int(v) for v in values)
+		return offset
+
+	@property
+	def nbytes(self):
+		index_bytes = 2 if (not self.u or max(self.u) < 65536) else 4
+		return 8 * len(self.f64) + (index_bytes * len(self.u) + 7) // 8 * 8
+
+
+def _uniform(values):
+	return len(values) > 0 and all(v == values[0] for v in values)
+
+
+def _slot_preamble(printer, prefix, consts, indices, tables, position, lines, indent):
+	"""declares every slot of one statement (or loop term) as a local: literal if uniform, table read otherwise."""
+	for c, values in enumerate(consts):
+		if _uniform(values):
+			lines.append(f"{indent}const double {prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
+		else:
+			lines.append(f"{indent}const double {prefix}c{c} = JB_TF[{tables.add_f64(values)} + {position}];")
+	for i, values in enumerate(indices):
+		if _uniform(values):
+			lines.append(f"{indent}const int {prefix}i{i} = {values[0]};")
+		else:
+			lines.append(f"{indent}const int {prefix}i{i} = JB_TU[{tables.add_u(values)} + {position}];")
+
+
+def warp_statements(plan):
+	"""returns (lines of the body of Sys::rhs_warp, Tables)."""
+	printer = CudaPrinter()
+	tables = Tables()
+	lines = []
+
+	emitted = set()
+	pending = list(plan.temporaries)
+	helper_symbols = {symbol for symbol, _ in plan.helpers}
+	def flush():
+		progress = True
+		while progress:
+			progress = False
+			for item in list(pending):
+				needs = {s for s in item[1].free_symbols if s in helper_symbols or s.name.startswith("jb_call_")}
+				if needs <= emitted:
+					lines.append(f"const double {item[0].name} = {printer.doprint(item[1])};")
+					emitted.add(item[0])
+					pending.remove(item)
+					progress = True
+	flush()
+
+	# helpers: loops spread over the lanes and reduced, the rest redundantly on every lane
+	for symbol, group in plan.helpers:
+		lines.append("{")
+		for loop in group.loops:
+			count = loop.start[1]
+			lines.append(f"\tdouble {loop.symbol.name}_acc = 0.0;")
+			lines.append(f"\tfor (int k = lane; k < {count}; k += 32) {{")
+			_slot_preamble(printer, loop.prefix, loop.consts, loop.indices, tables, "k", lines, "\t\t")
+			lines.append(f"\t\t{loop.symbol.name}_acc += {printer.doprint(loop.body)};")
+			lines.append("\t}")
+			lines.append(f"\tconst double {loop.symbol.name} = jb::warp_sum({loop.symbol.name}_acc);")
+		_slot_preamble(printer, group.prefix, group.consts, group.indices, tables, "0", lines, "\t")
+		lines.append(f"\t{symbol.name} = {printer.doprint(group.body)};")
+		lines.append("}")
+		emitted.add(symbol)
+		flush()
+	assert not pending, "unresolvable temporaries"
+
+	for g, group in enumerate(plan.groups):
+		out_offset = None if group.size == 1 else tables.add_u(group.outs)
+		lines.append(f"// group {g}: {group.size} statement(s)")
+		lines.append(f"for (int m = lane; m < {group.size}; m += 32) {{")
+		for loop in group.loops:
+			start = tables.add_u(loop.start)
+			lines.append(f"\tdouble {loop.symbol.name} = 0.0;")
+			lines.append(f"\tfor (int k = JB_TU[{start} + m], k_end = JB_TU[{start} + m + 1]; k < k_end; ++k) {{")
+			_slot_preamble(printer, loop.prefix, loop.consts, loop.indices, tables, "k", lines, "\t\t")
+			lines.append(f"\t\t{loop.symbol.name} += {printer.doprint(loop.body)};")
+			lines.append("\t}")
+		_slot_preamble(printer, group.prefix, group.consts, group.indices, tables, "m", lines, "\t")
+		target = str(group.outs[0]) if out_offset is None else f"JB_TU[{out_offset} + m]"
+		lines.append(f"\tdy.set({target}, {printer.doprint(group.body)});")
+		lines.append("}")
+	helper_declarations = [f"double {symbol.name};" for symbol, _ in plan.helpers]
+	return helper_declarations + lines, tables

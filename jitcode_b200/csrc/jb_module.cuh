@@ -4,8 +4,10 @@
 //   struct jb_generated::Sys   N, NP, NB, NL, NT, Par, rhs(t, y, dy, par), tangent_index(k)
 //   JB_MODULE_METHOD           JB_DP5 | JB_DOP853
 //   JB_MODULE_DRIVER           JB_DRV_ODE | JB_DRV_IVP_DENSE | JB_DRV_IVP_LAND
-//   JB_MODULE_STORAGE          JB_STORE_REGISTERS | JB_STORE_GLOBAL
+//   JB_MODULE_STORAGE          JB_STORE_REGISTERS | JB_STORE_GLOBAL | JB_STORE_WARP
 //   JB_MODULE_THREADS          threads per block of the integrate kernel
+// and, for JB_STORE_WARP, the tables of the vectorised right-hand side: jb_generated::jb_tf (doubles),
+// jb_generated::jb_tu (unsigned indices of type Sys::TU), Sys::TF_COUNT, Sys::TU_COUNT.
 // It replaces the module table and entry points of the reference's jitced_template.c:213-240.
 #pragma once
 
@@ -19,36 +21,98 @@ namespace jb {
 
 using Sys = jb_generated::Sys;
 using Tab = std::conditional<JB_MODULE_METHOD == JB_DP5, DP5, DOP853>::type;
-constexpr bool MODULE_REG = JB_MODULE_STORAGE == JB_STORE_REGISTERS;
+constexpr int MODULE_MODE = JB_MODULE_STORAGE;
+constexpr bool MODULE_REG = MODULE_MODE == JB_STORE_REGISTERS;
+constexpr bool MODULE_WARP = MODULE_MODE == JB_STORE_WARP;
 using ModuleLayout = Layout<Tab, JB_MODULE_DRIVER>;
 
+// ---- warp storage: shared memory of a block = [tables of the right-hand side][stage vectors of warp 0][of warp 1]…
+template <class S, bool W> struct WarpShared {
+	static constexpr int TABLE_DOUBLES = 0, ROWS = 0, WARPS = 1;
+	static constexpr size_t BYTES = 0, EVAL_BYTES = 0;
+};
+template <class S> struct WarpShared<S, true> {
+	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) ((S::TU_COUNT * sizeof(typename S::TU) + 7) / 8);
+	static constexpr int ROWS = 2 + ModuleLayout::KR + (ModuleLayout::DENSE ? 1 : 0);     // Y, Z, K rows, y_old
+	static constexpr int WARPS = JB_MODULE_THREADS / 32;
+	static constexpr size_t BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * ROWS * S::N);
+	static constexpr size_t EVAL_BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * 2 * S::N);
+};
+using Shared = WarpShared<Sys, MODULE_WARP>;
+
+template <class S>
+__device__ __forceinline__ void stage_tables(double *smem)
+{
+	for (int i = threadIdx.x; i < S::TF_COUNT; i += blockDim.x) smem[i] = jb_generated::jb_tf[i];
+	typename S::TU *tu = reinterpret_cast<typename S::TU *>(smem + S::TF_COUNT);
+	for (int i = threadIdx.x; i < S::TU_COUNT; i += blockDim.x) tu[i] = jb_generated::jb_tu[i];
+	__syncthreads();
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(JB_MODULE_THREADS)
 jb_integrate_kernel(const __grid_constant__ Params a)
 {
-	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= a.B) return;
-	run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODULE_REG>(a, b);
+	if constexpr (MODE == JB_STORE_WARP) {
+		// persistent blocks; every warp integrates trajectories b, b + (warps in the grid), …
+		extern __shared__ __align__(16) double jb_smem[];
+		stage_tables<Sys>(jb_smem);
+		const int warp = threadIdx.x >> 5;
+		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * Shared::ROWS * Sys::N;
+		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
+		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < a.B; b += stride) {
+			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b, mine, jb_smem);
+			__syncwarp();
+		}
+	} else {
+		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+		if (b >= a.B) return;
+		run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b);
+	}
 }
 
 // dY = f(t, Y): the batched counterpart of py_f (jitced_template.c:67-116)
+template <int MODE>
 __global__ void __launch_bounds__(JB_MODULE_THREADS)
 jb_eval_f_kernel(const double *t, const double *Y, const double *P, double *dY, int64_t B)
 {
-	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= B) return;
-	Sys::Par par;
+	if constexpr (MODE == JB_STORE_WARP) {
+		extern __shared__ __align__(16) double jb_smem[];
+		stage_tables<Sys>(jb_smem);
+		const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+		double *const in = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * 2 * Sys::N;
+		double *const out = in + Sys::N;
+		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
+		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < B; b += stride) {
+			Sys::Par par;
 #pragma unroll
-	for (int k = 0; k < Sys::NP; ++k) par.v[k] = P[tile_offset(b, Sys::NP) + k * TILE];
-	const int64_t off = tile_offset(b, Sys::N);
-	if constexpr (MODULE_REG) {
-		RVec<Sys::N> y, dy;
-#pragma unroll
-		for (int i = 0; i < Sys::N; ++i) y.v[i] = Y[off + i * TILE];
-		Sys::rhs(t[b], y, dy, par);
-#pragma unroll
-		for (int i = 0; i < Sys::N; ++i) dY[off + i * TILE] = dy.v[i];
+			for (int k = 0; k < Sys::NP; ++k) par.v[k] = P[b * Sys::NP + k];
+			for (int i = lane; i < Sys::N; i += 32) in[i] = Y[b * Sys::N + i];
+			const SVec vin{in};
+			SVec vout{out};
+			RhsCall<Sys, MODE>::call(t[b], vin, vout, par, jb_smem);
+			for (int i = lane; i < Sys::N; i += 32) dY[b * Sys::N + i] = out[i];
+			__syncwarp();
+		}
 	} else {
-		rhs_outlined<Sys>(t[b], Y + off, dY + off, par);
+		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+		if (b >= B) return;
+		Sys::Par par;
+#pragma unroll
+		for (int k = 0; k < Sys::NP; ++k) par.v[k] = P[tile_offset(b, Sys::NP) + k * TILE];
+		const int64_t off = tile_offset(b, Sys::N);
+		if constexpr (MODE == JB_STORE_REGISTERS) {
+			RVec<Sys::N> y, dy;
+#pragma unroll
+			for (int i = 0; i < Sys::N; ++i) y.v[i] = Y[off + i * TILE];
+			RhsCall<Sys, MODE>::call(t[b], y, dy, par, nullptr);
+#pragma unroll
+			for (int i = 0; i < Sys::N; ++i) dY[off + i * TILE] = dy.v[i];
+		} else {
+			const GVec in{const_cast<double *>(Y) + off};
+			GVec out{dY + off};
+			RhsCall<Sys, MODE>::call(t[b], in, out, par, nullptr);
+		}
 	}
 }
 
@@ -109,6 +173,23 @@ static int fail(int code, const char *what)
 	return code;
 }
 
+// persistent grid of the warp-storage kernels: one block per SM (its warps share the staged tables)
+static int warp_grid(int64_t B, size_t shared_bytes, const void *kernel, int *blocks)
+{
+	static int sm_count = 0;
+	if (sm_count == 0) {
+		int device = 0;
+		cudaError_t err = cudaGetDevice(&device);
+		if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+		if (err != cudaSuccess) return fail((int) err, "querying the device");
+	}
+	const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared_bytes);
+	if (err != cudaSuccess) return fail((int) err, "reserving shared memory");
+	const int64_t needed = (B + Shared::WARPS - 1) / Shared::WARPS;
+	*blocks = (int) (needed < sm_count ? needed : sm_count);
+	return 0;
+}
+
 static int launched(const char *what)
 {
 	launch_counter.fetch_add(1, std::memory_order_relaxed);
@@ -141,18 +222,25 @@ int jb_get_info(jb_module_info *info)
 	info->storage = JB_MODULE_STORAGE;
 	info->state_vectors = jb::ModuleLayout::STATE_VECTORS;
 	info->state_scalars = jb::ModuleLayout::STATE_SCALARS;
-	info->work_vectors = jb::MODULE_REG ? 0 : jb::ModuleLayout::WORK_VECTORS;
+	info->work_vectors = jb::MODULE_MODE == JB_STORE_GLOBAL ? jb::ModuleLayout::WORK_VECTORS : 0;
 	info->threads_per_block = JB_MODULE_THREADS;
+	info->shared_bytes = (int32_t) jb::Shared::BYTES;
 	return 0;
 }
 
 int jb_eval_f(const double *t, const double *Y, const double *P, double *dY, int64_t B, int64_t ld, void *stream)
 {
 	if (B <= 0) return 0;
-	if (!t || !Y || !dY || (jb::Sys::NP > 0 && !P) || ld < B || ld % JB_TILE)
+	if (!t || !Y || !dY || (jb::Sys::NP > 0 && !P) || ld < B || (!jb::MODULE_WARP && ld % JB_TILE))
 		return jb::fail(JB_E_BAD_ARGUMENT, "jb_eval_f: bad argument");
+	if (jb::MODULE_WARP) {
+		int blocks = 0;
+		if (const int err = jb::warp_grid(B, jb::Shared::EVAL_BYTES, (const void *) jb::jb_eval_f_kernel<jb::MODULE_MODE>, &blocks)) return err;
+		jb::jb_eval_f_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, jb::Shared::EVAL_BYTES, (cudaStream_t) stream>>>(t, Y, P, dY, B);
+		return jb::launched("jb_eval_f");
+	}
 	const unsigned blocks = (unsigned) ((B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);
-	jb::jb_eval_f_kernel<<<blocks, JB_MODULE_THREADS, 0, (cudaStream_t) stream>>>(t, Y, P, dY, B);
+	jb::jb_eval_f_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, 0, (cudaStream_t) stream>>>(t, Y, P, dY, B);
 	return jb::launched("jb_eval_f");
 }
 
@@ -161,14 +249,16 @@ int jb_integrate(const jb_integrate_args *x)
 	if (!x || x->struct_size != sizeof(jb_integrate_args))
 		return jb::fail(JB_E_ABI, "jb_integrate: argument block has the wrong size (ABI mismatch)");
 	if (x->B <= 0 || x->n_times <= 0) return 0;
-	if (x->ld < x->B || x->ld % JB_TILE || !x->times || !x->t || !x->Y || !x->status
+	if (x->ld < x->B || (!jb::MODULE_WARP && x->ld % JB_TILE) || !x->times || !x->t || !x->Y || !x->status
 			|| (jb::Sys::NP > 0 && !x->P)
 			|| (jb::ModuleLayout::STATE_VECTORS > 0 && !x->state)
 			|| (jb::ModuleLayout::STATE_SCALARS > 0 && !x->sstate)
-			|| (!jb::MODULE_REG && !x->work)
+			|| (jb::MODULE_MODE == JB_STORE_GLOBAL && !x->work)
 			|| (jb::ModuleLayout::DENSE && !x->Yres))
 		return jb::fail(JB_E_BAD_ARGUMENT, "jb_integrate: missing or inconsistent buffers");
 	if (x->post != JB_POST_NONE) {
+		if (jb::MODULE_WARP)
+			return jb::fail(JB_E_UNSUPPORTED, "jb_integrate: Lyapunov post-steps are not available with warp storage");
 		if (jb::Sys::NL <= 0 || (x->post == JB_POST_LYAP_TRANSVERSAL && jb::Sys::NT <= 0)
 				|| (x->post == JB_POST_LYAP_RESTRICTED && (jb::Sys::NL != 1 || (x->n_proj > 0 && !x->proj))))
 			return jb::fail(JB_E_UNSUPPORTED, "jb_integrate: this module has no tangent vectors for the requested post-step");
@@ -201,15 +291,26 @@ int jb_integrate(const jb_integrate_args *x)
 	a.Yres = x->Yres; a.Yrec = x->Yrec; a.lyap_rec = x->lyap_rec; a.lyap_acc = x->lyap_acc;
 	a.proj = x->proj;
 	a.status = x->status; a.n_accepted = x->n_accepted; a.n_rejected = x->n_rejected;
+	if (jb::MODULE_WARP) {
+		int blocks = 0;
+		if (const int err = jb::warp_grid(x->B, jb::Shared::BYTES, (const void *) jb::jb_integrate_kernel<jb::MODULE_MODE>, &blocks)) return err;
+		jb::jb_integrate_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, jb::Shared::BYTES, (cudaStream_t) x->stream>>>(a);
+		return jb::launched("jb_integrate");
+	}
 	const unsigned blocks = (unsigned) ((x->B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);
-	jb::jb_integrate_kernel<<<blocks, JB_MODULE_THREADS, 0, (cudaStream_t) x->stream>>>(a);
+	jb::jb_integrate_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, 0, (cudaStream_t) x->stream>>>(a);
 	return jb::launched("jb_integrate");
 }
 
 int jb_pack(const double *rows, double *tiled, int64_t B, int64_t n, int64_t ld, void *stream)
 {
 	if (B <= 0 || n <= 0) return 0;
-	if (!rows || !tiled || ld < B || ld % JB_TILE) return jb::fail(JB_E_BAD_ARGUMENT, "jb_pack: bad argument");
+	if (!rows || !tiled || ld < B || (!jb::MODULE_WARP && ld % JB_TILE)) return jb::fail(JB_E_BAD_ARGUMENT, "jb_pack: bad argument");
+	if (jb::MODULE_WARP) {      // row layout: the reference's own
+		jb::launch_counter.fetch_add(1, std::memory_order_relaxed);
+		const cudaError_t err = cudaMemcpyAsync(tiled, rows, sizeof(double) * B * n, cudaMemcpyDeviceToDevice, (cudaStream_t) stream);
+		return err == cudaSuccess ? 0 : jb::fail((int) err, "jb_pack");
+	}
 	jb::jb_pack_kernel<<<(unsigned) (ld / JB_TILE), 256, 0, (cudaStream_t) stream>>>(rows, tiled, B, n);
 	return jb::launched("jb_pack");
 }
@@ -217,7 +318,12 @@ int jb_pack(const double *rows, double *tiled, int64_t B, int64_t n, int64_t ld,
 int jb_unpack(const double *tiled, double *rows, int64_t B, int64_t n, int64_t ld, void *stream)
 {
 	if (B <= 0 || n <= 0) return 0;
-	if (!rows || !tiled || ld < B || ld % JB_TILE) return jb::fail(JB_E_BAD_ARGUMENT, "jb_unpack: bad argument");
+	if (!rows || !tiled || ld < B || (!jb::MODULE_WARP && ld % JB_TILE)) return jb::fail(JB_E_BAD_ARGUMENT, "jb_unpack: bad argument");
+	if (jb::MODULE_WARP) {
+		jb::launch_counter.fetch_add(1, std::memory_order_relaxed);
+		const cudaError_t err = cudaMemcpyAsync(rows, tiled, sizeof(double) * B * n, cudaMemcpyDeviceToDevice, (cudaStream_t) stream);
+		return err == cudaSuccess ? 0 : jb::fail((int) err, "jb_unpack");
+	}
 	jb::jb_unpack_kernel<<<(unsigned) (ld / JB_TILE), 256, 0, (cudaStream_t) stream>>>(tiled, rows, B, n);
 	return jb::launched("jb_unpack");
 }

@@ -16,9 +16,15 @@
 // launch; memory is laid out in trajectory-minor tiles of 32 (one tile = one warp), so that every
 // global access of a warp is one contiguous 256-byte segment at a compile-time offset from a
 // per-thread base pointer (no address arithmetic in the generated code).
-//   REG  = true : y and all stages live in registers for the whole launch (small systems, FP64-pipe bound);
-//   REG  = false: they live in a caller-provided workspace (large systems, HBM/L2 bound); buffers are
-//                 rotated by pointer instead of copied.
+//   JB_STORE_REGISTERS  thread per trajectory; y and all stages live in registers for the whole launch
+//                       (small systems, FP64-pipe bound);
+//   JB_STORE_GLOBAL     thread per trajectory; they live in a caller-provided tiled workspace
+//                       (mid-size or irregular systems, HBM/L2 bound); buffers rotate by pointer swap;
+//   JB_STORE_WARP       WARP per trajectory, lanes across components; y and all stages live in shared
+//                       memory for the whole launch, the right-hand side is the vectorised form printed
+//                       by _vectorise.py, norms are shuffle reductions, and every control decision is
+//                       warp-uniform — no divergence between trajectories and no HBM traffic between
+//                       the first and the last sample time (large regular networks).
 #pragma once
 
 #include <cstdint>
@@ -47,6 +53,19 @@ struct GVec {               // one trajectory's column of a tile: element i at p
 	__device__ __forceinline__ void set(int i, double x) const { p[i * TILE] = x; }
 };
 
+struct SVec {               // contiguous vector: shared memory (warp storage) or one row of a (B, n) global array
+	double *p;
+	__device__ __forceinline__ double operator()(int i) const { return p[i]; }
+	__device__ __forceinline__ void set(int i, double x) const { p[i] = x; }
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int offset = 16; offset > 0; offset >>= 1) v += __shfl_xor_sync(0xffffffffu, v, offset);
+	return v;
+}
+
 // dst takes the value of src; src becomes scratch (registers: copy; global: pointer swap)
 template <int N>
 __device__ __forceinline__ void take(RVec<N> &dst, RVec<N> &src)
@@ -55,6 +74,12 @@ __device__ __forceinline__ void take(RVec<N> &dst, RVec<N> &src)
 	for (int i = 0; i < N; ++i) dst.v[i] = src.v[i];
 }
 __device__ __forceinline__ void take(GVec &dst, GVec &src)
+{
+	double *const p = dst.p;
+	dst.p = src.p;
+	src.p = p;
+}
+__device__ __forceinline__ void take(SVec &dst, SVec &src)
 {
 	double *const p = dst.p;
 	dst.p = src.p;
@@ -111,12 +136,12 @@ template <class Tab, int DRIVER> struct Layout {
 	static constexpr int WORK_VECTORS = 1 + KR + (DENSE ? 1 : 0);   // Z, K rows, y_old
 };
 
-template <class Sys, bool REG> struct RhsCall;
+template <class Sys, int MODE> struct RhsCall;
 
 // registers: the right-hand side is inlined at every call site
-template <class Sys> struct RhsCall<Sys, true> {
+template <class Sys> struct RhsCall<Sys, JB_STORE_REGISTERS> {
 	template <class VI, class VO>
-	static __device__ __forceinline__ void call(double t, const VI &in, VO &out, const typename Sys::Par &par)
+	static __device__ __forceinline__ void call(double t, const VI &in, VO &out, const typename Sys::Par &par, const void *)
 	{
 		Sys::rhs(t, in, out, par);
 	}
@@ -130,49 +155,117 @@ __device__ __noinline__ void rhs_outlined(double t, const double *__restrict__ i
 	GVec vo{out};
 	Sys::rhs(t, vi, vo, par);
 }
-template <class Sys> struct RhsCall<Sys, false> {
-	static __device__ __forceinline__ void call(double t, const GVec &in, GVec &out, const typename Sys::Par &par)
+template <class Sys> struct RhsCall<Sys, JB_STORE_GLOBAL> {
+	static __device__ __forceinline__ void call(double t, const GVec &in, GVec &out, const typename Sys::Par &par, const void *)
 	{
 		rhs_outlined<Sys>(t, in.p, out.p, par);
 	}
 };
+// warp: one out-of-line copy of the vectorised right-hand side; lanes read what other lanes wrote
+template <class Sys>
+__device__ __noinline__ void rhs_warp_outlined(double t, const double *__restrict__ in, double *__restrict__ out,
+		const typename Sys::Par par, const void *tables)
+{
+	__syncwarp();
+	const SVec vi{const_cast<double *>(in)};
+	SVec vo{out};
+	Sys::rhs_warp(t, vi, vo, par, (int) (threadIdx.x & 31), tables);
+	__syncwarp();
+}
+template <class Sys> struct RhsCall<Sys, JB_STORE_WARP> {
+	static __device__ __forceinline__ void call(double t, const SVec &in, SVec &out, const typename Sys::Par &par, const void *tables)
+	{
+		rhs_warp_outlined<Sys>(t, in.p, out.p, par, tables);
+	}
+};
 
-template <class Sys, class Tab, int DRIVER, bool REG>
+// How the components of a vector are spread over threads: all of them on this thread (registers,
+// global) or strided over the lanes of the warp (warp storage).
+template <int N, int MODE> struct Components {
+	static constexpr bool WARP = MODE == JB_STORE_WARP;
+	static constexpr int UNR = MODE == JB_STORE_REGISTERS ? (N > 0 ? N : 1) : 4;
+
+	template <class F>
+	static __device__ __forceinline__ void for_each(F &&body)
+	{
+		if constexpr (WARP) {
+			for (int i = threadIdx.x & 31; i < N; i += 32) body(i);
+		} else {
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) body(i);
+		}
+	}
+
+	// Σ_i value(i), known to every thread that works on the trajectory
+	template <class F>
+	static __device__ __forceinline__ double sum(F &&value)
+	{
+		double total = 0.0;
+		if constexpr (WARP) {
+			for (int i = threadIdx.x & 31; i < N; i += 32) total += value(i);
+			return warp_sum(total);
+		} else {
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) total += value(i);
+			return total;
+		}
+	}
+
+	// two sums in one pass: value(i, s0, s1) adds its contributions
+	template <class F>
+	static __device__ __forceinline__ void sum2(F &&value, double &s0, double &s1)
+	{
+		s0 = s1 = 0.0;
+		if constexpr (WARP) {
+			for (int i = threadIdx.x & 31; i < N; i += 32) value(i, s0, s1);
+			s0 = warp_sum(s0);
+			s1 = warp_sum(s1);
+		} else {
+#pragma unroll UNR
+			for (int i = 0; i < N; ++i) value(i, s0, s1);
+		}
+	}
+};
+
+template <class Sys, class Tab, int DRIVER, int MODE>
 struct Stepper {
 	static constexpr int N = Sys::N;
 	using L = Layout<Tab, DRIVER>;
+	using C = Components<N, MODE>;
+	static constexpr bool REG = MODE == JB_STORE_REGISTERS;
+	static constexpr bool WARP = MODE == JB_STORE_WARP;
 	static constexpr bool DENSE = L::DENSE;
 	static constexpr bool IVP = L::IVP;
 	static constexpr int KR = L::KR;
 	static constexpr int S = Tab::NSTAGE;
-	static constexpr int UNR = REG ? (N > 0 ? N : 1) : 4;   // unroll factor of component loops
-	using Vec = typename std::conditional<REG, RVec<N>, GVec>::type;
+	using Vec = typename std::conditional<REG, RVec<N>, typename std::conditional<WARP, SVec, GVec>::type>::type;
+	using CVec = typename std::conditional<WARP, SVec, GVec>::type;    // caller-visible (canonical) vectors
 
 	Vec Y, Z, YO, K[KR];
 	typename Sys::Par par;
 	double atol_s, rtol;
 	const double *atol_vec;
+	const void *tables;
 
 	__device__ __forceinline__ double atol(int i) const { return atol_vec ? atol_vec[i] : atol_s; }
 
 	__device__ __forceinline__ void rhs(double t, const Vec &in, Vec &out)
 	{
-		RhsCall<Sys, REG>::call(t, in, out, par);
+		RhsCall<Sys, MODE>::call(t, in, out, par, tables);
 	}
 
 	// dst = Y + h * Σ_{j<ROW} a(ROW,j) K[j]   (stage input for ROW < S, solution for ROW == S)
 	template <int ROW>
 	__device__ __forceinline__ void combine(Vec &dst, double h)
 	{
-#pragma unroll UNR
-		for (int i = 0; i < N; ++i) {
+		C::for_each([&](int i) {
 			double acc = 0.0;
 			static_for<0, ROW>([&](auto j) {
 				constexpr double a = Coef<Tab>::a(ROW, j);
 				if constexpr (a != 0.0) acc = fma(a, K[j](i), acc);
 			});
 			dst.set(i, fma(h, acc, Y(i)));
-		}
+		});
 	}
 
 	// one step attempt from (t, Y, K[0]) with step h: fills K[1..], Z = y_new; returns the error norm
@@ -186,9 +279,7 @@ struct Stepper {
 		combine<S>(Z, h);
 		if constexpr (Tab::ERR_NEEDS_FSAL) {
 			rhs(t + h, Z, K[S]);
-			double sum = 0.0;
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) {
+			const double sum = C::sum([&](int i) {
 				double e = 0.0;
 				static_for<0, Tab::KROWS>([&](auto j) {
 					constexpr double w = DP5::E[j];
@@ -196,13 +287,12 @@ struct Stepper {
 				});
 				const double sk = fma(rtol, fmax(fabs(Y(i)), fabs(Z(i))), atol(i));
 				const double q = h * e / sk;
-				sum = fma(q, q, sum);
-			}
+				return q * q;
+			});
 			return sqrt(sum / N);
 		} else {
-			double s5 = 0.0, s3 = 0.0;
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) {
+			double s5, s3;
+			C::sum2([&](int i, double &a5, double &a3) {
 				double e5 = 0.0, e3 = 0.0;
 				static_for<0, S>([&](auto j) {
 					constexpr double w5 = dop853::E5[j];
@@ -213,9 +303,9 @@ struct Stepper {
 				const double sk = fma(rtol, fmax(fabs(Y(i)), fabs(Z(i))), atol(i));
 				e5 /= sk;
 				e3 /= sk;
-				s5 = fma(e5, e5, s5);
-				s3 = fma(e3, e3, s3);
-			}
+				a5 = fma(e5, e5, a5);
+				a3 = fma(e3, e3, a3);
+			}, s5, s3);
 			if (s5 == 0.0 && s3 == 0.0) return 0.0;
 			double deno = fma(0.01, s3, s5);
 			if (deno <= 0.0) deno = 1.0;
@@ -233,19 +323,15 @@ struct Stepper {
 	template <class F>
 	__device__ __forceinline__ double weighted_sq(F &&value)
 	{
-		double sum = 0.0;
-#pragma unroll UNR
-		for (int i = 0; i < N; ++i) {
+		return C::sum([&](int i) {
 			const double q = value(i) / fma(rtol, fabs(Y(i)), atol(i));
-			sum = fma(q, q, sum);
-		}
-		return sum;
+			return q * q;
+		});
 	}
 
 	__device__ __forceinline__ void euler_probe(const Vec &f0, double h)
 	{
-#pragma unroll UNR
-		for (int i = 0; i < N; ++i) Z.set(i, fma(h, f0(i), Y(i)));
+		C::for_each([&](int i) { Z.set(i, fma(h, f0(i), Y(i))); });
 	}
 };
 
@@ -331,44 +417,58 @@ __device__ __forceinline__ double lyap_transversal(Vec &Y)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Everything one trajectory does during one launch.
+// Everything one trajectory does during one launch.  Thread storage: called by the trajectory's
+// thread.  Warp storage: called by all 32 lanes of the trajectory's warp with identical scalar
+// state; `smem` is the warp's private stage area, `tables` the staged tables of the right-hand side.
 
-template <class Sys, class Tab, int DRIVER, bool REG>
-__device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
+template <class Sys, class Tab, int DRIVER, int MODE>
+__device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b, double *smem = nullptr, const void *tables = nullptr)
 {
-	using ST = Stepper<Sys, Tab, DRIVER, REG>;
-	using L = Layout<Tab, DRIVER>;
+	using ST = Stepper<Sys, Tab, DRIVER, MODE>;
+	using C = typename ST::C;
+	using CVec = typename ST::CVec;
 	constexpr int N = Sys::N;
 	constexpr int S = Tab::NSTAGE;
+	constexpr bool REG = ST::REG;
+	constexpr bool WARP = ST::WARP;
 	constexpr bool DENSE = ST::DENSE;
 	constexpr bool IVP = ST::IVP;
-	constexpr int UNR = ST::UNR;
 	constexpr int NLY = Sys::NL > 0 ? Sys::NL : 1;
 	const int64_t ld = a.ld;
-	const int64_t vec = (int64_t) N * ld;              // one tiled vector
-	const int64_t off = tile_offset(b, N);             // this trajectory inside a tiled vector
+	const int64_t vec = (int64_t) N * ld;                                   // one caller-visible vector
+	const int64_t off = WARP ? b * (int64_t) N : tile_offset(b, N);         // this trajectory inside it
+	const bool leader = !WARP || (threadIdx.x & 31) == 0;                   // writes the per-trajectory scalars
 
 	ST st;
 	st.rtol = a.rtol;
 	st.atol_s = a.atol;
 	st.atol_vec = a.atol_vec;
+	st.tables = tables;
 #pragma unroll
-	for (int k = 0; k < Sys::NP; ++k) st.par.v[k] = a.P[tile_offset(b, Sys::NP) + k * TILE];
+	for (int k = 0; k < Sys::NP; ++k)
+		st.par.v[k] = WARP ? a.P[b * Sys::NP + k] : a.P[tile_offset(b, Sys::NP) + k * TILE];
 
 	int status = a.status[b];
 	double t = a.t[b];
 	int64_t n_acc = 0, n_rej = 0;
 
 	// ---- canonical (caller-visible) locations
-	const GVec Yc{a.Y + off};
-	const GVec Fc{IVP ? a.state + SV_F * vec + off : nullptr};
-	const GVec Oc{DENSE ? a.state + SV_YOLD * vec + off : nullptr};
-	auto Qc = [&](int p) { return GVec{a.state + (SV_DENSE0 + p) * vec + off}; };
+	const CVec Yc{a.Y + off};
+	const CVec Fc{IVP ? a.state + SV_F * vec + off : nullptr};
+	const CVec Oc{DENSE ? a.state + SV_YOLD * vec + off : nullptr};
+	auto Qc = [&](int p) { return CVec{a.state + (SV_DENSE0 + p) * vec + off}; };
 
 	// ---- bind working storage
 	if constexpr (REG) {
 #pragma unroll
 		for (int i = 0; i < N; ++i) st.Y.v[i] = Yc(i);
+	} else if constexpr (WARP) {
+		st.Y.p = smem;
+		st.Z.p = smem + N;
+#pragma unroll
+		for (int j = 0; j < ST::KR; ++j) st.K[j].p = smem + (2 + j) * N;
+		if constexpr (DENSE) st.YO.p = smem + (2 + ST::KR) * N;
+		C::for_each([&](int i) { st.Y.set(i, Yc(i)); });
 	} else {
 		st.Y.p = Yc.p;
 		st.Z.p = a.work + off;
@@ -492,8 +592,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 					take(st.K[0], st.K[S]);
 					pending_f = false;
 				} else if (!have_f) {
-#pragma unroll UNR
-					for (int i = 0; i < N; ++i) st.K[0].set(i, Fc(i));
+					C::for_each([&](int i) { st.K[0].set(i, Fc(i)); });
 				}
 				have_f = true;
 				// ---- RungeKutta._step_impl
@@ -532,14 +631,14 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 
 		// ================= the sample at T
 		if (status != JB_OK) continue;
-		double *const rec = a.Yrec ? a.Yrec + (int64_t) it * vec + off : nullptr;
+		const CVec rec{a.Yrec ? a.Yrec + (int64_t) it * vec + off : nullptr};
+		const CVec res{a.Yres ? a.Yres + off : nullptr};
 		double dt_lyap = T - t_start;
 		if constexpr (DENSE) {
 			if (!interpolant) {
 				// ---- materialise the interpolant of the last step (rk.py:178-180, 693-712)
 				if constexpr (std::is_same<Tab, DP5>::value) {
-#pragma unroll UNR
-					for (int i = 0; i < N; ++i) {
+					C::for_each([&](int i) {
 						static_for<0, 4>([&](auto p) {
 							double q = 0.0;
 							static_for<0, 7>([&](auto j) {
@@ -549,24 +648,22 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 							Qc(p).set(i, q);
 						});
 						Oc.set(i, st.YO(i));
-					}
+					});
 				} else {
 					// three extra stages from (t_old, y_old), then F[0..6]
 					static_for<S + 1, S + 4>([&](auto s) {
-#pragma unroll UNR
-						for (int i = 0; i < N; ++i) {
+						C::for_each([&](int i) {
 							double acc = 0.0;
 							static_for<0, s>([&](auto j) {
 								constexpr double c = dop853::A[s][j];
 								if constexpr (c != 0.0) acc = fma(c, st.K[j](i), acc);
 							});
 							st.Z.set(i, fma(h_prev, acc, st.YO(i)));
-						}
+						});
 						constexpr double cs = Coef<DOP853>::c(s);
 						st.rhs(fma(cs, h_prev, t_old), st.Z, st.K[s]);
 					});
-#pragma unroll UNR
-					for (int i = 0; i < N; ++i) {
+					C::for_each([&](int i) {
 						const double delta = st.Y(i) - st.YO(i);
 						const double f_old = st.K[0](i), f_new = st.K[S](i);
 						Qc(0).set(i, delta);
@@ -581,7 +678,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 							Qc(3 + r).set(i, h_prev * q);
 						});
 						Oc.set(i, st.YO(i));
-					}
+					});
 				}
 				interpolant = true;
 			}
@@ -589,8 +686,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 			const double hh = t - t_old;
 			const double x = (T - t_old) / hh;
 			const bool restart = a.post != JB_POST_NONE;
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) {
+			C::for_each([&](int i) {
 				double r;
 				if constexpr (std::is_same<Tab, DP5>::value) {
 					r = Qc(3)(i);
@@ -608,10 +704,10 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 				}
 				if (restart) st.Z.set(i, r);
 				else {
-					a.Yres[off + (int64_t) i * TILE] = r;
-					if (rec) rec[i * TILE] = r;
+					res.set(i, r);
+					if (rec.p) rec.set(i, r);
 				}
-			}
+			});
 			if (restart) {
 				// jitcode_lyap.integrate re-creates the stepper at (T, sample) (_jitcode.py:773)
 				take(st.Y, st.Z);
@@ -622,44 +718,42 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 			}
 		}
 
-		if (a.post != JB_POST_NONE) {
-			double norms[NLY];
-			if constexpr (Sys::NL > 0) {
-				if (a.post == JB_POST_LYAP_QR)
-					lyap_orthonormalise<Sys::NB, Sys::NL, REG>(st.Y, norms);
-				else if (a.post == JB_POST_LYAP_RESTRICTED)
-					norms[0] = lyap_restricted<Sys::NB, REG>(st.Y, a.proj, a.n_proj);
-				else if (a.post == JB_POST_LYAP_TRANSVERSAL)
-					norms[0] = lyap_transversal<Sys, REG>(st.Y);
-			}
-			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
-			for (int k = 0; k < NLY; ++k) {
-				if (k >= n_out) break;
-				const double lyap = log(norms[k]) / dt_lyap;
-				if (a.lyap_rec) a.lyap_rec[(int64_t) it * n_out * ld + tile_offset(b, n_out) + k * TILE] = lyap;
-				if (it >= a.lyap_discard) {
-					lyap_sum[k] += lyap;
-					lyap_sq[k] = fma(lyap, lyap, lyap_sq[k]);
+		if constexpr (!WARP) {
+			if (a.post != JB_POST_NONE) {
+				double norms[NLY];
+				if constexpr (Sys::NL > 0) {
+					if (a.post == JB_POST_LYAP_QR)
+						lyap_orthonormalise<Sys::NB, Sys::NL, REG>(st.Y, norms);
+					else if (a.post == JB_POST_LYAP_RESTRICTED)
+						norms[0] = lyap_restricted<Sys::NB, REG>(st.Y, a.proj, a.n_proj);
+					else if (a.post == JB_POST_LYAP_TRANSVERSAL)
+						norms[0] = lyap_transversal<Sys, REG>(st.Y);
 				}
-			}
-			if constexpr (IVP) {
-				// the tangent vectors changed: the stepper restarts from the new state
-				initialised = false;
-				interpolant = false;
-				pending_f = have_f = false;
+				const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+				for (int k = 0; k < NLY; ++k) {
+					if (k >= n_out) break;
+					const double lyap = log(norms[k]) / dt_lyap;
+					if (a.lyap_rec) a.lyap_rec[(int64_t) it * n_out * ld + tile_offset(b, n_out) + k * TILE] = lyap;
+					if (it >= a.lyap_discard) {
+						lyap_sum[k] += lyap;
+						lyap_sq[k] = fma(lyap, lyap, lyap_sq[k]);
+					}
+				}
+				if constexpr (IVP) {
+					// the tangent vectors changed: the stepper restarts from the new state
+					initialised = false;
+					interpolant = false;
+					pending_f = have_f = false;
+				}
 			}
 		}
 		if constexpr (!DENSE) {
-			if (rec) {
-#pragma unroll UNR
-				for (int i = 0; i < N; ++i) rec[i * TILE] = st.Y(i);
-			}
+			if (rec.p) C::for_each([&](int i) { rec.set(i, st.Y(i)); });
 		} else if (a.post != JB_POST_NONE) {
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) {
-				a.Yres[off + (int64_t) i * TILE] = st.Y(i);
-				if (rec) rec[i * TILE] = st.Y(i);
-			}
+			C::for_each([&](int i) {
+				res.set(i, st.Y(i));
+				if (rec.p) rec.set(i, st.Y(i));
+			});
 		}
 	}
 
@@ -668,32 +762,34 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b)
 #pragma unroll
 		for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
 	} else {
-		if (st.Y.p != Yc.p) {
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) Yc.set(i, st.Y(i));
-		}
+		if (st.Y.p != Yc.p) C::for_each([&](int i) { Yc.set(i, st.Y(i)); });
 	}
 	if constexpr (IVP) {
 		if (pending_f || have_f) {
 			const auto &F = pending_f ? st.K[S] : st.K[0];
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) Fc.set(i, F(i));
+			C::for_each([&](int i) { Fc.set(i, F(i)); });
 		}
-		a.sstate[SS_H_ABS * ld + b] = h_abs;
-		a.sstate[SS_T_OLD * ld + b] = t_old;
-		a.sstate[SS_H_PREV * ld + b] = h_prev;
-		a.sstate[SS_FLAGS * ld + b] = (double) ((initialised ? FLAG_INITIALISED : 0) | (interpolant ? FLAG_INTERPOLANT : 0));
+		if (leader) {
+			a.sstate[SS_H_ABS * ld + b] = h_abs;
+			a.sstate[SS_T_OLD * ld + b] = t_old;
+			a.sstate[SS_H_PREV * ld + b] = h_prev;
+			a.sstate[SS_FLAGS * ld + b] = (double) ((initialised ? FLAG_INITIALISED : 0) | (interpolant ? FLAG_INTERPOLANT : 0));
+		}
 	}
-	a.t[b] = t;
-	a.status[b] = status;
-	if (a.n_accepted) a.n_accepted[b] += n_acc;
-	if (a.n_rejected) a.n_rejected[b] += n_rej;
-	if (a.lyap_acc && a.post != JB_POST_NONE) {
-		const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
-		for (int k = 0; k < NLY; ++k) {
-			if (k >= n_out) break;
-			a.lyap_acc[tile_offset(b, n_out) + k * TILE] += lyap_sum[k];
-			a.lyap_acc[(int64_t) n_out * ld + tile_offset(b, n_out) + k * TILE] += lyap_sq[k];
+	if (leader) {
+		a.t[b] = t;
+		a.status[b] = status;
+		if (a.n_accepted) a.n_accepted[b] += n_acc;
+		if (a.n_rejected) a.n_rejected[b] += n_rej;
+	}
+	if constexpr (!WARP) {
+		if (a.lyap_acc && a.post != JB_POST_NONE) {
+			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+			for (int k = 0; k < NLY; ++k) {
+				if (k >= n_out) break;
+				a.lyap_acc[tile_offset(b, n_out) + k * TILE] += lyap_sum[k];
+				a.lyap_acc[(int64_t) n_out * ld + tile_offset(b, n_out) + k * TILE] += lyap_sq[k];
+			}
 		}
 	}
 }

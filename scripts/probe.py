@@ -7,7 +7,7 @@ from jitcode_b200 import jitcode
 
 def run(label, system, Y0, pars, name, T, **kw):
 	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=system["n"], control_pars=system["control_pars"], verbose=False)
-	ODE.set_integrator(name, rtol=1e-6, atol=1e-12, **kw)
+	ODE.set_integrator(name, rtol=1e-6, atol=1e-12, storage=storage if "roessler" in label else None, **kw)
 	if pars is not None and pars.shape[1]:
 		ODE.set_parameters(torch.as_tensor(pars).cuda())
 	Yd = torch.as_tensor(Y0).cuda()
@@ -24,6 +24,7 @@ def run(label, system, Y0, pars, name, T, **kw):
 		print(f"{label:28s} {name:7s} B={len(Y0):8d} T={T:6.1f} {ms:10.2f} ms  steps={acc+rej:12d} (rej {rej})  {(acc+rej)/ms*1e3:.3e} steps/s", flush=True)
 
 which = sys.argv[1:] or ["lv", "ro"]
+storage = next((a[8:] for a in which if a.startswith("storage=")), None)
 if "lv" in which:
 	Y0, _ = W.lotka_volterra_ensemble(1_000_000)
 	for name in ("dopri5", "RK45"):

@@ -47,9 +47,11 @@ def test_f_of_y0_golden(golden):
 	assert_allclose(ODE.f(g["t"], g["X"]), g["fX"], rtol=1e-13, atol=1e-16)
 
 
-def test_f_roessler_golden(golden):
+@pytest.mark.parametrize("storage", ["warp", "global"])
+def test_f_roessler_golden(golden, storage):
 	g = golden("roessler_100")
 	ODE = make(W.roessler_network(100))
+	ODE.compile_cuda(storage=storage)
 	ODE.set_parameters(g["kX"][0])
 	assert_allclose(ODE.f(g["tX"], g["X"]), g["fX"], rtol=1e-12, atol=1e-15)
 
@@ -118,12 +120,14 @@ def test_control_parameters_per_trajectory(golden):
 			within_tolerance(ODE.integrate(T), g[name][i])
 
 
-def test_roessler_network_golden(golden):
+@pytest.mark.parametrize("storage", ["warp", "global"])
+def test_roessler_network_golden(golden, storage):
 	# chaotic: agreement to 1e-3 relative (of the state's scale) up to T = 50
 	g = golden("roessler_100")
 	ODE = make(W.roessler_network(100))
 	for name in ("dopri5", "RK45"):
-		ODE.set_integrator(name, **TOL)
+		ODE.set_integrator(name, storage=storage, **TOL)
+		assert ODE.integrator.module.info.storage == {"warp": 2, "global": 1}[storage]
 		ODE.set_parameters(g["pars"][:, 0])
 		ODE.set_initial_value(g["Y0"], 0.0)
 		for i, T in enumerate(g["times"]):
@@ -132,6 +136,24 @@ def test_roessler_network_golden(golden):
 			assert np.abs(result - g[name][i]).max() < 1e-3 * scale, (name, T)
 			if i == 0:
 				assert_allclose(result, g[name][i], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("RK45", True), ("RK45", False), ("dop853", True), ("DOP853", True)])
+def test_warp_storage_matches_global_storage(name, interpolate):
+	"""the two large-system kernels (thread per trajectory in HBM tiles / warp per trajectory in shared memory)
+	run the same controller: on a short, non-chaotic horizon they agree to rounding, with equal step counts."""
+	system = W.roessler_network(100)
+	Y0, pars = W.roessler_ensemble(333, seed=9)          # odd size: partial tiles and a partial last block
+	results, counts = {}, {}
+	for storage in ("warp", "global"):
+		ODE = make(system)
+		ODE.set_integrator(name, interpolate=interpolate, storage=storage, **TOL)
+		ODE.set_parameters(pars[:, 0])
+		ODE.set_initial_value(Y0, 0.0)
+		results[storage] = np.stack([ODE.integrate(T) for T in (0.5, 1.0, 3.0)])
+		counts[storage] = ODE.step_counts()
+	assert_allclose(results["warp"], results["global"], rtol=1e-9, atol=1e-11)
+	assert abs(sum(counts["warp"]) - sum(counts["global"])) <= 0.001 * sum(counts["global"])
 
 
 # ------------------------------------------------------------------ against the CPU oracle on seeded ensembles

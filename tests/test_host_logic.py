@@ -129,6 +129,38 @@ def test_statements_share_repeated_calls():
 	assert "par.v[0]" in text and "jb_helper_0" in text
 
 
+@pytest.mark.parametrize("name", ["roessler", "fhn", "lotka_volterra", "kuramoto"])
+def test_vectoriser_plan_matches_direct_evaluation(name):
+	"""the SIMT-vectorised form (groups of equally shaped statements + tables + loops) computes the same f."""
+	from jitcode_b200 import _vectorise
+	system, pars = {
+		"roessler": (W.roessler_network(24), [0.013]), "fhn": (W.fhn(), []),
+		"lotka_volterra": (W.lotka_volterra(gamma_as_parameter=True), [0.55]), "kuramoto": (W.kuramoto(24), []),
+	}[name]
+	f, n = _symbolic.handle_input(system["f_sym"], system["n"])
+	helpers = _symbolic.sort_helpers(system["helpers"])
+	plan = _vectorise.make_plan(f, helpers, system["control_pars"])
+	state = np.random.default_rng(3).random(n)
+	subs = dict(zip(system["control_pars"], pars))
+	expected = evaluate([entry.subs(subs) for entry in f], [(s, d.subs(subs)) for s, d in helpers], state, time=0.7)
+	np.testing.assert_allclose(_vectorise.evaluate_plan(plan, 0.7, state, pars), expected, rtol=1e-13, atol=1e-15)
+	lines, tables = _vectorise.warp_statements(plan)
+	assert sum(line.startswith("\tdy.set(") or line.startswith("dy.set(") for line in lines) == len(plan.groups)
+	if name == "roessler":
+		assert [group.size for group in plan.groups] == [24, 24, 24] and plan.efficiency == 0.75
+		assert len(plan.helpers) == 1 and plan.helpers[0][1].loops[0].start == [0, 24]
+
+
+def test_warp_module_builds():
+	system = W.roessler_network(100)
+	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=300, control_pars=system["control_pars"], verbose=False)
+	module = ODE.compile_cuda()
+	assert module.info.storage == _codegen.JB_STORE_WARP and module.info.work_vectors == 0
+	assert module.info.threads_per_block % 32 == 0 and 0 < module.info.shared_bytes <= 227 * 1024
+	thread_module = ODE.compile_cuda(storage="global")
+	assert thread_module.info.storage == _codegen.JB_STORE_GLOBAL and thread_module.info.work_vectors == 8
+
+
 def test_module_builds_loads_and_exports_every_symbol():
 	"""the C ABI: every function declared in include/jitcode_b200.h is exported by a compiled module."""
 	header = (ROOT / "include" / "jitcode_b200.h").read_text()
