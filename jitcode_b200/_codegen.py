@@ -136,7 +136,7 @@ def _c_array(values, per_line=16):
 	return ",\n\t".join(", ".join(values[k:k+per_line]) for k in range(0, len(values), per_line))
 
 
-def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None):
+def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None, component_of=None):
 	"""the complete translation unit of one module (what _render_template produces from
 	jitced_template.c in the reference, _jitcode.py:397-406).
 
@@ -157,7 +157,9 @@ def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, met
 	warp = storage == JB_STORE_WARP
 	tf = [repr(float(v)) for v in tables.f64] if warp else []
 	tu = [str(int(v)) for v in tables.u] if warp else []
-	tu_type = "unsigned short" if (not tu or max(int(v) for v in tu) < 65536) else "unsigned int"
+	tu_type = "unsigned short" if (not tu or max(max(int(v) for v in tu), n) < 65536) else "unsigned int"
+	components = [str(int(c)) for c in (component_of if warp else range(n))]
+	n_row = (n + 2) // 2 * 2 if warp else n
 	if warp:
 		function = f"""	template <class VI, class VO>
 	static __device__ __forceinline__ void rhs_warp(const double t, const VI &y, VO &dy, const Par &par, const int lane, const void *jb_tables)
@@ -186,6 +188,10 @@ __device__ const double jb_tf[{max(1, len(tf))}] = {{
 __device__ const {tu_type} jb_tu[{max(1, len(tu))}] = {{
 	{_c_array(tu, 24)}
 }};
+// component stored at each position of the kernel's vectors (identity unless the vectoriser regrouped them)
+__device__ const {tu_type} jb_component[{n}] = {{
+	{_c_array(components, 24)}
+}};
 
 struct Sys {{
 	static constexpr int N = {n};      // dimension of the integrated system
@@ -194,7 +200,12 @@ struct Sys {{
 	static constexpr int NL = {n_lyap};     // tangent vectors
 	static constexpr int NT = {len(tangent_indices)};     // transversal tangent coordinates
 	static constexpr int TF_COUNT = {len(tf)}, TU_COUNT = {len(tu)};
+	static constexpr int NROW = {n_row};   // shared-memory row length (warp storage): position N holds 0
 	typedef {tu_type} TU;
+	static __device__ __forceinline__ const TU *components(const void *tables)
+	{{
+		return reinterpret_cast<const TU *>(static_cast<const double *>(tables) + TF_COUNT) + TU_COUNT;
+	}}
 	struct Par {{ double v[NP > 0 ? NP : 1]; }};
 {tangent}
 {function}

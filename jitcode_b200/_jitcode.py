@@ -63,7 +63,7 @@ def _storage_for(n, method, driver):
 def _warps_per_block(n, method, driver, table_bytes):
 	"""how many trajectories (warps) of a warp-storage module fit one SM's shared memory."""
 	rows = 2 + _stage_rows(method, driver) + (1 if driver == _codegen.JB_DRV_IVP_DENSE else 0)
-	return min(16, (SHARED_MEMORY_PER_BLOCK - table_bytes - 1024) // (rows * n * 8))
+	return min(16, (SHARED_MEMORY_PER_BLOCK - table_bytes - 4 * n - 64) // (rows * (n + 2) * 8))
 
 
 class jitcode:
@@ -229,8 +229,8 @@ class jitcode:
 			if self._f_list and self._post == JB_POST_NONE:
 				try:
 					plan = _vectorise.make_plan(self._f_list, self.helpers, self.control_pars)
-					lines, tables = _vectorise.warp_statements(plan)
-					self._plan = (plan, lines, tables)
+					lines, tables, component_of = _vectorise.warp_statements(plan)
+					self._plan = (plan, lines, tables, component_of)
 				except NotImplementedError:
 					pass
 		return self._plan
@@ -256,13 +256,13 @@ class jitcode:
 		if key not in self._modules:
 			if not self._f_list:
 				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
-			tables = None
+			tables = component_of = None
 			if storage == _codegen.JB_STORE_WARP:
 				plan = self._warp_plan()
 				if plan is None:
 					raise NotImplementedError("This system cannot be vectorised for warp storage (or it has a Lyapunov post-step).")
 				self.check()
-				_, statements, tables = plan
+				_, statements, tables, component_of = plan
 				if threads is None:
 					table_bytes = tables.nbytes
 					warps = _warps_per_block(self.n, method, driver, table_bytes)
@@ -278,7 +278,7 @@ class jitcode:
 			source = _codegen.module_source(
 				statements, self.n, len(self.control_pars),
 				self._n_basic_module, self._n_lyap_module, self._tangent_indices_module,
-				method, driver, storage, threads, tables=tables,
+				method, driver, storage, threads, tables=tables, component_of=component_of,
 			)
 			path = _build.compile_module(
 				source, self._compile_options["extra_compile_args"], self._compile_options["extra_link_args"],

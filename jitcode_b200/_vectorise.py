@@ -312,40 +312,146 @@ class Tables:
 		self.f64.extend(float(v) for v in values)
 		return offset
 
-	def add_u(self, values):
+	def add_u(self, values, align=1):
+		while len(self.u) % align:
+			self.u.append(0)
 		offset = len(self.u)
 		self.u.extend(int(v) for v in values)
 		return offset
 
 	@property
+	def wide(self):
+		return bool(self.u) and max(self.u) >= 65536
+
+	@property
 	def nbytes(self):
-		index_bytes = 2 if (not self.u or max(self.u) < 65536) else 4
-		return 8 * len(self.f64) + (index_bytes * len(self.u) + 7) // 8 * 8
+		return 8 * len(self.f64) + ((4 if self.wide else 2) * len(self.u) + 7) // 8 * 8
 
 
 def _uniform(values):
 	return len(values) > 0 and all(v == values[0] for v in values)
 
 
-def _slot_preamble(printer, prefix, consts, indices, tables, position, lines, indent):
-	"""declares every slot of one statement (or loop term) as a local: literal if uniform, table read otherwise."""
+def component_positions(plan):
+	"""Where component i lives inside the kernel's vectors: the outputs of every group are made contiguous
+	(group after group, statement after statement), so that a group's lanes write — and, for neighbour
+	couplings, mostly read — consecutive shared-memory words.  The permutation costs nothing: every index
+	the right-hand side uses comes from the tables printed here; only loading and storing the caller's
+	state goes through it (Sys::component_of)."""
+	position = {}
+	for group in plan.groups:
+		for out in group.outs:
+			position[out] = len(position)
+	assert sorted(position) == list(range(plan.n)), "every component needs exactly one equation"
+	return position
+
+
+def _paddable(loop):
+	"""can a loop be padded to uniform length with terms that contribute exactly zero (varying constants 0,
+	indices pointing to the zero slot)?"""
+	body = loop.body
+	for c, values in enumerate(loop.consts):
+		symbol = sympy.Symbol(f"{loop.prefix}c{c}")
+		body = body.xreplace({symbol: sympy.Float(values[0]) if _uniform(values) else sympy.Integer(0)})
+	body = body.replace(lambda e: _is_dynvar(e), lambda e: sympy.Integer(0))
+	try:
+		return body == 0 or sympy.simplify(body) == 0
+	except Exception:
+		return False
+
+
+def _ell(values, start, size, width, pad):
+	"""CSR → ELL: entry (k, m) at k*size + m, padded with `pad`."""
+	out = [pad] * (width * size)
+	for m in range(size):
+		for k, value in enumerate(values[start[m]:start[m+1]]):
+			out[k*size + m] = value
+	return out
+
+
+def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
+	"""one variable-length sum of a group, in ELL form: all lanes run the same (unrolled) number of terms."""
+	size = group.size
+	lengths = [loop.start[m+1] - loop.start[m] for m in range(size)]
+	width = max(lengths)
+	name = loop.symbol.name
+	# terms ordered by distance from the statement's own component: lanes m, m+1, … then read neighbouring words
+	order = []
+	for m in range(size):
+		terms = list(range(loop.start[m], loop.start[m+1]))
+		if loop.n_index and group.outs[m] >= 0:
+			own = position[group.outs[m]]
+			terms.sort(key=lambda k: (position[loop.indices[0][k]] - own) % len(position))
+		order.extend(terms)
+	consts = [[slot[k] for k in order] for slot in loop.consts]
+	indices = [[position[slot[k]] for k in order] for slot in loop.indices]
+	padded = _paddable(loop)
+
+	if padded and loop.n_index == 1 and not any(not _uniform(values) for values in consts) and not tables.wide and zero_slot < 65536:
+		# bare gather Σ g(y[idx]): two 16-bit indices per 32-bit table word, two accumulators
+		width += width % 2
+		ell = _ell(indices[0], loop.start, size, width, zero_slot)
+		pairs = []
+		for kk in range(width // 2):
+			for m in range(size):
+				pairs.extend([ell[(2*kk)*size + m], ell[(2*kk+1)*size + m]])
+		offset = tables.add_u(pairs, align=2)
+		for c, values in enumerate(consts):
+			lines.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
+		index_symbol = f"{loop.prefix}i0"
+		term = printer.doprint(loop.body)
+		lines.append(f"\tdouble {name}_a = 0.0, {name}_b = 0.0;")
+		lines.append("\t{")
+		lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + m;")
+		lines.append("#pragma unroll")
+		lines.append(f"\t\tfor (int k = 0; k < {width // 2}; ++k) {{")
+		lines.append(f"\t\t\tconst unsigned pair = pairs[k * {size}];")
+		lines.append(f"\t\t\t{{ const int {index_symbol} = pair & 0xffffu; {name}_a += {term}; }}")
+		lines.append(f"\t\t\t{{ const int {index_symbol} = pair >> 16; {name}_b += {term}; }}")
+		lines.append("\t\t}")
+		lines.append("\t}")
+		lines.append(f"\tconst double {name} = {name}_a + {name}_b;")
+		return
+
+	# general terms: one ELL table per varying slot; padding terms vanish, or are skipped by a per-lane count
+	lines.append(f"\tdouble {name} = 0.0;")
+	lines.append("\t{")
+	if not padded:
+		lines.append(f"\t\tconst int count = JB_TU[{tables.add_u(lengths)} + m];")
+	lines.append("#pragma unroll 4")
+	lines.append(f"\t\tfor (int k = 0; k < {width}; ++k) {{")
+	indent = "\t\t\t"
+	if not padded:
+		lines.append("\t\t\tif (k < count) {")
+		indent = "\t\t\t\t"
 	for c, values in enumerate(consts):
 		if _uniform(values):
-			lines.append(f"{indent}const double {prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
+			lines.append(f"{indent}const double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
 		else:
-			lines.append(f"{indent}const double {prefix}c{c} = JB_TF[{tables.add_f64(values)} + {position}];")
-	for i, values in enumerate(indices):
-		if _uniform(values):
-			lines.append(f"{indent}const int {prefix}i{i} = {values[0]};")
-		else:
-			lines.append(f"{indent}const int {prefix}i{i} = JB_TU[{tables.add_u(values)} + {position}];")
+			offset = tables.add_f64(_ell(values, loop.start, size, width, 0.0))
+			lines.append(f"{indent}const double {loop.prefix}c{c} = JB_TF[{offset} + k * {size} + m];")
+	for j, values in enumerate(indices):
+		offset = tables.add_u(_ell(values, loop.start, size, width, zero_slot))
+		lines.append(f"{indent}const int {loop.prefix}i{j} = JB_TU[{offset} + k * {size} + m];")
+	lines.append(f"{indent}{name} += {printer.doprint(loop.body)};")
+	if not padded:
+		lines.append("\t\t\t}")
+	lines.append("\t\t}")
+	lines.append("\t}")
 
 
 def warp_statements(plan):
-	"""returns (lines of the body of Sys::rhs_warp, Tables)."""
+	"""returns (lines of the body of Sys::rhs_warp, Tables, component_of) where component_of[q] is the
+	component stored at position q of the kernel's vectors; position n is a slot that always holds 0."""
 	printer = CudaPrinter()
 	tables = Tables()
 	lines = []
+	position = component_positions(plan)
+	zero_slot = plan.n
+
+	def located(expr):
+		"""y(i) with a literal index → y(position of i)."""
+		return expr.replace(lambda e: _is_dynvar(e) and e.args[0].is_Integer, lambda e: Y(sympy.Integer(position[int(e.args[0])])))
 
 	emitted = set()
 	pending = list(plan.temporaries)
@@ -357,11 +463,26 @@ def warp_statements(plan):
 			for item in list(pending):
 				needs = {s for s in item[1].free_symbols if s in helper_symbols or s.name.startswith("jb_call_")}
 				if needs <= emitted:
-					lines.append(f"const double {item[0].name} = {printer.doprint(item[1])};")
+					lines.append(f"const double {item[0].name} = {printer.doprint(located(item[1]))};")
 					emitted.add(item[0])
 					pending.remove(item)
 					progress = True
 	flush()
+
+	def slot_preamble(prefix, consts, indices, where, indent):
+		for c, values in enumerate(consts):
+			if _uniform(values):
+				lines.append(f"{indent}const double {prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
+			else:
+				lines.append(f"{indent}const double {prefix}c{c} = JB_TF[{tables.add_f64(values)} + {where}];")
+		for j, values in enumerate(indices):
+			values = [position[v] for v in values]
+			if _uniform(values):
+				lines.append(f"{indent}const int {prefix}i{j} = {values[0]};")
+			elif where == "m" and _uniform([v - m for m, v in enumerate(values)]):
+				lines.append(f"{indent}const int {prefix}i{j} = {values[0]} + m;")      # consecutive positions: no table
+			else:
+				lines.append(f"{indent}const int {prefix}i{j} = JB_TU[{tables.add_u(values)} + {where}];")
 
 	# helpers: loops spread over the lanes and reduced, the rest redundantly on every lane
 	for symbol, group in plan.helpers:
@@ -370,11 +491,11 @@ def warp_statements(plan):
 			count = loop.start[1]
 			lines.append(f"\tdouble {loop.symbol.name}_acc = 0.0;")
 			lines.append(f"\tfor (int k = lane; k < {count}; k += 32) {{")
-			_slot_preamble(printer, loop.prefix, loop.consts, loop.indices, tables, "k", lines, "\t\t")
+			slot_preamble(loop.prefix, loop.consts, loop.indices, "k", "\t\t")
 			lines.append(f"\t\t{loop.symbol.name}_acc += {printer.doprint(loop.body)};")
 			lines.append("\t}")
 			lines.append(f"\tconst double {loop.symbol.name} = jb::warp_sum({loop.symbol.name}_acc);")
-		_slot_preamble(printer, group.prefix, group.consts, group.indices, tables, "0", lines, "\t")
+		slot_preamble(group.prefix, group.consts, group.indices, "0", "\t")
 		lines.append(f"\t{symbol.name} = {printer.doprint(group.body)};")
 		lines.append("}")
 		emitted.add(symbol)
@@ -382,19 +503,16 @@ def warp_statements(plan):
 	assert not pending, "unresolvable temporaries"
 
 	for g, group in enumerate(plan.groups):
-		out_offset = None if group.size == 1 else tables.add_u(group.outs)
-		lines.append(f"// group {g}: {group.size} statement(s)")
+		base = position[group.outs[0]]
+		lines.append(f"// group {g}: {group.size} statement(s), components at positions {base} … {base + group.size - 1}")
 		lines.append(f"for (int m = lane; m < {group.size}; m += 32) {{")
 		for loop in group.loops:
-			start = tables.add_u(loop.start)
-			lines.append(f"\tdouble {loop.symbol.name} = 0.0;")
-			lines.append(f"\tfor (int k = JB_TU[{start} + m], k_end = JB_TU[{start} + m + 1]; k < k_end; ++k) {{")
-			_slot_preamble(printer, loop.prefix, loop.consts, loop.indices, tables, "k", lines, "\t\t")
-			lines.append(f"\t\t{loop.symbol.name} += {printer.doprint(loop.body)};")
-			lines.append("\t}")
-		_slot_preamble(printer, group.prefix, group.consts, group.indices, tables, "m", lines, "\t")
-		target = str(group.outs[0]) if out_offset is None else f"JB_TU[{out_offset} + m]"
-		lines.append(f"\tdy.set({target}, {printer.doprint(group.body)});")
+			_print_loop(printer, loop, group, position, tables, lines, zero_slot)
+		slot_preamble(group.prefix, group.consts, group.indices, "m", "\t")
+		lines.append(f"\tdy.set({base} + m, {printer.doprint(group.body)});")
 		lines.append("}")
 	helper_declarations = [f"double {symbol.name};" for symbol, _ in plan.helpers]
-	return helper_declarations + lines, tables
+	component_of = [None] * plan.n
+	for component, where in position.items():
+		component_of[where] = component
+	return helper_declarations + lines, tables, component_of

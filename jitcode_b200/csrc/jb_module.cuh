@@ -32,11 +32,11 @@ template <class S, bool W> struct WarpShared {
 	static constexpr size_t BYTES = 0, EVAL_BYTES = 0;
 };
 template <class S> struct WarpShared<S, true> {
-	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) ((S::TU_COUNT * sizeof(typename S::TU) + 7) / 8);
+	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) (((S::TU_COUNT + S::N) * sizeof(typename S::TU) + 7) / 8);
 	static constexpr int ROWS = 2 + ModuleLayout::KR + (ModuleLayout::DENSE ? 1 : 0);     // Y, Z, K rows, y_old
 	static constexpr int WARPS = JB_MODULE_THREADS / 32;
-	static constexpr size_t BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * ROWS * S::N);
-	static constexpr size_t EVAL_BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * 2 * S::N);
+	static constexpr size_t BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * ROWS * S::NROW);
+	static constexpr size_t EVAL_BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * 2 * S::NROW);
 };
 using Shared = WarpShared<Sys, MODULE_WARP>;
 
@@ -46,6 +46,7 @@ __device__ __forceinline__ void stage_tables(double *smem)
 	for (int i = threadIdx.x; i < S::TF_COUNT; i += blockDim.x) smem[i] = jb_generated::jb_tf[i];
 	typename S::TU *tu = reinterpret_cast<typename S::TU *>(smem + S::TF_COUNT);
 	for (int i = threadIdx.x; i < S::TU_COUNT; i += blockDim.x) tu[i] = jb_generated::jb_tu[i];
+	for (int i = threadIdx.x; i < S::N; i += blockDim.x) tu[S::TU_COUNT + i] = jb_generated::jb_component[i];
 	__syncthreads();
 }
 
@@ -58,7 +59,7 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 		extern __shared__ __align__(16) double jb_smem[];
 		stage_tables<Sys>(jb_smem);
 		const int warp = threadIdx.x >> 5;
-		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * Shared::ROWS * Sys::N;
+		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * Shared::ROWS * Sys::NROW;
 		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
 		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < a.B; b += stride) {
 			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b, mine, jb_smem);
@@ -80,18 +81,20 @@ jb_eval_f_kernel(const double *t, const double *Y, const double *P, double *dY, 
 		extern __shared__ __align__(16) double jb_smem[];
 		stage_tables<Sys>(jb_smem);
 		const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-		double *const in = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * 2 * Sys::N;
-		double *const out = in + Sys::N;
+		double *const in = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * 2 * Sys::NROW;
+		double *const out = in + Sys::NROW;
+		const typename Sys::TU *const comp = Sys::components(jb_smem);
+		if (lane == 0) for (int i = Sys::N; i < Sys::NROW; ++i) in[i] = 0.0;
 		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
 		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < B; b += stride) {
 			Sys::Par par;
 #pragma unroll
 			for (int k = 0; k < Sys::NP; ++k) par.v[k] = P[b * Sys::NP + k];
-			for (int i = lane; i < Sys::N; i += 32) in[i] = Y[b * Sys::N + i];
+			for (int i = lane; i < Sys::N; i += 32) in[i] = Y[b * Sys::N + comp[i]];
 			const SVec vin{in};
 			SVec vout{out};
 			RhsCall<Sys, MODE>::call(t[b], vin, vout, par, jb_smem);
-			for (int i = lane; i < Sys::N; i += 32) dY[b * Sys::N + i] = out[i];
+			for (int i = lane; i < Sys::N; i += 32) dY[b * Sys::N + comp[i]] = out[i];
 			__syncwarp();
 		}
 	} else {

@@ -59,6 +59,15 @@ struct SVec {               // contiguous vector: shared memory (warp storage) o
 	__device__ __forceinline__ void set(int i, double x) const { p[i] = x; }
 };
 
+// caller-visible vector of a warp-storage module: position q of the kernel's vectors holds component comp[q]
+template <class TU>
+struct PVec {
+	double *p;
+	const TU *comp;
+	__device__ __forceinline__ double operator()(int q) const { return p[comp[q]]; }
+	__device__ __forceinline__ void set(int q, double x) const { p[comp[q]] = x; }
+};
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -239,15 +248,21 @@ struct Stepper {
 	static constexpr int KR = L::KR;
 	static constexpr int S = Tab::NSTAGE;
 	using Vec = typename std::conditional<REG, RVec<N>, typename std::conditional<WARP, SVec, GVec>::type>::type;
-	using CVec = typename std::conditional<WARP, SVec, GVec>::type;    // caller-visible (canonical) vectors
+	using IVec = typename std::conditional<WARP, SVec, GVec>::type;    // persistent solver vectors in the caller's memory
+	using UVec = typename std::conditional<WARP, PVec<typename Sys::TU>, GVec>::type;   // the caller's state and samples
 
 	Vec Y, Z, YO, K[KR];
 	typename Sys::Par par;
 	double atol_s, rtol;
 	const double *atol_vec;
 	const void *tables;
+	const typename Sys::TU *comp;     // warp storage: component stored at each position
 
-	__device__ __forceinline__ double atol(int i) const { return atol_vec ? atol_vec[i] : atol_s; }
+	__device__ __forceinline__ double atol(int i) const
+	{
+		if constexpr (WARP) return atol_vec ? atol_vec[comp[i]] : atol_s;
+		else return atol_vec ? atol_vec[i] : atol_s;
+	}
 
 	__device__ __forceinline__ void rhs(double t, const Vec &in, Vec &out)
 	{
@@ -426,7 +441,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 {
 	using ST = Stepper<Sys, Tab, DRIVER, MODE>;
 	using C = typename ST::C;
-	using CVec = typename ST::CVec;
+	using IVec = typename ST::IVec;
+	using UVec = typename ST::UVec;
 	constexpr int N = Sys::N;
 	constexpr int S = Tab::NSTAGE;
 	constexpr bool REG = ST::REG;
@@ -444,6 +460,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	st.atol_s = a.atol;
 	st.atol_vec = a.atol_vec;
 	st.tables = tables;
+	st.comp = nullptr;
 #pragma unroll
 	for (int k = 0; k < Sys::NP; ++k)
 		st.par.v[k] = WARP ? a.P[b * Sys::NP + k] : a.P[tile_offset(b, Sys::NP) + k * TILE];
@@ -453,21 +470,30 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	int64_t n_acc = 0, n_rej = 0;
 
 	// ---- canonical (caller-visible) locations
-	const CVec Yc{a.Y + off};
-	const CVec Fc{IVP ? a.state + SV_F * vec + off : nullptr};
-	const CVec Oc{DENSE ? a.state + SV_YOLD * vec + off : nullptr};
-	auto Qc = [&](int p) { return CVec{a.state + (SV_DENSE0 + p) * vec + off}; };
+	auto user = [&](double *base) {
+		if constexpr (WARP) return UVec{base, st.comp};
+		else return UVec{base};
+	};
+	if constexpr (WARP) st.comp = Sys::components(tables);
+	const UVec Yc = user(a.Y + off);
+	const IVec Fc{IVP ? a.state + SV_F * vec + off : nullptr};
+	const IVec Oc{DENSE ? a.state + SV_YOLD * vec + off : nullptr};
+	auto Qc = [&](int p) { return IVec{a.state + (SV_DENSE0 + p) * vec + off}; };
 
 	// ---- bind working storage
 	if constexpr (REG) {
 #pragma unroll
 		for (int i = 0; i < N; ++i) st.Y.v[i] = Yc(i);
 	} else if constexpr (WARP) {
+		// rows of NROW > N doubles: position N always holds 0 (padding target of the vectorised loops)
+		constexpr int NROW = Sys::NROW;
 		st.Y.p = smem;
-		st.Z.p = smem + N;
+		st.Z.p = smem + NROW;
 #pragma unroll
-		for (int j = 0; j < ST::KR; ++j) st.K[j].p = smem + (2 + j) * N;
-		if constexpr (DENSE) st.YO.p = smem + (2 + ST::KR) * N;
+		for (int j = 0; j < ST::KR; ++j) st.K[j].p = smem + (2 + j) * NROW;
+		if constexpr (DENSE) st.YO.p = smem + (2 + ST::KR) * NROW;
+		for (int r = threadIdx.x & 31; r < 2 + ST::KR + (DENSE ? 1 : 0); r += 32)
+			for (int i = N; i < NROW; ++i) smem[r * NROW + i] = 0.0;
 		C::for_each([&](int i) { st.Y.set(i, Yc(i)); });
 	} else {
 		st.Y.p = Yc.p;
@@ -631,8 +657,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 
 		// ================= the sample at T
 		if (status != JB_OK) continue;
-		const CVec rec{a.Yrec ? a.Yrec + (int64_t) it * vec + off : nullptr};
-		const CVec res{a.Yres ? a.Yres + off : nullptr};
+		const UVec rec = user(a.Yrec ? a.Yrec + (int64_t) it * vec + off : nullptr);
+		const UVec res = user(a.Yres ? a.Yres + off : nullptr);
 		double dt_lyap = T - t_start;
 		if constexpr (DENSE) {
 			if (!interpolant) {
@@ -762,7 +788,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 #pragma unroll
 		for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
 	} else {
-		if (st.Y.p != Yc.p) C::for_each([&](int i) { Yc.set(i, st.Y(i)); });
+		if (WARP || st.Y.p != Yc.p) C::for_each([&](int i) { Yc.set(i, st.Y(i)); });
 	}
 	if constexpr (IVP) {
 		if (pending_f || have_f) {

@@ -144,8 +144,9 @@ def test_vectoriser_plan_matches_direct_evaluation(name):
 	subs = dict(zip(system["control_pars"], pars))
 	expected = evaluate([entry.subs(subs) for entry in f], [(s, d.subs(subs)) for s, d in helpers], state, time=0.7)
 	np.testing.assert_allclose(_vectorise.evaluate_plan(plan, 0.7, state, pars), expected, rtol=1e-13, atol=1e-15)
-	lines, tables = _vectorise.warp_statements(plan)
-	assert sum(line.startswith("\tdy.set(") or line.startswith("dy.set(") for line in lines) == len(plan.groups)
+	lines, tables, component_of = _vectorise.warp_statements(plan)
+	assert sorted(component_of) == list(range(n))
+	assert sum(line.lstrip().startswith("dy.set(") for line in lines) == len(plan.groups)
 	if name == "roessler":
 		assert [group.size for group in plan.groups] == [24, 24, 24] and plan.efficiency == 0.75
 		assert len(plan.helpers) == 1 and plan.helpers[0][1].loops[0].start == [0, 24]
