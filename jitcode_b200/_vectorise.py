@@ -306,6 +306,7 @@ class Tables:
 	"""two flat tables (doubles, unsigned integers) that the kernel stages in shared memory."""
 	def __init__(self):
 		self.f64, self.u = [], []
+		self.offsets = []      # byte offsets (32 bit) into a shared-memory vector, read four at a time
 
 	def add_f64(self, values):
 		offset = len(self.f64)
@@ -319,13 +320,19 @@ class Tables:
 		self.u.extend(int(v) for v in values)
 		return offset
 
+	def add_offsets(self, positions):
+		assert len(self.offsets) % 4 == 0 and len(positions) % 4 == 0
+		offset = len(self.offsets)
+		self.offsets.extend(8 * int(p) for p in positions)
+		return offset
+
 	@property
 	def wide(self):
 		return bool(self.u) and max(self.u) >= 65536
 
 	@property
 	def nbytes(self):
-		return 8 * len(self.f64) + ((4 if self.wide else 2) * len(self.u) + 7) // 8 * 8
+		return 8 * len(self.f64) + 4 * len(self.offsets) + ((4 if self.wide else 2) * len(self.u) + 7) // 8 * 8 + 16
 
 
 def _uniform(values):
@@ -387,30 +394,31 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 	indices = [[position[slot[k]] for k in order] for slot in loop.indices]
 	padded = _paddable(loop)
 
-	if padded and loop.n_index == 1 and not any(not _uniform(values) for values in consts) and not tables.wide and zero_slot < 65536:
-		# bare gather Σ g(y[idx]): two 16-bit indices per 32-bit table word, two accumulators
-		width += width % 2
+	if padded and loop.n_index == 1 and not any(not _uniform(values) for values in consts):
+		# bare gather Σ g(y[idx]): byte offsets of four terms per 128-bit table read, four accumulators
+		width = (width + 3) // 4 * 4
 		ell = _ell(indices[0], loop.start, size, width, zero_slot)
-		pairs = []
-		for kk in range(width // 2):
+		quads = []
+		for kq in range(width // 4):
 			for m in range(size):
-				pairs.extend([ell[(2*kk)*size + m], ell[(2*kk+1)*size + m]])
-		offset = tables.add_u(pairs, align=2)
+				quads.extend(ell[(4*kq + j)*size + m] for j in range(4))
+		offset = tables.add_offsets(quads)
 		for c, values in enumerate(consts):
 			lines.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
-		index_symbol = f"{loop.prefix}i0"
 		term = printer.doprint(loop.body)
-		lines.append(f"\tdouble {name}_a = 0.0, {name}_b = 0.0;")
+		reads = f"y({loop.prefix}i0)"
+		assert reads in term
+		lines.append(f"\tdouble {name}_a = 0.0, {name}_b = 0.0, {name}_c = 0.0, {name}_d = 0.0;")
 		lines.append("\t{")
-		lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + m;")
+		lines.append(f"\t\tconst uint4 *const quads = reinterpret_cast<const uint4 *>(JB_TO + {offset}) + m;")
 		lines.append("#pragma unroll")
-		lines.append(f"\t\tfor (int k = 0; k < {width // 2}; ++k) {{")
-		lines.append(f"\t\t\tconst unsigned pair = pairs[k * {size}];")
-		lines.append(f"\t\t\t{{ const int {index_symbol} = pair & 0xffffu; {name}_a += {term}; }}")
-		lines.append(f"\t\t\t{{ const int {index_symbol} = pair >> 16; {name}_b += {term}; }}")
+		lines.append(f"\t\tfor (int k = 0; k < {width // 4}; ++k) {{")
+		lines.append(f"\t\t\tconst uint4 quad = quads[k * {size}];")
+		for accumulator, field in zip("abcd", "xyzw"):
+			lines.append(f"\t\t\t{name}_{accumulator} += {term.replace(reads, f'y.at(quad.{field})')};")
 		lines.append("\t\t}")
 		lines.append("\t}")
-		lines.append(f"\tconst double {name} = {name}_a + {name}_b;")
+		lines.append(f"\tconst double {name} = ({name}_a + {name}_b) + ({name}_c + {name}_d);")
 		return
 
 	# general terms: one ELL table per varying slot; padding terms vanish, or are skipped by a per-lane count

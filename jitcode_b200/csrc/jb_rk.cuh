@@ -56,6 +56,11 @@ struct GVec {               // one trajectory's column of a tile: element i at p
 struct SVec {               // contiguous vector: shared memory (warp storage) or one row of a (B, n) global array
 	double *p;
 	__device__ __forceinline__ double operator()(int i) const { return p[i]; }
+	// element at a byte offset (the vectorised right-hand side keeps pre-scaled offsets in its tables)
+	__device__ __forceinline__ double at(unsigned bytes) const
+	{
+		return *reinterpret_cast<const double *>(reinterpret_cast<const char *>(p) + bytes);
+	}
 	__device__ __forceinline__ void set(int i, double x) const { p[i] = x; }
 };
 
