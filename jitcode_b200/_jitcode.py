@@ -60,10 +60,33 @@ def _storage_for(n, method, driver):
 	return _codegen.JB_STORE_REGISTERS if rows * n <= 88 else _codegen.JB_STORE_GLOBAL
 
 
-def _warps_per_block(n, method, driver, table_bytes):
-	"""how many trajectories (warps) of a warp-storage module fit one SM's shared memory."""
-	rows = 2 + _stage_rows(method, driver) + (1 if driver == _codegen.JB_DRV_IVP_DENSE else 0)
-	return min(16, (SHARED_MEMORY_PER_BLOCK - table_bytes - 4 * n - 64) // (rows * (n + 2) * 8))
+def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None):
+	"""(kregs, threads) of a warp-storage module.
+
+	kregs : how many stage rows K[0 … kregs) — plus the state — every lane keeps in registers (its share: every
+		32nd component) instead of shared memory.  Shared memory is the bottleneck of this kernel (gathers of the
+		vectorised right-hand side), so as many rows as the register file allows are taken out of it.
+	threads : 32 × the number of trajectories (warps) per block; one block per SM."""
+	stages = _stage_rows(method, driver)
+	passes = (n + 31) // 32
+	dense = 1 if driver == _codegen.JB_DRV_IVP_DENSE else 0
+	row_bytes = (n + 2) // 2 * 2 * 8
+	available = SHARED_MEMORY_PER_BLOCK - table_bytes - 4 * n - 64
+
+	def warps(k):
+		by_shared = available // ((2 + dense + stages - k) * row_bytes)
+		registers = 90 + 2 * passes * (1 + k) if k else 96       # measured on the Rössler network (profiles/)
+		if registers > 255:
+			return 0
+		return max(0, min(16, by_shared, 65536 // (32 * registers)))
+
+	if kregs is None:
+		# most trajectories per SM first (latency hiding), then most rows out of shared memory
+		kregs = max(range(stages + 1), key=lambda k: (warps(k), k))
+	kregs = max(0, min(int(kregs), stages))
+	if threads is None:
+		threads = 32 * warps(kregs)
+	return kregs, threads
 
 
 class jitcode:
@@ -202,7 +225,7 @@ class jitcode:
 		raise NotImplementedError("There is no CPU fallback: the derivative only exists as CUDA code.")
 
 	def compile_cuda(self, extra_compile_args=None, extra_link_args=None, verbose=False, modulename=None, omp=None,
-			method=_codegen.JB_DP5, driver=_codegen.JB_DRV_ODE, storage=None, threads=None):
+			method=_codegen.JB_DP5, driver=_codegen.JB_DRV_ODE, storage=None, threads=None, kregs=None):
 		if isinstance(storage, str):
 			storage = STORAGE_BY_NAME[storage]
 		"""
@@ -218,7 +241,7 @@ class jitcode:
 		if extra_link_args is not None:
 			self._compile_options["extra_link_args"] = tuple(extra_link_args)
 		self._compile_options["verbose"] = verbose
-		return self._module(method, driver, storage, threads)
+		return self._module(method, driver, storage, threads, kregs)
 
 	compile_C = compile_cuda
 
@@ -240,19 +263,18 @@ class jitcode:
 		if storage == _codegen.JB_STORE_GLOBAL and self.n >= 64:
 			plan = self._warp_plan()
 			if plan is not None and plan[0].efficiency >= 0.5:
-				table_bytes = plan[2].nbytes
-				if _warps_per_block(self.n, method, driver, table_bytes) >= 2:
+				if _warp_configuration(self.n, method, driver, plan[2].nbytes)[1] >= 64:
 					storage = _codegen.JB_STORE_WARP
 		return storage
 
-	def _module(self, method, driver, storage=None, threads=None):
+	def _module(self, method, driver, storage=None, threads=None, kregs=None):
 		if storage is None:
 			if (method, driver, None) in self._modules:
 				return self._modules[(method, driver, None)]
 			storage = self._choose_storage(method, driver) if self._f_list else None
 			if storage is None:
 				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
-		key = (method, driver, storage) if threads is None else (method, driver, storage, threads)
+		key = (method, driver, storage) if (threads is None and kregs is None) else (method, driver, storage, threads, kregs)
 		if key not in self._modules:
 			if not self._f_list:
 				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
@@ -263,12 +285,9 @@ class jitcode:
 					raise NotImplementedError("This system cannot be vectorised for warp storage (or it has a Lyapunov post-step).")
 				self.check()
 				_, statements, tables, component_of = plan
-				if threads is None:
-					table_bytes = tables.nbytes
-					warps = _warps_per_block(self.n, method, driver, table_bytes)
-					if warps < 1:
-						raise ValueError("The system is too large for warp storage: one trajectory does not fit shared memory.")
-					threads = 32 * warps
+				kregs, threads = _warp_configuration(self.n, method, driver, tables.nbytes, kregs, threads)
+				if threads < 32:
+					raise ValueError("The system is too large for warp storage: one trajectory does not fit shared memory.")
 			else:
 				if self._statements is None:
 					self.generate_f_cuda()
@@ -278,7 +297,7 @@ class jitcode:
 			source = _codegen.module_source(
 				statements, self.n, len(self.control_pars),
 				self._n_basic_module, self._n_lyap_module, self._tangent_indices_module,
-				method, driver, storage, threads, tables=tables, component_of=component_of,
+				method, driver, storage, threads, tables=tables, component_of=component_of, kregs=kregs or 0,
 			)
 			path = _build.compile_module(
 				source, self._compile_options["extra_compile_args"], self._compile_options["extra_link_args"],
@@ -427,7 +446,7 @@ class jitcode:
 	_post = JB_POST_NONE
 	_proj = None
 
-	def set_integrator(self, name, nsteps=10**6, interpolate=True, *, device=None, storage=None, threads=None, **integrator_params):
+	def set_integrator(self, name, nsteps=10**6, interpolate=True, *, device=None, storage=None, threads=None, kregs=None, **integrator_params):
 		"""
 		As in the reference (_jitcode.py:560-626).
 
@@ -438,7 +457,8 @@ class jitcode:
 		nsteps : limit of step attempts per `integrate` call for the `ode` names.
 		integrator_params : rtol, atol (scalar or one per component), max_step, first_step, and for the `ode`
 			names safety, ifactor, dfactor, beta — passed to the kernel with SciPy's defaults.
-		device / storage ("registers" | "global") / threads : where and how the kernel runs (engine-specific).
+		device / storage ("registers" | "global" | "warp") / threads / kregs : where and how the kernel runs
+			(engine-specific; see _storage_for, _choose_storage and _warp_configuration).
 		"""
 		if name in NOT_REBUILT:
 			raise NotImplementedError(f"The B200 engine only implements the explicit Dormand–Prince pairs (dopri5, dop853, RK45, DOP853), not {name!r}.")
@@ -452,9 +472,9 @@ class jitcode:
 		if isinstance(storage, str):
 			storage = STORAGE_BY_NAME[storage]
 		old_integrator = self.integrator
-		module = self._module(method, driver, storage, threads)   # compiling needs no GPU …
+		module = self._module(method, driver, storage, threads, kregs)   # compiling needs no GPU …
 		require_cuda(device)                                      # … running does
-		self._integrator_config = (method, driver, storage, threads)
+		self._integrator_config = (method, driver, storage, threads, kregs)
 		self._f_module = module
 		integrator_params.pop("verbosity", None)
 		self.integrator = CudaEnsembleIntegrator(

@@ -394,31 +394,44 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 	indices = [[position[slot[k]] for k in order] for slot in loop.indices]
 	padded = _paddable(loop)
 
-	if padded and loop.n_index == 1 and not any(not _uniform(values) for values in consts):
-		# bare gather Σ g(y[idx]): byte offsets of four terms per 128-bit table read, four accumulators
-		width = (width + 3) // 4 * 4
-		ell = _ell(indices[0], loop.start, size, width, zero_slot)
-		quads = []
-		for kq in range(width // 4):
-			for m in range(size):
-				quads.extend(ell[(4*kq + j)*size + m] for j in range(4))
-		offset = tables.add_offsets(quads)
+	if padded and loop.n_index == 1 and not any(not _uniform(values) for values in consts) and 8 * zero_slot < 65536 and not tables.wide:
+		# bare gather Σ g(y[idx]).  Shared-memory bandwidth is what this kernel runs out of, so the table is
+		# as small as it gets: 16-bit byte offsets, two per 32-bit word (one wavefront per 64 gathers), and every
+		# pass of 32 statements is padded only to ITS longest statement.
+		n_pass = (size + 31) // 32
+		words, bases, widths = [], [], []
+		for p in range(n_pass):
+			members = range(32*p, min(size, 32*p + 32))
+			pass_width = max(lengths[m] for m in members)
+			pass_width += pass_width % 2
+			bases.append(len(words) // 2)      # in 32-bit words
+			widths.append(pass_width // 2)
+			for kp in range(pass_width // 2):
+				for lane in range(32):
+					m = 32*p + lane
+					pair = []
+					for k in (2*kp, 2*kp + 1):
+						inside = m < size and k < lengths[m]
+						pair.append(8 * (indices[0][loop.start[m] + k] if inside else zero_slot))
+					words.extend(pair)
+		offset = tables.add_u(words, align=2)
 		for c, values in enumerate(consts):
 			lines.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
 		term = printer.doprint(loop.body)
 		reads = f"y({loop.prefix}i0)"
 		assert reads in term
-		lines.append(f"\tdouble {name}_a = 0.0, {name}_b = 0.0, {name}_c = 0.0, {name}_d = 0.0;")
+		lines.append(f"\tdouble {name}_a = 0.0, {name}_b = 0.0;")
 		lines.append("\t{")
-		lines.append(f"\t\tconst uint4 *const quads = reinterpret_cast<const uint4 *>(JB_TO + {offset}) + m;")
+		lines.append(f"\t\tconstexpr int pass_base[{n_pass}] = {{ {', '.join(map(str, bases))} }}, pass_pairs[{n_pass}] = {{ {', '.join(map(str, widths))} }};")
+		lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
 		lines.append("#pragma unroll")
-		lines.append(f"\t\tfor (int k = 0; k < {width // 4}; ++k) {{")
-		lines.append(f"\t\t\tconst uint4 quad = quads[k * {size}];")
-		for accumulator, field in zip("abcd", "xyzw"):
-			lines.append(f"\t\t\t{name}_{accumulator} += {term.replace(reads, f'y.at(quad.{field})')};")
+		lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
+		lines.append("\t\t\tconst unsigned pair = pairs[k * 32];")
+		lines.append(f"\t\t\t{name}_a += {term.replace(reads, 'y.at(pair & 0xffffu)')};")
+		lines.append(f"\t\t\t{name}_b += {term.replace(reads, 'y.at(pair >> 16)')};")
 		lines.append("\t\t}")
 		lines.append("\t}")
-		lines.append(f"\tconst double {name} = ({name}_a + {name}_b) + ({name}_c + {name}_d);")
+		lines.append(f"\tconst double {name} = {name}_a + {name}_b;")
 		return
 
 	# general terms: one ELL table per varying slot; padding terms vanish, or are skipped by a per-lane count
@@ -513,7 +526,16 @@ def warp_statements(plan):
 	for g, group in enumerate(plan.groups):
 		base = position[group.outs[0]]
 		lines.append(f"// group {g}: {group.size} statement(s), components at positions {base} … {base + group.size - 1}")
-		lines.append(f"for (int m = lane; m < {group.size}; m += 32) {{")
+		n_pass = (group.size + 31) // 32
+		if group.loops and n_pass <= 16:
+			# passes unrolled: every pass knows its own trip counts at compile time
+			lines.append("#pragma unroll")
+			lines.append(f"for (int pass = 0; pass < {n_pass}; ++pass) {{")
+			lines.append("\tconst int m = lane + 32 * pass;")
+			lines.append(f"\tif (m >= {group.size}) break;")
+		else:
+			lines.append(f"for (int m = lane; m < {group.size}; m += 32) {{")
+			lines.append("\tconst int pass = m >> 5; (void) pass;")
 		for loop in group.loops:
 			_print_loop(printer, loop, group, position, tables, lines, zero_slot)
 		slot_preamble(group.prefix, group.consts, group.indices, "m", "\t")

@@ -6,6 +6,7 @@
 //   JB_MODULE_DRIVER           JB_DRV_ODE | JB_DRV_IVP_DENSE | JB_DRV_IVP_LAND
 //   JB_MODULE_STORAGE          JB_STORE_REGISTERS | JB_STORE_GLOBAL | JB_STORE_WARP
 //   JB_MODULE_THREADS          threads per block of the integrate kernel
+//   JB_MODULE_KREGS            warp storage: how many stage rows (plus the state) are cached in registers
 // and, for JB_STORE_WARP, the tables of the vectorised right-hand side: jb_generated::jb_tf (doubles),
 // jb_generated::jb_to (32-bit byte offsets), jb_generated::jb_tu (unsigned indices of type Sys::TU),
 // jb_generated::jb_component, Sys::TF_COUNT, Sys::TO_COUNT, Sys::TU_COUNT.
@@ -34,7 +35,7 @@ template <class S, bool W> struct WarpShared {
 };
 template <class S> struct WarpShared<S, true> {
 	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) ((S::TO_COUNT * sizeof(unsigned) + (S::TU_COUNT + S::N) * sizeof(typename S::TU) + 15) / 16) * 2;
-	static constexpr int ROWS = 2 + ModuleLayout::KR + (ModuleLayout::DENSE ? 1 : 0);     // Y, Z, K rows, y_old
+	static constexpr int ROWS = WarpStore<S, Tab, JB_MODULE_DRIVER, JB_MODULE_KREGS>::ROWS;
 	static constexpr int WARPS = JB_MODULE_THREADS / 32;
 	static constexpr size_t BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * ROWS * S::NROW);
 	static constexpr size_t EVAL_BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * 2 * S::NROW);
@@ -65,7 +66,7 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * Shared::ROWS * Sys::NROW;
 		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
 		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < a.B; b += stride) {
-			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b, mine, jb_smem);
+			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
 			__syncwarp();
 		}
 	} else {
@@ -76,48 +77,44 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 }
 
 // dY = f(t, Y): the batched counterpart of py_f (jitced_template.c:67-116)
-template <int MODE>
+template <int MODE, class S = Sys>
 __global__ void __launch_bounds__(JB_MODULE_THREADS)
 jb_eval_f_kernel(const double *t, const double *Y, const double *P, double *dY, int64_t B)
 {
 	if constexpr (MODE == JB_STORE_WARP) {
 		extern __shared__ __align__(16) double jb_smem[];
-		stage_tables<Sys>(jb_smem);
+		stage_tables<S>(jb_smem);
 		const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-		double *const in = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * 2 * Sys::NROW;
-		double *const out = in + Sys::NROW;
-		const typename Sys::TU *const comp = Sys::components(jb_smem);
-		if (lane == 0) for (int i = Sys::N; i < Sys::NROW; ++i) in[i] = 0.0;
+		double *const in = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * 2 * S::NROW;
+		double *const out = in + S::NROW;
+		const typename S::TU *const comp = S::components(jb_smem);
+		if (lane == 0) for (int i = S::N; i < S::NROW; ++i) in[i] = 0.0;
 		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
 		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < B; b += stride) {
-			Sys::Par par;
+			typename S::Par par;
 #pragma unroll
-			for (int k = 0; k < Sys::NP; ++k) par.v[k] = P[b * Sys::NP + k];
-			for (int i = lane; i < Sys::N; i += 32) in[i] = Y[b * Sys::N + comp[i]];
-			const SVec vin{in};
-			SVec vout{out};
-			RhsCall<Sys, MODE>::call(t[b], vin, vout, par, jb_smem);
-			for (int i = lane; i < Sys::N; i += 32) dY[b * Sys::N + comp[i]] = out[i];
+			for (int k = 0; k < S::NP; ++k) par.v[k] = P[b * S::NP + k];
+			for (int i = lane; i < S::N; i += 32) in[i] = Y[b * S::N + comp[i]];
+			rhs_warp_outlined<S>(t[b], in, out, par, jb_smem);
+			for (int i = lane; i < S::N; i += 32) dY[b * S::N + comp[i]] = out[i];
 			__syncwarp();
 		}
 	} else {
 		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 		if (b >= B) return;
-		Sys::Par par;
+		typename S::Par par;
 #pragma unroll
-		for (int k = 0; k < Sys::NP; ++k) par.v[k] = P[tile_offset(b, Sys::NP) + k * TILE];
-		const int64_t off = tile_offset(b, Sys::N);
+		for (int k = 0; k < S::NP; ++k) par.v[k] = P[tile_offset(b, S::NP) + k * TILE];
+		const int64_t off = tile_offset(b, S::N);
 		if constexpr (MODE == JB_STORE_REGISTERS) {
-			RVec<Sys::N> y, dy;
+			RVec<S::N> y, dy;
 #pragma unroll
-			for (int i = 0; i < Sys::N; ++i) y.v[i] = Y[off + i * TILE];
-			RhsCall<Sys, MODE>::call(t[b], y, dy, par, nullptr);
+			for (int i = 0; i < S::N; ++i) y.v[i] = Y[off + i * TILE];
+			S::rhs(t[b], y, dy, par);
 #pragma unroll
-			for (int i = 0; i < Sys::N; ++i) dY[off + i * TILE] = dy.v[i];
+			for (int i = 0; i < S::N; ++i) dY[off + i * TILE] = dy.v[i];
 		} else {
-			const GVec in{const_cast<double *>(Y) + off};
-			GVec out{dY + off};
-			RhsCall<Sys, MODE>::call(t[b], in, out, par, nullptr);
+			rhs_outlined<S>(t[b], Y + off, dY + off, par);
 		}
 	}
 }

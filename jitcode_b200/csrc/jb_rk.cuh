@@ -150,16 +150,9 @@ template <class Tab, int DRIVER> struct Layout {
 	static constexpr int WORK_VECTORS = 1 + KR + (DENSE ? 1 : 0);   // Z, K rows, y_old
 };
 
-template <class Sys, int MODE> struct RhsCall;
+// ---------------------------------------------------------------------------------------------
+// calling the generated right-hand side
 
-// registers: the right-hand side is inlined at every call site
-template <class Sys> struct RhsCall<Sys, JB_STORE_REGISTERS> {
-	template <class VI, class VO>
-	static __device__ __forceinline__ void call(double t, const VI &in, VO &out, const typename Sys::Par &par, const void *)
-	{
-		Sys::rhs(t, in, out, par);
-	}
-};
 // global: one out-of-line copy of the (large) right-hand side
 template <class Sys>
 __device__ __noinline__ void rhs_outlined(double t, const double *__restrict__ in, double *__restrict__ out,
@@ -169,12 +162,6 @@ __device__ __noinline__ void rhs_outlined(double t, const double *__restrict__ i
 	GVec vo{out};
 	Sys::rhs(t, vi, vo, par);
 }
-template <class Sys> struct RhsCall<Sys, JB_STORE_GLOBAL> {
-	static __device__ __forceinline__ void call(double t, const GVec &in, GVec &out, const typename Sys::Par &par, const void *)
-	{
-		rhs_outlined<Sys>(t, in.p, out.p, par);
-	}
-};
 // warp: one out-of-line copy of the vectorised right-hand side; lanes read what other lanes wrote
 template <class Sys>
 __device__ __noinline__ void rhs_warp_outlined(double t, const double *__restrict__ in, double *__restrict__ out,
@@ -186,81 +173,209 @@ __device__ __noinline__ void rhs_warp_outlined(double t, const double *__restric
 	Sys::rhs_warp(t, vi, vo, par, (int) (threadIdx.x & 31), tables);
 	__syncwarp();
 }
-template <class Sys> struct RhsCall<Sys, JB_STORE_WARP> {
-	static __device__ __forceinline__ void call(double t, const SVec &in, SVec &out, const typename Sys::Par &par, const void *tables)
-	{
-		rhs_warp_outlined<Sys>(t, in.p, out.p, par, tables);
-	}
-};
 
-// How the components of a vector are spread over threads: all of them on this thread (registers,
-// global) or strided over the lanes of the warp (warp storage).
-template <int N, int MODE> struct Components {
-	static constexpr bool WARP = MODE == JB_STORE_WARP;
-	static constexpr int UNR = MODE == JB_STORE_REGISTERS ? (N > 0 ? N : 1) : 4;
-
-	template <class F>
-	static __device__ __forceinline__ void for_each(F &&body)
-	{
-		if constexpr (WARP) {
-			for (int i = threadIdx.x & 31; i < N; i += 32) body(i);
-		} else {
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) body(i);
-		}
-	}
-
-	// Σ_i value(i), known to every thread that works on the trajectory
-	template <class F>
-	static __device__ __forceinline__ double sum(F &&value)
-	{
-		double total = 0.0;
-		if constexpr (WARP) {
-			for (int i = threadIdx.x & 31; i < N; i += 32) total += value(i);
-			return warp_sum(total);
-		} else {
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) total += value(i);
-			return total;
-		}
-	}
-
-	// two sums in one pass: value(i, s0, s1) adds its contributions
-	template <class F>
-	static __device__ __forceinline__ void sum2(F &&value, double &s0, double &s1)
-	{
-		s0 = s1 = 0.0;
-		if constexpr (WARP) {
-			for (int i = threadIdx.x & 31; i < N; i += 32) value(i, s0, s1);
-			s0 = warp_sum(s0);
-			s1 = warp_sum(s1);
-		} else {
-#pragma unroll UNR
-			for (int i = 0; i < N; ++i) value(i, s0, s1);
-		}
-	}
-};
+// ---------------------------------------------------------------------------------------------
+// Storage policies.  Common interface used by the stepper and by run_trajectory:
+//   for_each(body(i, r)), sum(value(i, r)), sum2(value(i, r, s0, s1))     component loops / reductions
+//   y, z, yo, k<J> (i, r)  and  set_y, set_z, set_yo, set_k<J> (i, r, v)  element access
+//   rhs_y<J>(t), rhs_z<J>(t)      K[J] = f(t, Y) / f(t, Z)
+//   accept_y()                    Y ← Z            (Z becomes scratch)
+//   save_old()                    y_old ← Y        (before accept_y, dense driver)
+//   fsal<JD, JS>()                K[JD] ← K[JS]    (K[JS] becomes scratch)
+// `i` is the position of the component in the vector, `r` the pass of the lane-strided loop (a
+// compile-time constant where rows are cached in registers, otherwise a dummy).
 
 template <class Sys, class Tab, int DRIVER, int MODE>
-struct Stepper {
+struct ThreadStore {        // one thread per trajectory: registers (MODE 0) or the caller's tiled workspace (MODE 1)
 	static constexpr int N = Sys::N;
 	using L = Layout<Tab, DRIVER>;
-	using C = Components<N, MODE>;
 	static constexpr bool REG = MODE == JB_STORE_REGISTERS;
-	static constexpr bool WARP = MODE == JB_STORE_WARP;
-	static constexpr bool DENSE = L::DENSE;
-	static constexpr bool IVP = L::IVP;
+	static constexpr bool WARP = false;
 	static constexpr int KR = L::KR;
-	static constexpr int S = Tab::NSTAGE;
-	using Vec = typename std::conditional<REG, RVec<N>, typename std::conditional<WARP, SVec, GVec>::type>::type;
-	using IVec = typename std::conditional<WARP, SVec, GVec>::type;    // persistent solver vectors in the caller's memory
-	using UVec = typename std::conditional<WARP, PVec<typename Sys::TU>, GVec>::type;   // the caller's state and samples
+	static constexpr int UNR = REG ? (N > 0 ? N : 1) : 4;   // unroll factor of component loops
+	using Vec = typename std::conditional<REG, RVec<N>, GVec>::type;
+	using IVec = GVec;      // persistent solver vectors in the caller's memory
+	using UVec = GVec;      // the caller's state and samples
 
 	Vec Y, Z, YO, K[KR];
 	typename Sys::Par par;
+
+	template <class F> __device__ __forceinline__ void for_each(F &&body)
+	{
+#pragma unroll UNR
+		for (int i = 0; i < N; ++i) body(i, Idx<0>{});
+	}
+	template <class F> __device__ __forceinline__ double sum(F &&value)
+	{
+		double total = 0.0;
+#pragma unroll UNR
+		for (int i = 0; i < N; ++i) total += value(i, Idx<0>{});
+		return total;
+	}
+	template <class F> __device__ __forceinline__ void sum2(F &&value, double &s0, double &s1)
+	{
+		s0 = s1 = 0.0;
+#pragma unroll UNR
+		for (int i = 0; i < N; ++i) value(i, Idx<0>{}, s0, s1);
+	}
+
+	template <class R> __device__ __forceinline__ double y(int i, R) const { return Y(i); }
+	template <class R> __device__ __forceinline__ double z(int i, R) const { return Z(i); }
+	template <class R> __device__ __forceinline__ double yo(int i, R) const { return YO(i); }
+	template <int J, class R> __device__ __forceinline__ double k(int i, R) const { return K[J](i); }
+	template <class R> __device__ __forceinline__ void set_y(int i, R, double v) { Y.set(i, v); }
+	template <class R> __device__ __forceinline__ void set_z(int i, R, double v) { Z.set(i, v); }
+	template <class R> __device__ __forceinline__ void set_yo(int i, R, double v) { YO.set(i, v); }
+	template <int J, class R> __device__ __forceinline__ void set_k(int i, R, double v) { K[J].set(i, v); }
+
+	template <int J> __device__ __forceinline__ void call(double t, const Vec &in)
+	{
+		if constexpr (REG) Sys::rhs(t, in, K[J], par);
+		else rhs_outlined<Sys>(t, in.p, K[J].p, par);
+	}
+	template <int J> __device__ __forceinline__ void rhs_y(double t) { call<J>(t, Y); }
+	template <int J> __device__ __forceinline__ void rhs_z(double t) { call<J>(t, Z); }
+	__device__ __forceinline__ void accept_y() { take(Y, Z); }
+	__device__ __forceinline__ void save_old() { take(YO, Y); }
+	template <int JD, int JS> __device__ __forceinline__ void fsal() { take(K[JD], K[JS]); }
+};
+
+template <class Sys, class Tab, int DRIVER, int KREGS>
+struct WarpStore {          // one warp per trajectory, lanes across components
+	static constexpr int N = Sys::N;
+	static constexpr int NROW = Sys::NROW;
+	using L = Layout<Tab, DRIVER>;
+	static constexpr bool REG = false;
+	static constexpr bool WARP = true;
+	static constexpr int KR = L::KR;
+	static constexpr bool CACHED = KREGS > 0;           // Y and K[0 … KREGS) live in registers, lane-strided
+	static constexpr int NP = (N + 31) / 32;            // passes of a lane-strided loop
+	// shared-memory rows of one warp: Z, [staging row of the right-hand side], [Y], [y_old], K[KREGS … KR)
+	static constexpr int ROWS = 1 + (CACHED ? 1 : 1) + (L::DENSE ? 1 : 0) + (KR - KREGS);
+	using IVec = SVec;
+	using UVec = PVec<typename Sys::TU>;
+
+	double ry[CACHED ? NP : 1];
+	double rk[CACHED ? KREGS : 1][CACHED ? NP : 1];
+	double *pY, *pZ, *pYO, *pF, *pK[KR];
+	typename Sys::Par par;
+	const void *tables;
+
+	__device__ __forceinline__ void bind(double *smem)
+	{
+		int row = 0;
+		pZ = smem + NROW * row++;
+		if constexpr (CACHED) { pF = smem + NROW * row++; pY = nullptr; }
+		else { pY = smem + NROW * row++; pF = nullptr; }
+		pYO = L::DENSE ? smem + NROW * row++ : nullptr;
+#pragma unroll
+		for (int j = 0; j < KR; ++j) pK[j] = j < KREGS ? nullptr : smem + NROW * (row + j - KREGS);
+		// position N … NROW-1 of every row holds 0: padding target of the vectorised loops
+		for (int r = threadIdx.x & 31; r < ROWS; r += 32)
+			for (int i = N; i < NROW; ++i) smem[r * NROW + i] = 0.0;
+	}
+
+	template <class F> __device__ __forceinline__ void for_each(F &&body)
+	{
+		const int lane = threadIdx.x & 31;
+		if constexpr (CACHED) {
+			static_for<0, NP>([&](auto r) {
+				const int i = lane + 32 * r;
+				if (32 * (r + 1) <= N || i < N) body(i, r);
+			});
+		} else {
+			for (int i = lane; i < N; i += 32) body(i, Idx<0>{});
+		}
+	}
+	template <class F> __device__ __forceinline__ double sum(F &&value)
+	{
+		double total = 0.0;
+		for_each([&](int i, auto r) { total += value(i, r); });
+		return warp_sum(total);
+	}
+	template <class F> __device__ __forceinline__ void sum2(F &&value, double &s0, double &s1)
+	{
+		double a = 0.0, b = 0.0;
+		for_each([&](int i, auto r) { value(i, r, a, b); });
+		s0 = warp_sum(a);
+		s1 = warp_sum(b);
+	}
+
+	template <class R> __device__ __forceinline__ double y(int i, R r) const
+	{
+		if constexpr (CACHED) return ry[r];
+		else return pY[i];
+	}
+	template <class R> __device__ __forceinline__ double z(int i, R) const { return pZ[i]; }
+	template <class R> __device__ __forceinline__ double yo(int i, R) const { return pYO[i]; }
+	template <int J, class R> __device__ __forceinline__ double k(int i, R r) const
+	{
+		if constexpr (J < KREGS) return rk[J][r];
+		else return pK[J][i];
+	}
+	template <class R> __device__ __forceinline__ void set_y(int i, R r, double v)
+	{
+		if constexpr (CACHED) ry[r] = v;
+		else pY[i] = v;
+	}
+	template <class R> __device__ __forceinline__ void set_z(int i, R, double v) { pZ[i] = v; }
+	template <class R> __device__ __forceinline__ void set_yo(int i, R, double v) { pYO[i] = v; }
+	template <int J, class R> __device__ __forceinline__ void set_k(int i, R r, double v)
+	{
+		if constexpr (J < KREGS) rk[J][r] = v;
+		else pK[J][i] = v;
+	}
+
+	template <int J> __device__ __forceinline__ void call(double t, const double *in)
+	{
+		if constexpr (J < KREGS) {
+			rhs_warp_outlined<Sys>(t, in, pF, par, tables);
+			for_each([&](int i, auto r) { rk[J][r] = pF[i]; });
+		} else {
+			rhs_warp_outlined<Sys>(t, in, pK[J], par, tables);
+		}
+	}
+	template <int J> __device__ __forceinline__ void rhs_z(double t) { call<J>(t, pZ); }
+	template <int J> __device__ __forceinline__ void rhs_y(double t)
+	{
+		if constexpr (CACHED) {
+			for_each([&](int i, auto r) { pZ[i] = ry[r]; });     // Z is scratch wherever f(t, Y) is needed
+			call<J>(t, pZ);
+		} else {
+			call<J>(t, pY);
+		}
+	}
+	__device__ __forceinline__ void accept_y()
+	{
+		if constexpr (CACHED) for_each([&](int i, auto r) { ry[r] = pZ[i]; });
+		else { double *const p = pY; pY = pZ; pZ = p; }
+	}
+	__device__ __forceinline__ void save_old()
+	{
+		if constexpr (CACHED) for_each([&](int i, auto r) { pYO[i] = ry[r]; });
+		else { double *const p = pYO; pYO = pY; pY = p; }
+	}
+	template <int JD, int JS> __device__ __forceinline__ void fsal()
+	{
+		if constexpr (JD >= KREGS && JS >= KREGS) { double *const p = pK[JD]; pK[JD] = pK[JS]; pK[JS] = p; }
+		else for_each([&](int i, auto r) { set_k<JD>(i, r, k<JS>(i, r)); });
+	}
+};
+
+// ---------------------------------------------------------------------------------------------
+// the Runge–Kutta arithmetic, written once against the storage interface
+
+template <class Sys, class Tab, int DRIVER, class Store>
+struct Stepper : Store {
+	static constexpr int N = Sys::N;
+	using L = Layout<Tab, DRIVER>;
+	static constexpr bool DENSE = L::DENSE;
+	static constexpr bool IVP = L::IVP;
+	static constexpr int S = Tab::NSTAGE;
+	static constexpr bool WARP = Store::WARP;
+
 	double atol_s, rtol;
 	const double *atol_vec;
-	const void *tables;
 	const typename Sys::TU *comp;     // warp storage: component stored at each position
 
 	__device__ __forceinline__ double atol(int i) const
@@ -269,22 +384,17 @@ struct Stepper {
 		else return atol_vec ? atol_vec[i] : atol_s;
 	}
 
-	__device__ __forceinline__ void rhs(double t, const Vec &in, Vec &out)
-	{
-		RhsCall<Sys, MODE>::call(t, in, out, par, tables);
-	}
-
-	// dst = Y + h * Σ_{j<ROW} a(ROW,j) K[j]   (stage input for ROW < S, solution for ROW == S)
+	// Z = Y + h * Σ_{j<ROW} a(ROW,j) K[j]   (stage input for ROW < S, solution for ROW == S)
 	template <int ROW>
-	__device__ __forceinline__ void combine(Vec &dst, double h)
+	__device__ __forceinline__ void combine(double h)
 	{
-		C::for_each([&](int i) {
+		this->for_each([&](int i, auto r) {
 			double acc = 0.0;
 			static_for<0, ROW>([&](auto j) {
 				constexpr double a = Coef<Tab>::a(ROW, j);
-				if constexpr (a != 0.0) acc = fma(a, K[j](i), acc);
+				if constexpr (a != 0.0) acc = fma(a, this->template k<j>(i, r), acc);
 			});
-			dst.set(i, fma(h, acc, Y(i)));
+			this->set_z(i, r, fma(h, acc, this->y(i, r)));
 		});
 	}
 
@@ -292,35 +402,35 @@ struct Stepper {
 	__device__ __forceinline__ double attempt(double t, double h)
 	{
 		static_for<1, S>([&](auto s) {
-			combine<s>(Z, h);
+			combine<s>(h);
 			constexpr double cs = Coef<Tab>::c(s);
-			rhs(fma(cs, h, t), Z, K[s]);
+			this->template rhs_z<s>(fma(cs, h, t));
 		});
-		combine<S>(Z, h);
+		combine<S>(h);
 		if constexpr (Tab::ERR_NEEDS_FSAL) {
-			rhs(t + h, Z, K[S]);
-			const double sum = C::sum([&](int i) {
+			this->template rhs_z<S>(t + h);
+			const double sum = this->sum([&](int i, auto r) {
 				double e = 0.0;
 				static_for<0, Tab::KROWS>([&](auto j) {
 					constexpr double w = DP5::E[j];
-					if constexpr (w != 0.0) e = fma(w, K[j](i), e);
+					if constexpr (w != 0.0) e = fma(w, this->template k<j>(i, r), e);
 				});
-				const double sk = fma(rtol, fmax(fabs(Y(i)), fabs(Z(i))), atol(i));
+				const double sk = fma(rtol, fmax(fabs(this->y(i, r)), fabs(this->z(i, r))), atol(i));
 				const double q = h * e / sk;
 				return q * q;
 			});
 			return sqrt(sum / N);
 		} else {
 			double s5, s3;
-			C::sum2([&](int i, double &a5, double &a3) {
+			this->sum2([&](int i, auto r, double &a5, double &a3) {
 				double e5 = 0.0, e3 = 0.0;
 				static_for<0, S>([&](auto j) {
 					constexpr double w5 = dop853::E5[j];
 					constexpr double w3 = dop853::E3[j];
-					if constexpr (w5 != 0.0) e5 = fma(w5, K[j](i), e5);
-					if constexpr (w3 != 0.0) e3 = fma(w3, K[j](i), e3);
+					if constexpr (w5 != 0.0) e5 = fma(w5, this->template k<j>(i, r), e5);
+					if constexpr (w3 != 0.0) e3 = fma(w3, this->template k<j>(i, r), e3);
 				});
-				const double sk = fma(rtol, fmax(fabs(Y(i)), fabs(Z(i))), atol(i));
+				const double sk = fma(rtol, fmax(fabs(this->y(i, r)), fabs(this->z(i, r))), atol(i));
 				e5 /= sk;
 				e3 /= sk;
 				a5 = fma(e5, e5, a5);
@@ -336,22 +446,23 @@ struct Stepper {
 	// the 8th-order pair evaluates f(t+h, y_new) only once the step is accepted
 	__device__ __forceinline__ void finish_accepted(double t, double h)
 	{
-		if constexpr (!Tab::ERR_NEEDS_FSAL) rhs(t + h, Z, K[S]);
+		if constexpr (!Tab::ERR_NEEDS_FSAL) this->template rhs_z<S>(t + h);
 	}
 
 	// Σ_i (v_i / (atol_i + rtol |Y_i|))², the weighted norms of both start-up rules
 	template <class F>
 	__device__ __forceinline__ double weighted_sq(F &&value)
 	{
-		return C::sum([&](int i) {
-			const double q = value(i) / fma(rtol, fabs(Y(i)), atol(i));
+		return this->sum([&](int i, auto r) {
+			const double q = value(i, r) / fma(rtol, fabs(this->y(i, r)), atol(i));
 			return q * q;
 		});
 	}
 
-	__device__ __forceinline__ void euler_probe(const Vec &f0, double h)
+	// Z = Y + h K[0]
+	__device__ __forceinline__ void euler_probe(double h)
 	{
-		C::for_each([&](int i) { Z.set(i, fma(h, f0(i), Y(i))); });
+		this->for_each([&](int i, auto r) { this->set_z(i, r, fma(h, this->template k<0>(i, r), this->y(i, r))); });
 	}
 };
 
@@ -441,17 +552,17 @@ __device__ __forceinline__ double lyap_transversal(Vec &Y)
 // thread.  Warp storage: called by all 32 lanes of the trajectory's warp with identical scalar
 // state; `smem` is the warp's private stage area, `tables` the staged tables of the right-hand side.
 
-template <class Sys, class Tab, int DRIVER, int MODE>
+template <class Sys, class Tab, int DRIVER, int MODE, int KREGS = 0>
 __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b, double *smem = nullptr, const void *tables = nullptr)
 {
-	using ST = Stepper<Sys, Tab, DRIVER, MODE>;
-	using C = typename ST::C;
+	constexpr bool WARP = MODE == JB_STORE_WARP;
+	using Store = typename std::conditional<WARP, WarpStore<Sys, Tab, DRIVER, KREGS>, ThreadStore<Sys, Tab, DRIVER, MODE>>::type;
+	using ST = Stepper<Sys, Tab, DRIVER, Store>;
 	using IVec = typename ST::IVec;
 	using UVec = typename ST::UVec;
 	constexpr int N = Sys::N;
 	constexpr int S = Tab::NSTAGE;
-	constexpr bool REG = ST::REG;
-	constexpr bool WARP = ST::WARP;
+	constexpr bool REG = MODE == JB_STORE_REGISTERS;
 	constexpr bool DENSE = ST::DENSE;
 	constexpr bool IVP = ST::IVP;
 	constexpr int NLY = Sys::NL > 0 ? Sys::NL : 1;
@@ -464,7 +575,6 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	st.rtol = a.rtol;
 	st.atol_s = a.atol;
 	st.atol_vec = a.atol_vec;
-	st.tables = tables;
 	st.comp = nullptr;
 #pragma unroll
 	for (int k = 0; k < Sys::NP; ++k)
@@ -479,7 +589,10 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 		if constexpr (WARP) return UVec{base, st.comp};
 		else return UVec{base};
 	};
-	if constexpr (WARP) st.comp = Sys::components(tables);
+	if constexpr (WARP) {
+		st.tables = tables;
+		st.comp = Sys::components(tables);
+	}
 	const UVec Yc = user(a.Y + off);
 	const IVec Fc{IVP ? a.state + SV_F * vec + off : nullptr};
 	const IVec Oc{DENSE ? a.state + SV_YOLD * vec + off : nullptr};
@@ -490,16 +603,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 #pragma unroll
 		for (int i = 0; i < N; ++i) st.Y.v[i] = Yc(i);
 	} else if constexpr (WARP) {
-		// rows of NROW > N doubles: position N always holds 0 (padding target of the vectorised loops)
-		constexpr int NROW = Sys::NROW;
-		st.Y.p = smem;
-		st.Z.p = smem + NROW;
-#pragma unroll
-		for (int j = 0; j < ST::KR; ++j) st.K[j].p = smem + (2 + j) * NROW;
-		if constexpr (DENSE) st.YO.p = smem + (2 + ST::KR) * NROW;
-		for (int r = threadIdx.x & 31; r < 2 + ST::KR + (DENSE ? 1 : 0); r += 32)
-			for (int i = N; i < NROW; ++i) smem[r * NROW + i] = 0.0;
-		C::for_each([&](int i) { st.Y.set(i, Yc(i)); });
+		st.bind(smem);
+		st.for_each([&](int i, auto r) { st.set_y(i, r, Yc(i)); });
 	} else {
 		st.Y.p = Yc.p;
 		st.Z.p = a.work + off;
@@ -534,20 +639,20 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 		if constexpr (DRIVER == JB_DRV_ODE) {
 			// ================= Hairer DOPRI5 / DOP853, fresh start (dopri5.f DOPCOR, dop853.f DP86CO)
 			if (T > t) {
-				st.rhs(t, st.Y, st.K[0]);
+				st.template rhs_y<0>(t);
 				const double hmax = a.max_step > 0.0 ? a.max_step : fabs(T - t);
 				double h;
 				if (a.first_step > 0.0) {
 					h = a.first_step;
 				} else {
 					// HINIT
-					const double dnf = st.weighted_sq([&](int i) { return st.K[0](i); });
-					const double dny = st.weighted_sq([&](int i) { return st.Y(i); });
+					const double dnf = st.weighted_sq([&](int i, auto r) { return st.template k<0>(i, r); });
+					const double dny = st.weighted_sq([&](int i, auto r) { return st.y(i, r); });
 					h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
 					h = fmin(h, hmax);
-					st.euler_probe(st.K[0], h);
-					st.rhs(t + h, st.Z, st.K[1]);
-					const double der2 = sqrt(st.weighted_sq([&](int i) { return st.K[1](i) - st.K[0](i); })) / h;
+					st.euler_probe(h);
+					st.template rhs_z<1>(t + h);
+					const double der2 = sqrt(st.weighted_sq([&](int i, auto r) { return st.template k<1>(i, r) - st.template k<0>(i, r); })) / h;
 					const double der12 = fmax(fabs(der2), sqrt(dnf));
 					const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h) * 1e-3)
 							: pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
@@ -572,8 +677,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 						facold = fmax(err, 1e-4);
 						++n_acc;
 						st.finish_accepted(t, h);
-						take(st.Y, st.Z);
-						take(st.K[0], st.K[S]);
+						st.accept_y();
+						st.template fsal<0, S>();
 						t = last ? T : t + h;
 						if (fabs(hnew) > hmax) hnew = hmax;
 						if (reject) hnew = fmin(fabs(hnew), fabs(h));
@@ -595,16 +700,16 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			// ================= scipy solve_ivp stepper (rk.py RungeKutta), persistent between launches
 			if (!initialised) {
 				// RungeKutta.__init__: f = fun(t, y); select_initial_step with t_bound = ∞
-				st.rhs(t, st.Y, st.K[0]);
+				st.template rhs_y<0>(t);
 				if (a.first_step > 0.0) {
 					h_abs = a.first_step;
 				} else {
-					const double d0 = sqrt(st.weighted_sq([&](int i) { return st.Y(i); }) / N);
-					const double d1 = sqrt(st.weighted_sq([&](int i) { return st.K[0](i); }) / N);
+					const double d0 = sqrt(st.weighted_sq([&](int i, auto r) { return st.y(i, r); }) / N);
+					const double d1 = sqrt(st.weighted_sq([&](int i, auto r) { return st.template k<0>(i, r); }) / N);
 					const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-					st.euler_probe(st.K[0], h0);
-					st.rhs(t + h0, st.Z, st.K[1]);
-					const double d2 = sqrt(st.weighted_sq([&](int i) { return st.K[1](i) - st.K[0](i); }) / N) / h0;
+					st.euler_probe(h0);
+					st.template rhs_z<1>(t + h0);
+					const double d2 = sqrt(st.weighted_sq([&](int i, auto r) { return st.template k<1>(i, r) - st.template k<0>(i, r); }) / N) / h0;
 					const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3)
 							: pow(0.01 / fmax(d1, d2), 1.0 / (Tab::ERR_ORDER + 1));
 					h_abs = fmin(fmin(100.0 * h0, h1), a.max_step > 0.0 ? a.max_step : INFINITY);
@@ -620,10 +725,10 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			while (status == JB_OK && (t < T || (DENSE && !(t_old == t_old)))) {
 				// ---- begin a step: K[0] = f(t, Y)
 				if (pending_f) {
-					take(st.K[0], st.K[S]);
+					st.template fsal<0, S>();
 					pending_f = false;
 				} else if (!have_f) {
-					C::for_each([&](int i) { st.K[0].set(i, Fc(i)); });
+					st.for_each([&](int i, auto r) { st.template set_k<0>(i, r, Fc(i)); });
 				}
 				have_f = true;
 				// ---- RungeKutta._step_impl
@@ -644,8 +749,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 						h_abs *= factor;
 						++n_acc;
 						st.finish_accepted(t, h);
-						if constexpr (DENSE) take(st.YO, st.Y);
-						take(st.Y, st.Z);
+						if constexpr (DENSE) st.save_old();
+						st.accept_y();
 						t_old = t;
 						h_prev = h;
 						t = t_new;
@@ -669,46 +774,46 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			if (!interpolant) {
 				// ---- materialise the interpolant of the last step (rk.py:178-180, 693-712)
 				if constexpr (std::is_same<Tab, DP5>::value) {
-					C::for_each([&](int i) {
+					st.for_each([&](int i, auto r) {
 						static_for<0, 4>([&](auto p) {
 							double q = 0.0;
 							static_for<0, 7>([&](auto j) {
 								constexpr double w = DP5::P[j][p];
-								if constexpr (w != 0.0) q = fma(w, st.K[j](i), q);
+								if constexpr (w != 0.0) q = fma(w, st.template k<j>(i, r), q);
 							});
 							Qc(p).set(i, q);
 						});
-						Oc.set(i, st.YO(i));
+						Oc.set(i, st.yo(i, r));
 					});
 				} else {
 					// three extra stages from (t_old, y_old), then F[0..6]
 					static_for<S + 1, S + 4>([&](auto s) {
-						C::for_each([&](int i) {
+						st.for_each([&](int i, auto r) {
 							double acc = 0.0;
 							static_for<0, s>([&](auto j) {
-								constexpr double c = dop853::A[s][j];
-								if constexpr (c != 0.0) acc = fma(c, st.K[j](i), acc);
+								constexpr double c = Coef<DOP853>::a(s, j);
+								if constexpr (c != 0.0) acc = fma(c, st.template k<j>(i, r), acc);
 							});
-							st.Z.set(i, fma(h_prev, acc, st.YO(i)));
+							st.set_z(i, r, fma(h_prev, acc, st.yo(i, r)));
 						});
 						constexpr double cs = Coef<DOP853>::c(s);
-						st.rhs(fma(cs, h_prev, t_old), st.Z, st.K[s]);
+						st.template rhs_z<s>(fma(cs, h_prev, t_old));
 					});
-					C::for_each([&](int i) {
-						const double delta = st.Y(i) - st.YO(i);
-						const double f_old = st.K[0](i), f_new = st.K[S](i);
+					st.for_each([&](int i, auto r) {
+						const double delta = st.y(i, r) - st.yo(i, r);
+						const double f_old = st.template k<0>(i, r), f_new = st.template k<S>(i, r);
 						Qc(0).set(i, delta);
 						Qc(1).set(i, h_prev * f_old - delta);
 						Qc(2).set(i, 2.0 * delta - h_prev * (f_new + f_old));
-						static_for<0, 4>([&](auto r) {
+						static_for<0, 4>([&](auto row) {
 							double q = 0.0;
 							static_for<0, 16>([&](auto j) {
-								constexpr double w = dop853::D[r][j];
-								if constexpr (w != 0.0) q = fma(w, st.K[j](i), q);
+								constexpr double w = dop853::D[row][j];
+								if constexpr (w != 0.0) q = fma(w, st.template k<j>(i, r), q);
 							});
-							Qc(3 + r).set(i, h_prev * q);
+							Qc(3 + row).set(i, h_prev * q);
 						});
-						Oc.set(i, st.YO(i));
+						Oc.set(i, st.yo(i, r));
 					});
 				}
 				interpolant = true;
@@ -717,7 +822,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			const double hh = t - t_old;
 			const double x = (T - t_old) / hh;
 			const bool restart = a.post != JB_POST_NONE;
-			C::for_each([&](int i) {
+			st.for_each([&](int i, auto pass) {
 				double r;
 				if constexpr (std::is_same<Tab, DP5>::value) {
 					r = Qc(3)(i);
@@ -733,7 +838,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					});
 					r += Oc(i);
 				}
-				if (restart) st.Z.set(i, r);
+				if (restart) st.set_z(i, pass, r);
 				else {
 					res.set(i, r);
 					if (rec.p) rec.set(i, r);
@@ -741,7 +846,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			});
 			if (restart) {
 				// jitcode_lyap.integrate re-creates the stepper at (T, sample) (_jitcode.py:773)
-				take(st.Y, st.Z);
+				st.accept_y();
 				t = T;
 				initialised = false;
 				interpolant = false;
@@ -779,11 +884,11 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			}
 		}
 		if constexpr (!DENSE) {
-			if (rec.p) C::for_each([&](int i) { rec.set(i, st.Y(i)); });
+			if (rec.p) st.for_each([&](int i, auto r) { rec.set(i, st.y(i, r)); });
 		} else if (a.post != JB_POST_NONE) {
-			C::for_each([&](int i) {
-				res.set(i, st.Y(i));
-				if (rec.p) rec.set(i, st.Y(i));
+			st.for_each([&](int i, auto r) {
+				res.set(i, st.y(i, r));
+				if (rec.p) rec.set(i, st.y(i, r));
 			});
 		}
 	}
@@ -793,12 +898,14 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 #pragma unroll
 		for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
 	} else {
-		if (WARP || st.Y.p != Yc.p) C::for_each([&](int i) { Yc.set(i, st.Y(i)); });
+		bool copy_back = WARP;
+		if constexpr (!WARP) copy_back = st.Y.p != Yc.p;
+		if (copy_back) st.for_each([&](int i, auto r) { Yc.set(i, st.y(i, r)); });
 	}
 	if constexpr (IVP) {
 		if (pending_f || have_f) {
-			const auto &F = pending_f ? st.K[S] : st.K[0];
-			C::for_each([&](int i) { Fc.set(i, F(i)); });
+			if (pending_f) st.for_each([&](int i, auto r) { Fc.set(i, st.template k<S>(i, r)); });
+			else st.for_each([&](int i, auto r) { Fc.set(i, st.template k<0>(i, r)); });
 		}
 		if (leader) {
 			a.sstate[SS_H_ABS * ld + b] = h_abs;

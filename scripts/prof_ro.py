@@ -10,7 +10,8 @@ name = sys.argv[3] if len(sys.argv) > 3 else "dopri5"
 system = W.roessler_network(100)
 Y0, pars = W.roessler_ensemble(B)
 ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=system["n"], control_pars=system["control_pars"], verbose=False)
-ODE.set_integrator(name, rtol=1e-6, atol=1e-12)
+import os
+ODE.set_integrator(name, rtol=1e-6, atol=1e-12, kregs=(int(os.environ["KREGS"]) if "KREGS" in os.environ else None))
 ODE.set_parameters(torch.as_tensor(pars).cuda())
 for rep in range(2):
 	ODE.set_initial_value(torch.as_tensor(Y0).cuda(), 0.0)
