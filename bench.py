@@ -197,7 +197,7 @@ def run_ours(args):
 	system = wl["system"]
 	n = system["n"]
 	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=n, control_pars=system["control_pars"], verbose=False)
-	ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=ATOL, storage=args.storage)
+	ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=ATOL, storage=args.storage, kregs=args.kregs)
 	integrator = ODE.integrator
 	module = integrator.module
 
@@ -272,21 +272,30 @@ def run_ours(args):
 			peak, peak_source = json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (burst copy)"
 		else:
 			peak, peak_source = 6650.0, "fallback of B200_PROFILING.md"
-		own_attempts = sum(integrator.step_counts()) / max(1, args.steps) if world == 1 else attempts / world / args.steps
-		own_attempts = (attempts / world) / args.steps
+		own_attempts = (attempts / world) / args.steps      # per launch
 		bytes_per_launch = 280.0 * n * own_attempts           # 35·n·8 B per trajectory-step
 		kernel_s = statistics.mean(kernel_ms) * 1e-3
 		achieved = bytes_per_launch / kernel_s / 1e9
+		storage_name = {0: "registers", 1: "global", 2: "warp"}.get(module.info.storage)
 		traffic_file = ROOT / "profiles" / "traffic.json"
 		traffic = None
 		if traffic_file.exists():
-			traffic = json.loads(traffic_file.read_text()).get(f"{args.workload}:{module.info.storage}")
+			# dram__bytes_read.sum + dram__bytes_write.sum per trajectory-step from the committed ncu --set full capture
+			per_step = json.loads(traffic_file.read_text()).get(f"{args.workload}:{storage_name}")
+			traffic = None if per_step is None else per_step * own_attempts
+		# the state never leaves the chip between samples in register / warp storage: FP64 is the second yardstick
+		import sympy
+		from jitcode_b200 import _peaks
+		rhs_flops = float(sum(sympy.count_ops(entry) for entry in ODE._f_list))
+		flops_per_step = 72.0 * n + 6.0 * rhs_flops
+		fp64_peak = _peaks.fp64_fma_tflops(device)
+		fp64_achieved = flops_per_step * own_attempts / kernel_s / 1e12
 		line = {
 			"metric": METRIC, "value": attempts / seconds, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
 			"ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 			"dtype": "f64", "data": "synthetic",
 			"config": {"workload": wl["label"], "integrator": wl["integrator"], "rtol": RTOL, "atol": ATOL, "t_end": wl["T"],
-					"trajectories_per_gpu": B, "n": n, "storage": {0: "registers", 1: "global", 2: "warp"}.get(module.info.storage),
+					"trajectories_per_gpu": B, "n": n, "storage": storage_name, "threads_per_block": module.info.threads_per_block,
 					"parallelism": f"trajectory shards x{world}, no data-path collective",
 					"l2": f"state per GPU {B*n*8/1e6:.0f} MB vs 126 MB L2 (no flush needed)" if B*n*8 > 2.5e8 else "ensemble re-packed from a fresh copy every step",
 					"accepted_fraction": accepted / max(1.0, attempts)},
@@ -297,7 +306,9 @@ def run_ours(args):
 			"clocks": clocks.summary(),
 			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
 					"kernel": "jb_integrate_kernel", "kernel_ms": statistics.mean(kernel_ms), "peak_source": peak_source,
-					"algorithmic_bytes_per_trajectory_step": 280 * n},
+					"algorithmic_bytes_per_trajectory_step": 280 * n,
+					"fp64": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
+							"flops_per_trajectory_step": flops_per_step, "peak_source": "DFMA microbenchmark measured in this run (jitcode_b200/_peaks.py)"}},
 		}
 		if world == 1 and not args.no_cpu_baseline:
 			line["cpu_baseline"] = cpu_baseline(wl, args.cpu_sample_per_core)
@@ -315,12 +326,13 @@ def main():
 	parser.add_argument("--workload", default="roessler", choices=["roessler", "lv"])
 	parser.add_argument("--trajectories", type=int, default=1 << 20, help="per GPU")
 	parser.add_argument("--storage", default=None, choices=[None, "registers", "global", "warp"])
+	parser.add_argument("--kregs", type=int, default=None)
 	parser.add_argument("--cpu-sample-per-core", type=int, default=None)
 	parser.add_argument("--no-cpu-baseline", action="store_true")
 	args = parser.parse_args()
 	args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 	if args.cpu_sample_per_core is None:
-		args.cpu_sample_per_core = 256 if args.workload == "roessler" else 4096
+		args.cpu_sample_per_core = 2048 if args.workload == "roessler" else 16384
 	if args.impl == "reference":
 		run_reference(args)
 	else:
