@@ -705,6 +705,18 @@ class jitcode_transversal_lyap(jitcode, GroupHandler):
 		lyap = integrator._export(integrator.last_lyaps)[..., 0]
 		return state[..., self.main_indices], lyap
 
+	def integrate_many(self, times, discard=0):
+		"""All calls of `integrate` for `times` in one launch: (states (T, B, n_groups), local exponents (T, B))."""
+		integrator = self.integrator
+		integrator.lyap_discard = discard
+		states = integrator.integrate_many(times)
+		lyaps = integrator.last_lyaps[..., 0]
+		if integrator._single:
+			lyaps = lyaps[:, 0]
+		if integrator._out_kind != "cuda":
+			lyaps = lyaps.cpu() if integrator._out_kind == "torch" else lyaps.cpu().numpy()
+		return states[..., self.main_indices], lyaps
+
 	@property
 	def y_dict(self):
 		raise NotImplementedError("Dictionary output is not supported for transversal Lyapunov exponents")

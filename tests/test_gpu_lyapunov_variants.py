@@ -1,0 +1,97 @@
+"""
+jitcode_restricted_lyap and jitcode_transversal_lyap on the GPU, compared with each other like the reference's
+tests/test_transversal_lyap.py:26-144 does — with the five couplings of that test as ONE ensemble (the coupling
+strength is a per-trajectory control parameter) and all 999 `integrate` calls as one launch.
+"""
+
+import numpy as np
+import pytest
+import sympy
+from scipy.stats import sem
+
+from jitcode_b200 import jitcode_restricted_lyap, jitcode_transversal_lyap, y
+
+pytestmark = pytest.mark.gpu
+
+a, b, c = -0.025794, 0.01, 0.02
+k = sympy.Symbol("k")
+
+SCENARIOS = {
+	"grouped by variables": {
+		"f": [
+			y(0)*(a-y(0))*(y(0)-1.0) - y(3) + k*(y(1)-y(0)),
+			y(1)*(a-y(1))*(y(1)-1.0) - y(4) + k*(y(2)-y(1)),
+			y(2)*(a-y(2))*(y(2)-1.0) - y(5) + k*(y(0)-y(2)),
+			b*y(0) - c*y(3),
+			b*y(1) - c*y(4),
+			b*y(2) - c*y(5),
+		],
+		"vectors": [[1., 1., 1., 0., 0., 0.], [0., 0., 0., 1., 1., 1.]],
+		"groups": ([0, 1, 2], [3, 4, 5]),
+	},
+	"grouped by oscillators": {
+		"f": [
+			y(0)*(a-y(0))*(y(0)-1.0) - y(1) + k*(y(2)-y(0)),
+			b*y(0) - c*y(1),
+			y(2)*(a-y(2))*(y(2)-1.0) - y(3) + k*(y(4)-y(2)),
+			b*y(2) - c*y(3),
+			y(4)*(a-y(4))*(y(4)-1.0) - y(5) + k*(y(0)-y(4)),
+			b*y(4) - c*y(5),
+		],
+		"vectors": [[1., 0., 1., 0., 1., 0.], [0., 1., 0., 1., 0., 1.]],
+		"groups": ([0, 2, 4], [1, 3, 5]),
+	},
+}
+COUPLINGS = [(-0.1, 1), (-0.2, 1), (0.1, -1), (0.2, -1), (0.0, 0)]
+
+
+@pytest.mark.parametrize("average_dynamics", [False, True])
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_restricted_and_transversal_agree(name, average_dynamics):
+	scenario = SCENARIOS[name]
+	n = len(scenario["f"])
+	rng = np.random.default_rng(42)
+	ks = np.array([coupling for coupling, _ in COUPLINGS])
+
+	ODE1 = jitcode_restricted_lyap(scenario["f"], vectors=scenario["vectors"], verbose=False, control_pars=[k], seed=1)
+	ODE1.set_integrator("dopri5")
+	ODE2 = jitcode_transversal_lyap(scenario["f"], groups=scenario["groups"], average_dynamics=average_dynamics,
+			verbose=False, control_pars=[k], seed=2)
+	ODE2.set_integrator("dopri5")
+	ODE1.set_parameters(ks)
+	ODE2.set_parameters(ks)
+
+	initial = np.empty((len(COUPLINGS), n))
+	for row, (_, sign) in enumerate(COUPLINGS):
+		if sign < 0:
+			initial[row] = rng.random(n)
+		else:       # start on the synchronisation manifold
+			single = rng.random(2)
+			for j, group in enumerate(scenario["groups"]):
+				initial[row, list(group)] = single[j]
+	ODE1.set_initial_value(initial, 0.0)
+	ODE2.set_initial_value(rng.random((len(COUPLINGS), 2)), 0.0)
+
+	times = np.arange(100, 100000, 100)
+	states1, lyaps1 = ODE1.integrate_many(times)
+	states2, lyaps2 = ODE2.integrate_many(times)
+	assert lyaps1.shape == (len(times), len(COUPLINGS), 1) and lyaps2.shape == (len(times), len(COUPLINGS))
+	assert states2.shape == (len(times), len(COUPLINGS), 2)
+
+	checked = 0
+	for row, (coupling, sign) in enumerate(COUPLINGS):
+		final = states1[-1, row]
+		on_manifold = all(final[i] == final[j] for group in scenario["groups"] for i in group for j in group)
+		if not on_manifold:
+			# the reference's test has the same escape hatch (:124-134): it only works where the compiled arithmetic
+			# happens to be exactly symmetric between the synchronised units
+			continue
+		L1, L2 = lyaps1[500:, row, 0], lyaps2[500:, row]
+		mean1, mean2 = L1.mean(), L2.mean()
+		margin1, margin2 = sem(L1), sem(L2)
+		sign1 = np.sign(mean1) if abs(mean1) > margin1 else 0
+		sign2 = np.sign(mean2) if abs(mean2) > margin2 else 0
+		assert sign1 == sign and sign2 == sign, (coupling, mean1, margin1, mean2, margin2)
+		assert abs(mean1 - mean2) < max(margin1, margin2, 1e-4), (coupling, mean1, margin1, mean2, margin2)
+		checked += 1
+	assert checked >= 2, "the dynamics left the synchronisation manifold for almost every coupling"
