@@ -145,6 +145,49 @@ int jb_unpack(const double *soa, double *rows, int64_t B, int64_t n, int64_t ld,
 /* how many kernels this module has launched since it was loaded (bench.py's gpu_launches) */
 int64_t jb_launch_count(void);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense sine-coupled phase oscillators (csrc/jb_dense.cu; one library, not generated per system):
+ *     dy_i/dt = omega_i + sum_j W_ij sin(y_j - y_i)
+ * — what the reference writes out as n*deg sine terms (examples/kuramoto_network.py:19-26) — as one FP64
+ * tensor-core GEMM per right-hand-side evaluation for the whole ensemble.  Replaces, for such systems, the same
+ * reference entry points as jb_eval_f / jb_integrate with driver JB_DRV_ODE ("dopri5", ODE_wrapper.integrate,
+ * integrator_tools.py:134-144).  Layout: plain structure of arrays, X[i*ld + b], ld a multiple of 64.
+ */
+typedef struct jb_dense_args {
+	uint32_t struct_size;      /* sizeof(jb_dense_args), checked */
+	int32_t  n;                /* oscillators */
+	int64_t  B, ld;            /* trajectories, padded (multiple of 64) */
+	const double *W;           /* [n][n] row-major coupling matrix (device) */
+	const double *omega;       /* [n] natural frequencies (device) */
+	double   T;                /* target time */
+	double   rtol, atol, max_step, first_step;
+	int64_t  nsteps;           /* step-attempt limit per call; 0 = Hairer's default */
+	double   safety, ifactor, dfactor, beta;   /* 0 = scipy.integrate.ode's defaults */
+	double  *t;                /* [ld] in/out */
+	double  *Y;                /* [n][ld] in/out */
+	double  *work;             /* [jb_dense_work_vectors()][n][ld] */
+	double  *ctrl;             /* [jb_dense_control_scalars()][ld] */
+	int32_t *status;           /* [ld] enum jb_status, sticky */
+	int64_t *n_accepted, *n_rejected;   /* [ld] += */
+	int32_t *scratch;          /* [ld/32 + 2] device scratch */
+	int32_t *host_flag;        /* one int32 in (pinned) host memory: the host polls the number of unfinished trajectories */
+	int32_t  rounds_per_check; /* lock-step rounds between two polls; 0 = default */
+	int32_t  reserved;
+	int64_t *rounds_out;       /* host: number of lock-step rounds of this call, or NULL */
+	void    *stream;
+} jb_dense_args;
+
+int         jb_dense_work_vectors(void);
+int         jb_dense_control_scalars(void);
+const char *jb_dense_last_error(void);
+int64_t     jb_dense_launch_count(void);
+int jb_dense_integrate(const jb_dense_args *args);
+int jb_dense_eval_f(const jb_dense_args *args, double *dY);
+/* C[M][N] = A[M][K] * B[K][N], row-major FP64 on the FP64 tensor cores (exported for tests) */
+int jb_dense_gemm(const double *A, const double *B, double *C, int M, int N, int K, void *stream);
+/* out[c*ld_out + r] = in[r*ld_in + c]: (B, n) rows <-> [n][ld] */
+int jb_dense_transpose(const double *in, double *out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,304 @@
+"""
+Dense sine-coupled phase oscillators — BASELINE config 5 (reference examples/kuramoto_network.py:7-37).
+
+    dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i)
+
+The reference writes the coupling out term by term (n·deg sines of generated C); for a dense network that
+is the one place where the right-hand side really is a matrix product (csrc/jb_dense.cu):
+sin(y_j − y_i) = sin y_j cos y_i − cos y_j sin y_i turns it into W·[sin Y | cos Y] for the whole ensemble,
+computed on the FP64 tensor cores.
+
+  * `detect_sine_coupling` recognises the structure in the symbolic input (so that the reference's API keeps
+    working unchanged: `jitcode(kuramoto_f, n=n)` + `set_integrator("dopri5")`);
+  * `CudaDenseSineIntegrator` is the integrator object (protocol of integrator_tools.py, like
+    `_integrator.CudaEnsembleIntegrator`) on top of the C ABI `jb_dense_*` of include/jitcode_b200.h.
+"""
+
+import ctypes
+
+import numpy as np
+import sympy
+import torch
+
+from . import _build
+from ._integrator import STATUS_TEXT, UnsuccessfulIntegration, require_cuda
+from ._symbolic import is_dynvar
+
+
+def detect_sine_coupling(f):
+	"""(W, omega) if every equation is  constant + Σ_j number · sin(±(y(j) − y(i))),  else None."""
+	n = len(f)
+	W = np.zeros((n, n))
+	omega = np.zeros(n)
+	found = False
+	for i, expr in enumerate(f):
+		for term in sympy.Add.make_args(expr):
+			coefficient, rest = term.as_coeff_Mul()
+			if not coefficient.is_Number:
+				return None
+			if rest is sympy.S.One:
+				omega[i] += float(coefficient)
+				continue
+			if rest.func is not sympy.sin:
+				return None
+			parts = sympy.Add.make_args(rest.args[0])
+			if len(parts) != 2:
+				return None
+			(c1, v1), (c2, v2) = parts[0].as_coeff_Mul(), parts[1].as_coeff_Mul()
+			if not (is_dynvar(v1) and is_dynvar(v2)) or {c1, c2} != {sympy.S.One, sympy.S.NegativeOne}:
+				return None
+			plus, minus = (v1, v2) if c1 == 1 else (v2, v1)
+			a, b = int(plus.args[0]), int(minus.args[0])
+			if b == i:        # sin(y_a − y_i)
+				W[i, a] += float(coefficient)
+			elif a == i:      # sin(y_i − y_b) = −sin(y_b − y_i)
+				W[i, b] -= float(coefficient)
+			else:
+				return None
+			found = True
+	return (W, omega) if found else None
+
+
+class DenseArgs(ctypes.Structure):
+	_fields_ = [
+		("struct_size", ctypes.c_uint32), ("n", ctypes.c_int32),
+		("B", ctypes.c_int64), ("ld", ctypes.c_int64),
+		("W", ctypes.c_void_p), ("omega", ctypes.c_void_p),
+		("T", ctypes.c_double),
+		("rtol", ctypes.c_double), ("atol", ctypes.c_double), ("max_step", ctypes.c_double), ("first_step", ctypes.c_double),
+		("nsteps", ctypes.c_int64),
+		("safety", ctypes.c_double), ("ifactor", ctypes.c_double), ("dfactor", ctypes.c_double), ("beta", ctypes.c_double),
+		("t", ctypes.c_void_p), ("Y", ctypes.c_void_p), ("work", ctypes.c_void_p), ("ctrl", ctypes.c_void_p),
+		("status", ctypes.c_void_p), ("n_accepted", ctypes.c_void_p), ("n_rejected", ctypes.c_void_p),
+		("scratch", ctypes.c_void_p), ("host_flag", ctypes.c_void_p),
+		("rounds_per_check", ctypes.c_int32), ("reserved", ctypes.c_int32),
+		("rounds_out", ctypes.c_void_p),
+		("stream", ctypes.c_void_p),
+	]
+
+DENSE_EXPORTS = ("jb_dense_work_vectors", "jb_dense_control_scalars", "jb_dense_last_error", "jb_dense_launch_count",
+		"jb_dense_integrate", "jb_dense_eval_f", "jb_dense_gemm", "jb_dense_transpose")
+
+_library = None
+
+def dense_library():
+	"""compiles (once, cached like every module) and loads csrc/jb_dense.cu."""
+	global _library
+	if _library is None:
+		path = _build.compile_module((_build.CSRC_DIR / "jb_dense.cu").read_text())
+		lib = ctypes.CDLL(str(path))
+		for name in DENSE_EXPORTS:
+			if not hasattr(lib, name):
+				raise _build.CudaModuleError(f"{path} does not export {name}")
+		lib.jb_dense_last_error.restype = ctypes.c_char_p
+		lib.jb_dense_launch_count.restype = ctypes.c_int64
+		lib.jb_dense_integrate.argtypes = [ctypes.POINTER(DenseArgs)]
+		lib.jb_dense_eval_f.argtypes = [ctypes.POINTER(DenseArgs), ctypes.c_void_p]
+		lib.jb_dense_gemm.argtypes = [ctypes.c_void_p]*3 + [ctypes.c_int]*3 + [ctypes.c_void_p]
+		lib.jb_dense_transpose.argtypes = [ctypes.c_void_p]*2 + [ctypes.c_int64]*4 + [ctypes.c_void_p]
+		lib.path = str(path)
+		_library = lib
+	return _library
+
+
+def _check(lib, code, what):
+	if code != 0:
+		raise _build.CudaModuleError(f"{what} failed with code {code}: {lib.jb_dense_last_error().decode(errors='replace')}")
+
+
+class DenseInfo:
+	"""what CudaEnsembleIntegrator users read from module.info"""
+	def __init__(self, n):
+		self.n, self.n_params, self.n_basic, self.n_lyap, self.storage = n, 0, n, 0, 3
+		self.threads_per_block, self.shared_bytes = 256, 0
+
+
+class DenseModule:
+	"""stands where a generated module stands (launch counter, info), for bench.py and tests"""
+	def __init__(self, n):
+		self.lib = dense_library()
+		self.path = self.lib.path
+		self.info = DenseInfo(n)
+
+	def launch_count(self):
+		return int(self.lib.jb_dense_launch_count())
+
+
+class CudaDenseSineIntegrator:
+	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5")."""
+
+	def __init__(self, W, omega, *, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
+			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, rounds_per_check=4):
+		self.device = require_cuda(device)
+		self.n = len(omega)
+		self.module = DenseModule(self.n)
+		self.lib = self.module.lib
+		self.W = torch.as_tensor(np.ascontiguousarray(W, dtype=float)).to(self.device)
+		self.omega = torch.as_tensor(np.ascontiguousarray(omega, dtype=float)).to(self.device)
+		if np.ndim(atol) != 0:
+			raise NotImplementedError("The dense engine takes a scalar atol.")
+		self.rtol, self.atol = float(rtol), float(atol)
+		self.max_step = float(max_step) if max_step and np.isfinite(max_step) else 0.0
+		self.first_step = float(first_step) if first_step else 0.0
+		self.nsteps = int(nsteps)
+		self.controller = (float(safety), float(ifactor), float(dfactor), float(beta))
+		self.rounds_per_check = int(rounds_per_check)
+		self.B = None
+		self.time = None
+		self._rows = None
+		self._out_kind, self._single = "numpy", False
+		self.kernel_events = None
+		self.rounds = 0
+		self.n_params = 0
+
+	@property
+	def stream(self):
+		return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+	def _alloc(self, B):
+		self.B, self.ld = B, (B + 63) // 64 * 64
+		n, ld, dev = self.n, self.ld, self.device
+		f64 = {"dtype": torch.float64, "device": dev}
+		self.Y = torch.zeros(n * ld, **f64)
+		self.tt = torch.zeros(ld, **f64)
+		self.work = torch.zeros(self.lib.jb_dense_work_vectors() * n * ld, **f64)
+		self.ctrl = torch.zeros(self.lib.jb_dense_control_scalars() * ld, **f64)
+		self.status = torch.zeros(ld, dtype=torch.int32, device=dev)
+		self.n_accepted = torch.zeros(ld, dtype=torch.int64, device=dev)
+		self.n_rejected = torch.zeros(ld, dtype=torch.int64, device=dev)
+		self.scratch = torch.zeros(ld // 32 + 2, dtype=torch.int32, device=dev)
+		self.host_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+		self.rounds_host = np.zeros(1, dtype=np.int64)
+
+	def _args(self, T):
+		a = DenseArgs()
+		a.struct_size = ctypes.sizeof(DenseArgs)
+		a.n, a.B, a.ld = self.n, self.B, self.ld
+		a.W, a.omega = self.W.data_ptr(), self.omega.data_ptr()
+		a.T = T
+		a.rtol, a.atol, a.max_step, a.first_step = self.rtol, self.atol, self.max_step, self.first_step
+		a.nsteps = self.nsteps
+		a.safety, a.ifactor, a.dfactor, a.beta = self.controller
+		a.t, a.Y, a.work, a.ctrl = self.tt.data_ptr(), self.Y.data_ptr(), self.work.data_ptr(), self.ctrl.data_ptr()
+		a.status, a.n_accepted, a.n_rejected = self.status.data_ptr(), self.n_accepted.data_ptr(), self.n_rejected.data_ptr()
+		a.scratch, a.host_flag = self.scratch.data_ptr(), self.host_flag.data_ptr()
+		a.rounds_per_check = self.rounds_per_check
+		a.rounds_out = self.rounds_host.ctypes.data
+		a.stream = self.stream
+		return a
+
+	def _to_device_rows(self, array):
+		kind = "numpy"
+		if isinstance(array, torch.Tensor):
+			kind = "cuda" if array.is_cuda else "torch"
+			rows = array.to(device=self.device, dtype=torch.float64, non_blocking=True)
+		else:
+			rows = torch.as_tensor(np.ascontiguousarray(array, dtype=float)).to(self.device, non_blocking=True)
+		single = rows.dim() == 1
+		if single:
+			rows = rows.reshape(1, -1)
+		if rows.dim() != 2 or rows.shape[1] != self.n:
+			raise ValueError("The dimension of the initial value does not match the dimension of your differential equations.")
+		return rows.contiguous(), kind, single
+
+	def _export(self, rows, out=None):
+		if self._single:
+			rows = rows[0]
+		if out is not None:
+			out.copy_(rows, non_blocking=True)
+			torch.cuda.current_stream(self.device).synchronize()
+			return out
+		if self._out_kind == "cuda":
+			return rows
+		host = rows.cpu()
+		return host if self._out_kind == "torch" else host.numpy()
+
+	def _rows_from(self, soa):
+		rows = torch.empty((self.B, self.n), dtype=torch.float64, device=self.device)
+		_check(self.lib, self.lib.jb_dense_transpose(soa.data_ptr(), rows.data_ptr(), self.n, self.B, self.ld, self.n, self.stream), "jb_dense_transpose")
+		return rows
+
+	# ---- protocol of integrator_tools
+
+	def set_parameters(self, pars):
+		pass
+
+	def set_initial_value(self, initial_value, time=0.0):
+		rows, kind, single = self._to_device_rows(initial_value)
+		if self.B != rows.shape[0]:
+			self._alloc(rows.shape[0])
+		self._out_kind, self._single = kind, single
+		_check(self.lib, self.lib.jb_dense_transpose(rows.data_ptr(), self.Y.data_ptr(), self.B, self.n, self.n, self.ld, self.stream), "jb_dense_transpose")
+		self.tt.fill_(float(time))
+		self.time = float(time)
+		self.status.zero_()
+		self._rows = rows
+
+	@property
+	def t(self):
+		if self.time is None:
+			raise RuntimeError("You must call set_initial_value first.")
+		return self.time
+
+	@property
+	def _y(self):
+		if self._rows is None:
+			raise RuntimeError("You must call set_initial_value first.")
+		return self._export(self._rows)
+
+	@property
+	def y_device(self):
+		return self._rows
+
+	def successful(self):
+		return not bool((self.status[:self.B] != 0).any().item())
+
+	def integrate(self, T, out=None):
+		T = float(T)
+		if self.B is None:
+			raise RuntimeError("You must call set_initial_value first.")
+		if T < self.time:
+			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
+		if T == self.time:
+			return self._export(self._rows, out)
+		args = self._args(T)
+		if self.kernel_events is not None:
+			start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			start.record()
+		_check(self.lib, self.lib.jb_dense_integrate(ctypes.byref(args)), "jb_dense_integrate")
+		if self.kernel_events is not None:
+			end.record()
+			self.kernel_events.append((start, end))
+		self.rounds += int(self.rounds_host[0])
+		self.time = T
+		self._rows = self._rows_from(self.Y)
+		failed = (self.status[:self.B] != 0).nonzero().flatten()
+		if failed.numel():
+			indices = failed.cpu().numpy()
+			status = self.status[:self.B][failed].cpu().numpy()
+			raise UnsuccessfulIntegration(
+				f"{len(indices)} of {self.B} trajectories failed (first: #{indices[0]}, {STATUS_TEXT.get(int(status[0]), status[0])}).", indices, status)
+		return self._export(self._rows, out)
+
+	def integrate_many(self, times):
+		return np.stack([np.asarray(torch.as_tensor(self.integrate(T)).cpu()) for T in times])
+
+	def eval_f(self, state):
+		rows, kind, single = self._to_device_rows(state)
+		if self.B != rows.shape[0]:
+			self._alloc(rows.shape[0])
+		self._out_kind, self._single = kind, single
+		_check(self.lib, self.lib.jb_dense_transpose(rows.data_ptr(), self.Y.data_ptr(), self.B, self.n, self.n, self.ld, self.stream), "jb_dense_transpose")
+		self.status.zero_()
+		out = torch.empty_like(self.Y)
+		args = self._args(0.0)
+		_check(self.lib, self.lib.jb_dense_eval_f(ctypes.byref(args), out.data_ptr()), "jb_dense_eval_f")
+		return self._export(self._rows_from(out))
+
+	def step_counts(self):
+		return int(self.n_accepted[:self.B].sum().item()), int(self.n_rejected[:self.B].sum().item())
+
+	def reset_step_counts(self):
+		self.n_accepted.zero_()
+		self.n_rejected.zero_()
+		self.rounds = 0

@@ -25,7 +25,7 @@ import numpy as np
 import sympy
 import torch
 
-from . import _build, _codegen, _vectorise
+from . import _build, _codegen, _dense, _vectorise
 from ._integrator import (
 	JB_POST_LYAP_QR, JB_POST_LYAP_RESTRICTED, JB_POST_LYAP_TRANSVERSAL, JB_POST_NONE,
 	CudaEnsembleIntegrator, UnsuccessfulIntegration, empty_integrator, require_cuda,
@@ -46,7 +46,8 @@ _used_module_names = set()
 
 
 SHARED_MEMORY_PER_BLOCK = 227 * 1024      # sm_100a: opt-in maximum of dynamic shared memory per block
-STORAGE_BY_NAME = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL, "warp": _codegen.JB_STORE_WARP}
+STORAGE_BY_NAME = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL, "warp": _codegen.JB_STORE_WARP, "dense": "dense"}
+DENSE_MINIMUM_N = 128       # below this the generic kernels (registers / warp storage) are the better fit
 
 
 def _stage_rows(method, driver):
@@ -132,6 +133,32 @@ class jitcode:
 		self._n_basic_module = self.n
 		self._n_lyap_module = 0
 		self._tangent_indices_module = []
+
+	@classmethod
+	def from_sine_coupling(cls, W, omega, verbose=False):
+		"""
+		The system  dy_i/dt = omega[i] + Σ_j W[i, j]·sin(y_j − y_i)  given by its data instead of by n·deg symbolic
+		sine terms (which SymPy needs minutes to build for a dense network of 1000 oscillators).  Equivalent to
+		`jitcode(f_sym)` with that f_sym — the symbolic input is recognised and ends up in the same kernels — and
+		only available with `set_integrator("dopri5")`.
+		"""
+		W, omega = np.asarray(W, dtype=float), np.asarray(omega, dtype=float)
+		if W.shape != (len(omega), len(omega)):
+			raise ValueError("W must be (n, n) for omega of length n.")
+		self = cls.__new__(cls)
+		jitcode.__init__(self, [y(0)], n=1, verbose=verbose)        # placeholder system; replaced by the coupling data
+		self._f_list, self.n = [], len(omega)
+		self._n_basic_module = self.n
+		self._sine_coupling = (W, omega)
+		return self
+
+	def _dense_coupling(self):
+		"""(W, omega) if the system is a network of sine-coupled phase oscillators, else None (cached)."""
+		if not hasattr(self, "_sine_coupling"):
+			self._sine_coupling = None
+			if self._f_list and not self.helpers and not self.control_pars and self._post == JB_POST_NONE:
+				self._sine_coupling = _dense.detect_sine_coupling(self._f_list)
+		return self._sine_coupling
 
 	# ------------------------------------------------------------------ input handling and checks
 
@@ -330,6 +357,9 @@ class jitcode:
 
 	def f(self, time, state):
 		"""Evaluates the compiled derivative on the GPU: state (n,) → (n,), or (B, n) → (B, n)."""
+		if isinstance(self.integrator, _dense.CudaDenseSineIntegrator) or not self._f_list:
+			helper = _dense.CudaDenseSineIntegrator(*self._dense_coupling())
+			return helper.eval_f(state)
 		module = self._f_module or (next(iter(self._modules.values())) if self._modules else self._module(_codegen.JB_DP5, _codegen.JB_DRV_ODE))
 		self._f_module = module
 		helper = CudaEnsembleIntegrator(module, device=getattr(self.integrator, "device", None))
@@ -432,7 +462,7 @@ class jitcode:
 		if count != len(self.control_pars):
 			raise ValueError("Number of values does not match number of control parameters.")
 		self.control_par_values = values
-		if isinstance(self.integrator, CudaEnsembleIntegrator):
+		if isinstance(self.integrator, CudaEnsembleIntegrator) and count:
 			self.integrator.set_parameters(self._parameter_rows())
 
 	def set_f_params(self, *args):
@@ -472,6 +502,17 @@ class jitcode:
 		if isinstance(storage, str):
 			storage = STORAGE_BY_NAME[storage]
 		old_integrator = self.integrator
+		dense = storage == "dense" or (storage is None and name == "dopri5" and self.n >= DENSE_MINIMUM_N and self._dense_coupling() is not None)
+		if dense:
+			if name != "dopri5" or self._dense_coupling() is None:
+				raise NotImplementedError("The dense engine integrates sine-coupled phase oscillators with \"dopri5\" only.")
+			_dense.dense_library()                                       # compiling needs no GPU …
+			require_cuda(device)                                         # … running does
+			integrator_params.pop("verbosity", None)
+			self._integrator_config = None
+			self.integrator = _dense.CudaDenseSineIntegrator(*self._dense_coupling(), device=device, nsteps=nsteps, **integrator_params)
+			self._restore_state(old_integrator)
+			return
 		module = self._module(method, driver, storage, threads, kregs)   # compiling needs no GPU …
 		require_cuda(device)                                      # … running does
 		self._integrator_config = (method, driver, storage, threads, kregs)
@@ -483,24 +524,27 @@ class jitcode:
 		)
 		if self.control_pars and self.control_par_values is not None:
 			self.integrator.set_parameters(self._parameter_rows())
-		# restore state and time, if applicable (_jitcode.py:619-626)
+		self._restore_state(old_integrator)
+
+	def _restore_state(self, old_integrator):
+		"""restore state and time from the previous integrator object, if applicable (_jitcode.py:619-626)"""
+		on_device = hasattr(old_integrator, "y_device")
 		try:
-			old_y = old_integrator.y_device if isinstance(old_integrator, CudaEnsembleIntegrator) else old_integrator._y
+			old_y = old_integrator.y_device if on_device else old_integrator._y
 			old_t = old_integrator.t
 		except (AttributeError, RuntimeError):
-			pass
-		else:
-			if old_y is not None and len(old_y):
-				self.integrator.set_initial_value(old_y, old_t)
-				if isinstance(old_integrator, CudaEnsembleIntegrator):
-					self.integrator._out_kind, self.integrator._single = old_integrator._out_kind, old_integrator._single
+			return
+		if old_y is not None and len(old_y):
+			self.integrator.set_initial_value(old_y, old_t)
+			if on_device:
+				self.integrator._out_kind, self.integrator._single = old_integrator._out_kind, old_integrator._single
 
 	def integrate(self, *args, **kwargs):
 		return self.integrator.integrate(*args, **kwargs)
 
 	def integrate_many(self, times):
 		"""`[integrate(T) for T in times]` in one kernel launch: (len(times), B, n)."""
-		if not isinstance(self.integrator, CudaEnsembleIntegrator):
+		if not hasattr(self.integrator, "integrate_many"):
 			raise RuntimeError("You must call set_integrator first.")
 		return self.integrator.integrate_many(times)
 

@@ -1,0 +1,619 @@
+// Dense sine-coupled phase oscillators (Kuramoto-type networks) — the one coupling that really is a
+// dense contraction (BASELINE config 5, reference examples/kuramoto_network.py:19-26):
+//
+//     dy_i/dt = ω_i + Σ_j W_ij · sin(y_j − y_i)                       n oscillators, W dense (n × n)
+//
+// The reference writes this out as n·deg sine terms of straight-line C (10⁵–10⁶ for n = 1000).  Here
+//     sin(y_j − y_i) = sin y_j · cos y_i − cos y_j · sin y_i
+// turns the coupling of a whole ensemble into ONE FP64 GEMM per right-hand-side evaluation,
+//     [G_s | G_c] = W · [sin Z | cos Z]        (n × n) · (n × 2B),        f = ω + cos Z ∘ G_s − sin Z ∘ G_c
+// with 2n sincos per trajectory instead of n·deg sines.  The GEMM runs on the FP64 tensor cores
+// (mma.sync.m8n8k4.f64 → SASS DMMA.8x8x4; tcgen05 has no f64 kind), the rest is element-wise.
+//
+// Because the contraction couples nothing across trajectories, every trajectory keeps its own step size:
+// the ensemble advances in lock-step ROUNDS — in each round every unfinished trajectory makes one step
+// attempt (accepted or rejected by its own error estimate), the six stages of all of them share the six
+// GEMMs.  State is structure-of-arrays, trajectory-minor: X[i][b] at X[i*ld + b].
+//
+// Controller: Hairer's DOPRI5 exactly as in jb_rk.cuh (driver JB_DRV_ODE): HINIT, PI control
+// with β = 0.04, `1.01·h` landing rule, fresh start per integrate call.  The host loop of rounds lives in
+// jb_dense_integrate (C++, no Python per launch).
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include "jb_tableaux.cuh"
+#include "jitcode_b200.h"
+
+namespace jbd {
+
+using jb::DP5;
+using jb::Idx;
+using jb::static_for;
+
+// ---------------------------------------------------------------------------------------------
+// C[M][N] = A[M][K] · B[K][N], all row-major FP64, on the FP64 tensor cores.
+// Block tile 128 × 64, K chunk 16, 8 warps as 4 (M) × 2 (N), each warp 32 × 32 = 4 × 4 DMMA tiles.
+// Column tiles whose flag in `skip` is non-zero are not computed (all their trajectories have finished).
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int LDA = BK + 4;     // shared-memory row lengths chosen so that a half-warp's fragment reads
+constexpr int LDB = BN + 4;     // (4 rows × 4 consecutive doubles) hit 32 distinct banks
+constexpr size_t GEMM_SHARED_BYTES = sizeof(double) * 2 * (BM * LDA + BK * LDB);     // double-buffered tiles
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+			: "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
+		int M, int N, int K, const int *__restrict__ tile_skip, int64_t ld)
+{
+	if (tile_skip) {
+		// columns n0 … n0+63 are trajectories (n0 mod ld) … of the sin or of the cos half; skip_flags are per 32 trajectories
+		const int64_t first = (((int64_t) blockIdx.x * BN) % ld) / 32;
+		if (tile_skip[first] && tile_skip[first + 1]) return;
+	}
+	extern __shared__ __align__(16) double gemm_shared[];
+	double (*sA)[BM * LDA] = reinterpret_cast<double (*)[BM * LDA]>(gemm_shared);
+	double (*sB)[BK * LDB] = reinterpret_cast<double (*)[BK * LDB]>(gemm_shared + 2 * BM * LDA);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int wm = warp >> 1, wn = warp & 1;                 // warp position in the block tile
+	const int64_t m0 = (int64_t) blockIdx.y * BM, n0 = (int64_t) blockIdx.x * BN;
+
+	double acc[4][4][2];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+#pragma unroll
+		for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+	auto load_tiles = [&](int buffer, int k0) {
+		// A tile: 128 rows × 16 doubles; thread loads 8 doubles (row = tid/2, half = tid%2)
+		{
+			const int row = tid >> 1, half = tid & 1;
+			const int64_t gm = m0 + row;
+#pragma unroll
+			for (int e = 0; e < 8; ++e) {
+				const int kk = half * 8 + e;
+				const int gk = k0 + kk;
+				sA[buffer][row * LDA + kk] = (gm < M && gk < K) ? A[gm * K + gk] : 0.0;
+			}
+		}
+		// B tile: 16 rows × 64 doubles; thread loads 4 doubles (row = tid/16, cols 4*(tid%16)…)
+		{
+			const int row = tid >> 4, col = (tid & 15) * 4;
+			const int gk = k0 + row;
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				const int64_t gn = n0 + col + e;
+				sB[buffer][row * LDB + col + e] = (gk < K && gn < N) ? B[(int64_t) gk * N + gn] : 0.0;
+			}
+		}
+	};
+
+	const int chunks = (K + BK - 1) / BK;
+	load_tiles(0, 0);
+	__syncthreads();
+	for (int chunk = 0; chunk < chunks; ++chunk) {
+		const int buffer = chunk & 1;
+		if (chunk + 1 < chunks) load_tiles(buffer ^ 1, (chunk + 1) * BK);
+		const double *a = sA[buffer] + (wm * 32 + (lane >> 2)) * LDA + (lane & 3);
+		const double *b = sB[buffer] + (lane & 3) * LDB + wn * 32 + (lane >> 2);
+#pragma unroll
+		for (int kk = 0; kk < BK; kk += 4) {
+			double fa[4], fb[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) fa[i] = a[i * 8 * LDA + kk];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) fb[j] = b[kk * LDB + j * 8];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+#pragma unroll
+				for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t gm = m0 + wm * 32 + i * 8 + (lane >> 2);
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int64_t gn = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
+			if (gm < M && gn < N) C[gm * N + gn] = acc[i][j][0];
+			if (gm < M && gn + 1 < N) C[gm * N + gn + 1] = acc[i][j][1];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-trajectory control block (structure of arrays, ctrl[k*ld + b])
+
+enum { C_H = 0, C_HMAX, C_FACOLD, C_ERR2, C_DNF, C_DNY, C_DER2, C_FLAGS, C_NSTEP, C_COUNT };
+enum { F_ACTIVE = 1, F_LAST = 2, F_REJECT = 4, F_ACCEPTED = 8 };      // C_FLAGS (stored as a double holding a small int)
+// work vectors, work[k*n*ld + i*ld + b]
+enum { W_Z = 0, W_K0 = 1 /* … W_K0+6 */, W_XS = 8 /* sin | cos: 2 vectors */, W_G = 10 /* G_s | G_c: 2 vectors */, W_COUNT = 12 };
+
+struct Dense {
+	int64_t B, ld;
+	int n;
+	const double *W, *omega;
+	double T, rtol, atol, max_step, first_step;
+	int64_t nmax;
+	double safety, facc1, facc2, beta, expo1;
+	double *t, *Y, *work, *ctrl;
+	int32_t *status;
+	int64_t *n_accepted, *n_rejected;
+	int32_t *tile_skip;     // [ld/32]: 1 if no trajectory of the 32-column tile is active
+	int32_t *active_count;  // [1]
+};
+
+__device__ __host__ __forceinline__ double *vec(const Dense &d, int k) { return d.work + (int64_t) k * d.n * d.ld; }
+// the GEMM operands are matrices with 2·ld columns: row i = [sin(i, 0 … ld) | cos(i, 0 … ld)], likewise [G_s | G_c]
+__device__ __forceinline__ double &xs_sin(const Dense &d, int i, int64_t b) { return vec(d, W_XS)[(int64_t) i * 2 * d.ld + b]; }
+__device__ __forceinline__ double &xs_cos(const Dense &d, int i, int64_t b) { return vec(d, W_XS)[(int64_t) i * 2 * d.ld + d.ld + b]; }
+__device__ __forceinline__ double g_sin(const Dense &d, int i, int64_t b) { return vec(d, W_G)[(int64_t) i * 2 * d.ld + b]; }
+__device__ __forceinline__ double g_cos(const Dense &d, int i, int64_t b) { return vec(d, W_G)[(int64_t) i * 2 * d.ld + d.ld + b]; }
+
+// element-wise kernels: blockDim = (32 trajectories, 8), each thread covers ROWS_PER_THREAD components
+constexpr int ROWS_PER_BLOCK = 64;
+
+template <class F>
+__device__ __forceinline__ void for_rows(const Dense &d, F &&body)
+{
+	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	const int i0 = blockIdx.y * ROWS_PER_BLOCK + threadIdx.y;
+	if (b >= d.B) return;
+#pragma unroll
+	for (int r = 0; r < ROWS_PER_BLOCK / 8; ++r) {
+		const int i = i0 + 8 * r;
+		if (i < d.n) body(i, b, (int64_t) i * d.ld + b);
+	}
+}
+
+__device__ __forceinline__ int flags_of(const Dense &d, int64_t b) { return (int) d.ctrl[C_FLAGS * d.ld + b]; }
+
+// adds `value` (a per-thread partial sum over this thread's rows) to slot[b]: shared-memory reduction over the
+// 8 row lanes of the block, then one atomic per (block, trajectory)
+__device__ __forceinline__ void reduce_to(double *slot, int64_t b, bool valid, double value)
+{
+	__shared__ double partial[8][32];
+	partial[threadIdx.y][threadIdx.x] = valid ? value : 0.0;
+	__syncthreads();
+	if (threadIdx.y == 0 && valid) {
+		double total = 0.0;
+#pragma unroll
+		for (int r = 0; r < 8; ++r) total += partial[r][threadIdx.x];
+		atomicAdd(slot + b, total);
+	}
+	__syncthreads();
+}
+
+// XS = [sin V | cos V] for the trajectories that take part in this evaluation
+template <int WHICH>    // 0: V = Y, 1: V = Z
+__global__ void __launch_bounds__(256) sincos_kernel(const Dense d, int need_flag)
+{
+	const double *V = WHICH == 0 ? d.Y : vec(d, W_Z);
+	for_rows(d, [&](int i, int64_t b, int64_t at) {
+		if (!(flags_of(d, b) & need_flag)) return;
+		sincos(V[at], &xs_sin(d, i, b), &xs_cos(d, i, b));
+	});
+}
+
+// K[J] = ω + cos ∘ G_s − sin ∘ G_c   (the right-hand side, given the GEMM result)
+template <int J>
+__device__ __forceinline__ double finish_rhs(const Dense &d, int i, int64_t b, int64_t at)
+{
+	const double value = d.omega[i] + xs_cos(d, i, b) * g_sin(d, i, b) - xs_sin(d, i, b) * g_cos(d, i, b);
+	vec(d, W_K0 + J)[at] = value;
+	return value;
+}
+
+// after the GEMM of f(t, Y): K[0] = f; HINIT sums dnf = Σ(f/sk)², dny = Σ(y/sk)²
+__global__ void __launch_bounds__(256) start_kernel(const Dense d)
+{
+	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	double dnf = 0.0, dny = 0.0;
+	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
+	if (active)
+		for_rows(d, [&](int i, int64_t, int64_t at) {
+			const double f0 = finish_rhs<0>(d, i, b, at);
+			const double sk = fma(d.rtol, fabs(d.Y[at]), d.atol);
+			const double qf = f0 / sk, qy = d.Y[at] / sk;
+			dnf = fma(qf, qf, dnf);
+			dny = fma(qy, qy, dny);
+		});
+	reduce_to(d.ctrl + C_DNF * d.ld, b, active, dnf);
+	reduce_to(d.ctrl + C_DNY * d.ld, b, active, dny);
+}
+
+// HINIT: first guess h0 and the Euler probe Z = Y + h0 K[0], XS = sincos(Z)
+__global__ void __launch_bounds__(256) probe_kernel(const Dense d)
+{
+	for_rows(d, [&](int i, int64_t b, int64_t at) {
+		if (!(flags_of(d, b) & F_ACTIVE)) return;
+		const double dnf = d.ctrl[C_DNF * d.ld + b], dny = d.ctrl[C_DNY * d.ld + b];
+		double h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+		h = fmin(h, d.ctrl[C_HMAX * d.ld + b]);
+		const double z = fma(h, vec(d, W_K0)[at], d.Y[at]);
+		vec(d, W_Z)[at] = z;
+		sincos(z, &xs_sin(d, i, b), &xs_cos(d, i, b));
+	});
+}
+
+// HINIT: der2 = Σ((f1 − f0)/sk)²
+__global__ void __launch_bounds__(256) probe_finish_kernel(const Dense d)
+{
+	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	double der2 = 0.0;
+	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
+	if (active)
+		for_rows(d, [&](int i, int64_t, int64_t at) {
+			const double f1 = finish_rhs<1>(d, i, b, at);
+			const double q = (f1 - vec(d, W_K0)[at]) / fma(d.rtol, fabs(d.Y[at]), d.atol);
+			der2 = fma(q, q, der2);
+		});
+	reduce_to(d.ctrl + C_DER2 * d.ld, b, active, der2);
+}
+
+// the top of Hairer's step loop for one trajectory: limits, landing rule; returns whether it attempts a step
+__device__ __forceinline__ void begin_attempt(const Dense &d, int64_t b, double t, double &h, int &flags, double &nstep)
+{
+	if (nstep > (double) d.nmax) { d.status[b] = JB_TOO_MANY_STEPS; flags &= ~F_ACTIVE; return; }
+	if (0.1 * fabs(h) <= fabs(t) * 2.3e-16) { d.status[b] = JB_STEP_TOO_SMALL; flags &= ~F_ACTIVE; return; }
+	if (!(h == h)) { d.status[b] = JB_NONFINITE; flags &= ~F_ACTIVE; return; }
+	if (t + 1.01 * h - d.T > 0.0) { h = d.T - t; flags |= F_LAST; }
+	nstep += 1.0;
+}
+
+__device__ __forceinline__ void publish_activity(const Dense &d, int64_t b, bool active)
+{
+	// one flag per 32-trajectory tile for the GEMM, one counter for the host
+	const unsigned any = __ballot_sync(0xffffffffu, active);
+	if ((threadIdx.x & 31) == 0 && b < d.ld) {
+		d.tile_skip[b / 32] = any == 0;
+		if (any) atomicAdd(d.active_count, __popc(any));
+	}
+}
+
+// one thread per trajectory: decide which trajectories integrate at all, reset their controllers
+__global__ void __launch_bounds__(256) setup_kernel(const Dense d)
+{
+	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	bool active = false;
+	if (b < d.B) {
+		active = d.status[b] == JB_OK && d.T > d.t[b];
+		d.ctrl[C_FLAGS * d.ld + b] = active ? F_ACTIVE : 0;
+		d.ctrl[C_HMAX * d.ld + b] = d.max_step > 0.0 ? d.max_step : fabs(d.T - d.t[b]);
+		d.ctrl[C_FACOLD * d.ld + b] = 1e-4;
+		d.ctrl[C_NSTEP * d.ld + b] = 0.0;
+		d.ctrl[C_DNF * d.ld + b] = d.ctrl[C_DNY * d.ld + b] = d.ctrl[C_DER2 * d.ld + b] = d.ctrl[C_ERR2 * d.ld + b] = 0.0;
+	}
+	publish_activity(d, b, active);
+}
+
+// HINIT's result (or first_step) and the first pass through the top of the step loop
+__global__ void __launch_bounds__(256) first_step_kernel(const Dense d, int have_probe)
+{
+	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	bool active = false;
+	if (b < d.B) {
+		int flags = flags_of(d, b);
+		if (flags & F_ACTIVE) {
+			const double hmax = d.ctrl[C_HMAX * d.ld + b];
+			double h;
+			if (!have_probe) {
+				h = d.first_step;
+			} else {
+				const double dnf = d.ctrl[C_DNF * d.ld + b], dny = d.ctrl[C_DNY * d.ld + b];
+				double h0 = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+				h0 = fmin(h0, hmax);
+				const double der2 = sqrt(d.ctrl[C_DER2 * d.ld + b]) / h0;
+				const double der12 = fmax(fabs(der2), sqrt(dnf));
+				const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h0) * 1e-3) : pow(0.01 / der12, 1.0 / DP5::HAIRER_ORDER);
+				h = fmin(fmin(100.0 * fabs(h0), h1), hmax);
+			}
+			double nstep = 0.0;
+			begin_attempt(d, b, d.t[b], h, flags, nstep);
+			d.ctrl[C_H * d.ld + b] = h;
+			d.ctrl[C_NSTEP * d.ld + b] = nstep;
+			d.ctrl[C_FLAGS * d.ld + b] = flags;
+			d.ctrl[C_ERR2 * d.ld + b] = 0.0;
+			active = flags & F_ACTIVE;
+		}
+	}
+	publish_activity(d, b, active);
+}
+
+// stage ROW of an attempt: (ROW > 1: K[ROW-1] = f from the last GEMM;)  Z = Y + h Σ_j a(ROW, j) K[j];  XS = sincos(Z)
+// ROW == 1 also applies the outcome of the previous round: accepted trajectories take Y ← Z, K[0] ← K[6].
+template <int ROW>
+__global__ void __launch_bounds__(256) stage_kernel(const Dense d)
+{
+	for_rows(d, [&](int i, int64_t b, int64_t at) {
+		const int flags = flags_of(d, b);
+		double k[7];
+		double y = d.Y[at];
+		if constexpr (ROW == 1) {
+			if (flags & F_ACCEPTED) {
+				y = vec(d, W_Z)[at];
+				d.Y[at] = y;
+				k[0] = vec(d, W_K0 + 6)[at];
+				vec(d, W_K0)[at] = k[0];
+			} else {
+				k[0] = vec(d, W_K0)[at];
+			}
+			if (!(flags & F_ACTIVE)) return;
+		} else {
+			if (!(flags & F_ACTIVE)) return;
+			static_for<0, ROW - 1>([&](auto j) {
+				constexpr double a = DP5::A[ROW][j];
+				if constexpr (a != 0.0) k[j] = vec(d, W_K0 + j)[at];
+			});
+			k[ROW - 1] = finish_rhs<ROW - 1>(d, i, b, at);
+		}
+		const double h = d.ctrl[C_H * d.ld + b];
+		double acc = 0.0;
+		static_for<0, ROW>([&](auto j) {
+			constexpr double a = DP5::A[ROW][j];
+			if constexpr (a != 0.0) acc = fma(a, k[j], acc);
+		});
+		const double z = fma(h, acc, y);
+		vec(d, W_Z)[at] = z;
+		sincos(z, &xs_sin(d, i, b), &xs_cos(d, i, b));
+	});
+}
+
+// after the GEMM of f(t+h, y_new): K[6] = f; error sum Σ (h Σ_j E_j K_j / sk)²
+__global__ void __launch_bounds__(256) error_kernel(const Dense d)
+{
+	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
+	double sum = 0.0;
+	if (active) {
+		const double h = d.ctrl[C_H * d.ld + b];
+		for_rows(d, [&](int i, int64_t, int64_t at) {
+			const double k6 = finish_rhs<6>(d, i, b, at);
+			double e = DP5::E[6] * k6;
+			static_for<0, 6>([&](auto j) {
+				constexpr double w = DP5::E[j];
+				if constexpr (w != 0.0) e = fma(w, vec(d, W_K0 + j)[at], e);
+			});
+			const double sk = fma(d.rtol, fmax(fabs(d.Y[at]), fabs(vec(d, W_Z)[at])), d.atol);
+			const double q = h * e / sk;
+			sum = fma(q, q, sum);
+		});
+	}
+	reduce_to(d.ctrl + C_ERR2 * d.ld, b, active, sum);
+}
+
+// one thread per trajectory: accept or reject, new step size, and the top of the next pass of the step loop
+__global__ void __launch_bounds__(256) control_kernel(const Dense d)
+{
+	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	bool active = false;
+	if (b < d.B) {
+		int flags = flags_of(d, b);
+		flags &= ~F_ACCEPTED;
+		if (flags & F_ACTIVE) {
+			double t = d.t[b], h = d.ctrl[C_H * d.ld + b], facold = d.ctrl[C_FACOLD * d.ld + b];
+			const double hmax = d.ctrl[C_HMAX * d.ld + b];
+			double nstep = d.ctrl[C_NSTEP * d.ld + b];
+			const double err = sqrt(d.ctrl[C_ERR2 * d.ld + b] / d.n);
+			const double fac11 = pow(err, d.expo1);
+			double fac = d.beta > 0.0 ? fac11 / pow(facold, d.beta) : fac11;
+			fac = fmax(d.facc2, fmin(d.facc1, fac / d.safety));
+			double hnew = h / fac;
+			if (err <= 1.0) {
+				facold = fmax(err, 1e-4);
+				d.n_accepted[b] += 1;
+				flags |= F_ACCEPTED;
+				t = (flags & F_LAST) ? d.T : t + h;
+				if (fabs(hnew) > hmax) hnew = hmax;
+				if (flags & F_REJECT) hnew = fmin(fabs(hnew), fabs(h));
+				flags &= ~F_REJECT;
+				if (flags & F_LAST) flags &= ~F_ACTIVE;
+			} else {
+				hnew = h / fmin(d.facc1, fac11 / d.safety);
+				flags |= F_REJECT;
+				flags &= ~F_LAST;
+				d.n_rejected[b] += 1;
+			}
+			h = hnew;
+			if (flags & F_ACTIVE) begin_attempt(d, b, t, h, flags, nstep);
+			d.t[b] = t;
+			d.ctrl[C_H * d.ld + b] = h;
+			d.ctrl[C_FACOLD * d.ld + b] = facold;
+			d.ctrl[C_NSTEP * d.ld + b] = nstep;
+			d.ctrl[C_ERR2 * d.ld + b] = 0.0;
+			active = flags & F_ACTIVE;
+		}
+		d.ctrl[C_FLAGS * d.ld + b] = flags;
+	}
+	publish_activity(d, b, active);
+}
+
+// the accepted trajectories of the very last round still have y_new in Z: Y ← Z
+__global__ void __launch_bounds__(256) commit_kernel(const Dense d)
+{
+	for_rows(d, [&](int, int64_t b, int64_t at) {
+		if (flags_of(d, b) & F_ACCEPTED) d.Y[at] = vec(d, W_Z)[at];
+	});
+}
+
+__global__ void clear_accepted_kernel(const Dense d)
+{
+	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (b < d.B) d.ctrl[C_FLAGS * d.ld + b] = (double) (flags_of(d, b) & ~F_ACCEPTED);
+}
+
+// (B, n) rows ↔ [n][ld] trajectory-minor
+__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ in, double *__restrict__ out,
+		int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out)
+{
+	__shared__ double tile[32][33];
+	const int64_t c0 = (int64_t) blockIdx.x * 32, r0 = (int64_t) blockIdx.y * 32;
+	for (int r = threadIdx.y; r < 32; r += 8)
+		if (r0 + r < rows && c0 + threadIdx.x < cols) tile[r][threadIdx.x] = in[(r0 + r) * ld_in + c0 + threadIdx.x];
+	__syncthreads();
+	for (int c = threadIdx.y; c < 32; c += 8)
+		if (c0 + c < cols && r0 + threadIdx.x < rows) out[(c0 + c) * ld_out + r0 + threadIdx.x] = tile[threadIdx.x][c];
+}
+
+static std::atomic<int64_t> launch_counter{0};
+static thread_local char error_text[256] = "";
+
+static int fail(int code, const char *what)
+{
+	if (code > 0) snprintf(error_text, sizeof error_text, "%s: %s", what, cudaGetErrorString((cudaError_t) code));
+	else snprintf(error_text, sizeof error_text, "%s", what);
+	return code;
+}
+
+#define JBD_LAUNCH(kernel, grid, block, ...) do { kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); jbd::launch_counter.fetch_add(1, std::memory_order_relaxed); } while (0)
+
+static void launch_gemm(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream)
+{
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SHARED_BYTES);
+		configured = true;
+	}
+	const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+	dgemm_dmma_kernel<<<grid, 256, GEMM_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
+	launch_counter.fetch_add(1, std::memory_order_relaxed);
+}
+
+static void gemm(const Dense &d, cudaStream_t stream)
+{
+	launch_gemm(d.W, vec(d, W_XS), vec(d, W_G), d.n, (int) (2 * d.ld), d.n, d.tile_skip, d.ld, stream);
+}
+
+}  // namespace jbd
+
+extern "C" {
+
+const char *jb_dense_last_error(void) { return jbd::error_text; }
+int64_t jb_dense_launch_count(void) { return jbd::launch_counter.load(std::memory_order_relaxed); }
+int jb_dense_work_vectors(void) { return jbd::W_COUNT; }
+int jb_dense_control_scalars(void) { return jbd::C_COUNT; }
+
+int jb_dense_gemm(const double *A, const double *B, double *C, int M, int N, int K, void *stream_)
+{
+	cudaStream_t stream = (cudaStream_t) stream_;
+	jbd::launch_gemm(A, B, C, M, N, K, nullptr, 0, stream);
+	const cudaError_t err = cudaGetLastError();
+	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_gemm");
+}
+
+int jb_dense_transpose(const double *in, double *out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, void *stream_)
+{
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const dim3 grid((unsigned) ((cols + 31) / 32), (unsigned) ((rows + 31) / 32));
+	JBD_LAUNCH(jbd::transpose_kernel, grid, dim3(32, 8), in, out, rows, cols, ld_in, ld_out);
+	const cudaError_t err = cudaGetLastError();
+	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_transpose");
+}
+
+// dY = f(Y) for B states (Y, dY: [n][ld]); work as for jb_dense_integrate
+int jb_dense_eval_f(const jb_dense_args *x, double *dY)
+{
+	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_eval_f: argument block has the wrong size");
+	jbd::Dense d{};
+	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega;
+	d.Y = x->Y; d.work = x->work; d.ctrl = x->ctrl; d.status = x->status;
+	d.tile_skip = x->scratch; d.active_count = x->scratch + x->ld / 32 + 1;
+	d.t = x->t; d.T = INFINITY;
+	cudaStream_t stream = (cudaStream_t) x->stream;
+	const dim3 eblock(32, 8), egrid((unsigned) (d.ld / 32), (unsigned) ((d.n + jbd::ROWS_PER_BLOCK - 1) / jbd::ROWS_PER_BLOCK));
+	JBD_LAUNCH(jbd::setup_kernel, (unsigned) ((d.B + 255) / 256), 256, d);
+	JBD_LAUNCH(jbd::sincos_kernel<0>, egrid, eblock, d, jbd::F_ACTIVE);
+	jbd::gemm(d, stream);
+	JBD_LAUNCH(jbd::start_kernel, egrid, eblock, d);
+	cudaError_t err = cudaMemcpyAsync(dY, jbd::vec(d, jbd::W_K0), sizeof(double) * d.n * d.ld, cudaMemcpyDeviceToDevice, stream);
+	if (err == cudaSuccess) err = cudaGetLastError();
+	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_eval_f");
+}
+
+// advance every trajectory to x->T (Hairer's DOPRI5, fresh start, lands exactly on T)
+int jb_dense_integrate(const jb_dense_args *x)
+{
+	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_integrate: argument block has the wrong size");
+	if (x->B <= 0) return 0;
+	if (x->ld < x->B || x->ld % 64 || x->n <= 0 || !x->W || !x->omega || !x->t || !x->Y || !x->work || !x->ctrl
+			|| !x->status || !x->n_accepted || !x->n_rejected || !x->scratch || !x->host_flag)
+		return jbd::fail(JB_E_BAD_ARGUMENT, "jb_dense_integrate: missing or inconsistent buffers");
+	jbd::Dense d{};
+	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega;
+	d.T = x->T; d.rtol = x->rtol; d.atol = x->atol; d.max_step = x->max_step; d.first_step = x->first_step;
+	d.nmax = x->nsteps > 0 ? x->nsteps : 100000;
+	d.safety = x->safety > 0.0 ? x->safety : 0.9;
+	d.facc1 = 1.0 / (x->dfactor > 0.0 ? x->dfactor : 0.2);
+	d.facc2 = 1.0 / (x->ifactor > 0.0 ? x->ifactor : 10.0);
+	d.beta = x->beta == 0.0 ? 0.04 : (x->beta < 0.0 ? 0.0 : x->beta);
+	d.expo1 = 0.2 - d.beta * 0.75;
+	d.t = x->t; d.Y = x->Y; d.work = x->work; d.ctrl = x->ctrl; d.status = x->status;
+	d.n_accepted = x->n_accepted; d.n_rejected = x->n_rejected;
+	d.tile_skip = x->scratch; d.active_count = x->scratch + x->ld / 32 + 1;
+	cudaStream_t stream = (cudaStream_t) x->stream;
+	const dim3 eblock(32, 8), egrid((unsigned) (d.ld / 32), (unsigned) ((d.n + jbd::ROWS_PER_BLOCK - 1) / jbd::ROWS_PER_BLOCK));
+	const unsigned tgrid = (unsigned) ((d.ld + 255) / 256);
+
+	auto active_trajectories = [&](int *count) -> cudaError_t {
+		cudaError_t err = cudaMemcpyAsync(x->host_flag, d.active_count, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+		if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+		*count = *x->host_flag;
+		return err;
+	};
+	auto reset_count = [&]() { return cudaMemsetAsync(d.active_count, 0, sizeof(int32_t), stream); };
+
+	// ---- fresh start: f(t, Y), HINIT
+	cudaError_t err = reset_count();
+	JBD_LAUNCH(jbd::setup_kernel, tgrid, 256, d);
+	int active = 0;
+	if (err == cudaSuccess) err = active_trajectories(&active);
+	if (err != cudaSuccess) return jbd::fail((int) err, "jb_dense_integrate");
+	if (active == 0) return 0;
+	JBD_LAUNCH(jbd::sincos_kernel<0>, egrid, eblock, d, jbd::F_ACTIVE);
+	jbd::gemm(d, stream);
+	JBD_LAUNCH(jbd::start_kernel, egrid, eblock, d);
+	const int have_probe = !(d.first_step > 0.0);
+	if (have_probe) {
+		JBD_LAUNCH(jbd::probe_kernel, egrid, eblock, d);
+		jbd::gemm(d, stream);
+		JBD_LAUNCH(jbd::probe_finish_kernel, egrid, eblock, d);
+	}
+	reset_count();
+	JBD_LAUNCH(jbd::first_step_kernel, tgrid, 256, d, have_probe);
+
+	// ---- rounds: one step attempt of every unfinished trajectory; the host looks at the counter every few rounds
+	const int check_every = x->rounds_per_check > 0 ? x->rounds_per_check : 4;
+	int64_t rounds = 0;
+	while (true) {
+		for (int r = 0; r < check_every; ++r) {
+			JBD_LAUNCH(jbd::stage_kernel<1>, egrid, eblock, d); jbd::gemm(d, stream);
+			JBD_LAUNCH(jbd::stage_kernel<2>, egrid, eblock, d); jbd::gemm(d, stream);
+			JBD_LAUNCH(jbd::stage_kernel<3>, egrid, eblock, d); jbd::gemm(d, stream);
+			JBD_LAUNCH(jbd::stage_kernel<4>, egrid, eblock, d); jbd::gemm(d, stream);
+			JBD_LAUNCH(jbd::stage_kernel<5>, egrid, eblock, d); jbd::gemm(d, stream);
+			JBD_LAUNCH(jbd::stage_kernel<6>, egrid, eblock, d); jbd::gemm(d, stream);
+			JBD_LAUNCH(jbd::error_kernel, egrid, eblock, d);
+			reset_count();
+			JBD_LAUNCH(jbd::control_kernel, tgrid, 256, d);
+			++rounds;
+		}
+		err = active_trajectories(&active);
+		if (err != cudaSuccess) return jbd::fail((int) err, "jb_dense_integrate");
+		if (active == 0) break;
+		if (rounds > d.nmax + 8) return jbd::fail(JB_E_UNSUPPORTED, "jb_dense_integrate: round limit exceeded");
+	}
+	JBD_LAUNCH(jbd::commit_kernel, egrid, eblock, d);
+	JBD_LAUNCH(jbd::clear_accepted_kernel, tgrid, 256, d);
+	if (x->rounds_out) *x->rounds_out = rounds;
+	err = cudaGetLastError();
+	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_integrate");
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""
+Dense sine-coupled phase oscillators (BASELINE config 5, reference examples/kuramoto_network.py) on the FP64
+tensor cores: the GEMM itself, the right-hand side, and the lock-step DOPRI5 against the generic kernels, the
+CPU oracle (the reference's written-out form) and size-independent properties at n = 1000.
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+from numpy.testing import assert_allclose
+
+import workloads as W
+from jitcode_b200 import _dense, jitcode
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-6, 1e-12
+
+
+def within_tolerance(result, expected, factor=10.0, rtol=RTOL, atol=ATOL):
+	excess = np.abs(result - expected) - factor * (atol + rtol * np.abs(expected))
+	assert np.all(excess <= 0), f"max excess {excess.max():.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 16), (256, 128, 64), (300, 200, 250), (1000, 192, 1000), (7, 5, 3)])
+def test_dmma_gemm(M, N, K):
+	lib = _dense.dense_library()
+	rng = np.random.default_rng(M + N + K)
+	A = torch.as_tensor(rng.normal(size=(M, K))).cuda()
+	B = torch.as_tensor(rng.normal(size=(K, N))).cuda()
+	C = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+	stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+	assert lib.jb_dense_gemm(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, stream) == 0
+	expected = A.cpu().numpy() @ B.cpu().numpy()
+	assert_allclose(C.cpu().numpy(), expected, rtol=1e-12, atol=1e-12 * np.sqrt(K))
+
+
+def kuramoto_rhs(Wm, omega, Y):
+	diff = Y[:, None, :] - Y[:, :, None]            # [b, i, j] = y_j − y_i
+	return omega + np.einsum("ij,bij->bi", Wm, np.sin(diff))
+
+
+def test_structure_detection_and_rhs():
+	n = 48
+	system = W.kuramoto(n)
+	ODE = jitcode(system["f_sym"], n=n, verbose=False)
+	Wm, omega = ODE._dense_coupling()
+	expected = system["c"] / (n - 1) * system["A"].T.astype(float)
+	np.fill_diagonal(expected, 0.0)                   # sin(y_i − y_i) vanishes symbolically
+	assert_allclose(Wm, expected, rtol=1e-14)
+	assert_allclose(omega, system["omega"], rtol=1e-14)
+	Y = W.kuramoto_ensemble(70, n)
+	generic = ODE.f(0.0, Y)                           # generated code of the written-out form
+	ODE.set_integrator("dopri5", storage="dense")
+	dense = ODE.f(0.0, Y)
+	assert_allclose(dense, kuramoto_rhs(Wm, omega, Y), rtol=1e-12, atol=1e-13)
+	assert_allclose(dense, generic, rtol=1e-11, atol=1e-12)
+
+
+def test_dense_integration_matches_generic_kernels_and_oracle():
+	from oracle import c_rhs, ensemble
+	n, B = 40, 150
+	system = W.kuramoto(n)
+	Y0 = W.kuramoto_ensemble(B, n)
+	times = [1.0, 5.0]
+	results, counts = {}, {}
+	for storage in ("dense", None):
+		ODE = jitcode(system["f_sym"], n=n, verbose=False)
+		ODE.set_integrator("dopri5", rtol=RTOL, atol=ATOL, storage=storage)
+		ODE.set_initial_value(Y0, 0.0)
+		results[storage] = np.stack([ODE.integrate(T) for T in times])
+		counts[storage] = ODE.step_counts()
+		with pytest.raises(ValueError):
+			ODE.integrate(0.5)
+	within_tolerance(results["dense"], results[None])
+	assert abs(sum(counts["dense"]) - sum(counts[None])) <= 0.02 * sum(counts[None])
+	handle = c_rhs.build_rhs(system["f_sym"], n=n)
+	ref = ensemble.run_ensemble(handle, "dopri5", Y0[:24], times, rtol=RTOL, atol=ATOL)
+	within_tolerance(results["dense"][:, :24], ref["y"])
+
+
+def test_dense_kuramoto_1000():
+	"""config 5 at full system size: n = 1000, dense adjacency; properties that need no reference run."""
+	data = W.kuramoto_data(1000)
+	n = data["n"]
+	Wm = data["c"] / (n - 1) * data["A"].T.astype(float)
+	np.fill_diagonal(Wm, 0.0)
+	ODE = jitcode.from_sine_coupling(Wm, data["omega"])
+	Y0 = W.kuramoto_ensemble(192, n)
+	assert_allclose(ODE.f(0.0, Y0[:16]), kuramoto_rhs(Wm, data["omega"], Y0[:16]), rtol=1e-11, atol=1e-12)
+	ODE.set_integrator("dopri5", rtol=1e-6, atol=1e-9)
+	ODE.set_initial_value(torch.as_tensor(Y0).cuda(), 0.0)
+	coarse = ODE.integrate(2.0).cpu().numpy()
+	accepted, rejected = ODE.step_counts()
+	rounds = ODE.integrator.rounds
+	assert accepted >= 192 and rounds * 192 >= accepted + rejected        # lock-step: rounds ≥ attempts of the slowest
+	assert (accepted + rejected) / (rounds * 192) > 0.5                   # … and most slots do useful work
+	# a ten times tighter run is the yardstick for the looser one
+	ODE.set_integrator("dopri5", rtol=1e-8, atol=1e-11)
+	ODE.set_initial_value(Y0, 0.0)
+	fine = ODE.integrate(2.0)
+	assert np.abs(coarse - fine).max() < 1e-4
+	# the mean phase velocity is the mean frequency plus the antisymmetric-part imbalance; for every trajectory
+	# Σ_i dy_i/dt = Σω + Σ_ij W_ij sin(y_j − y_i) holds — check f at the final state against NumPy once more
+	assert_allclose(ODE.f(0.0, fine[:8]), kuramoto_rhs(Wm, data["omega"], fine[:8]), rtol=1e-11, atol=1e-12)
