@@ -58,6 +58,15 @@ def workload(name, B, seed_offset=0):
 		Y0, pars = W.lotka_volterra_ensemble(B, seed=42 + seed_offset)
 		return {"system": system, "Y0": Y0, "pars": pars, "T": 100.0, "integrator": "dopri5",
 				"label": "Lotka-Volterra ensemble (n=2), random initial conditions"}
+	if name == "kuramoto":
+		# config 5: 1000 oscillators, dense adjacency; the symbolic form has 2·10^5 sine terms (SymPy needs minutes to
+		# build it), so the system enters through its data — same kernels as the recognised symbolic form
+		data = W.kuramoto_data(1000)
+		n = data["n"]
+		Wm = data["c"] / (n - 1) * data["A"].T.astype(float)
+		np.fill_diagonal(Wm, 0.0)
+		return {"system": {"n": n, "sine_coupling": (Wm, data["omega"]), "control_pars": []}, "Y0": W.kuramoto_ensemble(B, n, seed=44 + seed_offset),
+				"pars": np.empty((B, 0)), "T": 5.0, "integrator": "dopri5", "label": "kuramoto_network n=1000 dense adjacency"}
 	raise SystemExit(f"unknown workload {name}")
 
 
@@ -99,6 +108,9 @@ def cpu_baseline(wl, per_core):
 def run_reference(args):
 	rank = int(os.environ.get("RANK", "0"))
 	if rank != 0:
+		return
+	if args.workload == "kuramoto":
+		print(json.dumps({"impl": "reference", "unavailable": "the reference's written-out form of the dense 1000-oscillator network (2e5 sine terms of generated C) is not built by the default run"}))
 		return
 	per_core = args.cpu_sample_per_core
 	from oracle import ensemble
@@ -196,8 +208,13 @@ def run_ours(args):
 	wl = workload(args.workload, B, seed_offset=1000 * rank)      # every rank integrates its own shard
 	system = wl["system"]
 	n = system["n"]
-	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=n, control_pars=system["control_pars"], verbose=False)
-	ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=ATOL, storage=args.storage, kregs=args.kregs)
+	dense = "sine_coupling" in system
+	if dense:
+		ODE = jitcode.from_sine_coupling(*system["sine_coupling"])
+		ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=1e-9)
+	else:
+		ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=n, control_pars=system["control_pars"], verbose=False)
+		ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=ATOL, storage=args.storage, kregs=args.kregs)
 	integrator = ODE.integrator
 	module = integrator.module
 
@@ -276,7 +293,7 @@ def run_ours(args):
 		bytes_per_launch = 280.0 * n * own_attempts           # 35·n·8 B per trajectory-step
 		kernel_s = statistics.mean(kernel_ms) * 1e-3
 		achieved = bytes_per_launch / kernel_s / 1e9
-		storage_name = {0: "registers", 1: "global", 2: "warp"}.get(module.info.storage)
+		storage_name = {0: "registers", 1: "global", 2: "warp", 3: "dense"}.get(module.info.storage)
 		traffic_file = ROOT / "profiles" / "traffic.json"
 		traffic = None
 		if traffic_file.exists():
@@ -286,7 +303,7 @@ def run_ours(args):
 		# the state never leaves the chip between samples in register / warp storage: FP64 is the second yardstick
 		import sympy
 		from jitcode_b200 import _peaks
-		rhs_flops = float(sum(sympy.count_ops(entry) for entry in ODE._f_list))
+		rhs_flops = float(sum(sympy.count_ops(entry) for entry in ODE._f_list)) if not dense else 4.0 * n * n
 		flops_per_step = 72.0 * n + 6.0 * rhs_flops
 		fp64_peak = _peaks.fp64_fma_tflops(device)
 		fp64_achieved = flops_per_step * own_attempts / kernel_s / 1e12
@@ -310,7 +327,12 @@ def run_ours(args):
 					"fp64": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
 							"flops_per_trajectory_step": flops_per_step, "peak_source": "DFMA microbenchmark measured in this run (jitcode_b200/_peaks.py)"}},
 		}
-		if world == 1 and not args.no_cpu_baseline:
+		if dense:
+			# the contraction is the kernel: FP64 tensor cores against the measured FP64 peak
+			line["roofline"].update({"bound": "tensor", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
+					"peak_source": "FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)", "kernel": "dgemm_dmma_kernel + element-wise stages (jb_dense_integrate)"})
+			line["config"]["lock_step_rounds_per_step"] = integrator.rounds / max(1, args.steps)
+		if world == 1 and not args.no_cpu_baseline and not dense:
 			line["cpu_baseline"] = cpu_baseline(wl, args.cpu_sample_per_core)
 		print(json.dumps(line))
 	if world > 1:
@@ -323,13 +345,15 @@ def main():
 	parser.add_argument("--steps", type=int, default=5)
 	parser.add_argument("--warmup", type=int, default=3)
 	parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
-	parser.add_argument("--workload", default="roessler", choices=["roessler", "lv"])
+	parser.add_argument("--workload", default="roessler", choices=["roessler", "lv", "kuramoto"])
 	parser.add_argument("--trajectories", type=int, default=1 << 20, help="per GPU")
 	parser.add_argument("--storage", default=None, choices=[None, "registers", "global", "warp"])
 	parser.add_argument("--kregs", type=int, default=None)
 	parser.add_argument("--cpu-sample-per-core", type=int, default=None)
 	parser.add_argument("--no-cpu-baseline", action="store_true")
 	args = parser.parse_args()
+	if args.workload == "kuramoto" and args.trajectories == 1 << 20:
+		args.trajectories = 4096
 	args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 	if args.cpu_sample_per_core is None:
 		args.cpu_sample_per_core = 2048 if args.workload == "roessler" else 16384
