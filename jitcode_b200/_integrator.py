@@ -119,6 +119,7 @@ class CudaEnsembleIntegrator:
 		self._out_kind = "numpy"
 		self._single = False
 		self.last_lyaps = None
+		self._sampled = False      # an integrate call has produced a sample since set_initial_value
 		self.kernel_events = None   # set to [] to collect (start, end) CUDA events around every integrate launch
 
 	# ------------------------------------------------------------------ plumbing
@@ -218,7 +219,12 @@ class CudaEnsembleIntegrator:
 		self._pack(rows, self.P, self.n_params)
 		self._pars_on_device = True
 		if self.sstate is not None:
-			self.sstate.zero_()   # the solve_ivp stepper is re-created with the new right-hand side
+			# the solve_ivp stepper is re-created with the new right-hand side — from the last SAMPLE (t, y(t)),
+			# which for the dense driver is not where the stepper itself stands (it has stepped beyond t)
+			if self.driver == JB_DRV_IVP_DENSE and self._sampled:
+				self.Y.copy_(self.Yres)
+				self.tt.fill_(self.time)
+			self.sstate.zero_()
 
 	def set_initial_value(self, initial_value, time=0.0):
 		rows, kind, single = self._to_device_rows(initial_value, self.n, "initial value")
@@ -229,6 +235,7 @@ class CudaEnsembleIntegrator:
 		self.tt.fill_(float(time))
 		self.time = float(time)
 		self.status.zero_()
+		self._sampled = False
 		if self.sstate is not None:
 			self.sstate.zero_()       # IVP_wrapper.set_initial_value re-creates the stepper (:90-93)
 		self._rows = rows
@@ -318,6 +325,7 @@ class CudaEnsembleIntegrator:
 		else:
 			self.module.integrate(args)
 		self.time = times[-1]
+		self._sampled = True
 		return Yrec, lyap_rec
 
 	def _current_rows(self):

@@ -722,6 +722,9 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			}
 			const double max_step = a.max_step > 0.0 ? a.max_step : INFINITY;
 			const double t_bound = DENSE ? INFINITY : T;
+			// solve_ivp has no step limit; a launch must end nevertheless
+			constexpr int64_t ATTEMPT_CAP = (int64_t) 1 << 26;
+			int64_t attempts_here = 0;
 			while (status == JB_OK && (t < T || (DENSE && !(t_old == t_old)))) {
 				// ---- begin a step: K[0] = f(t, Y)
 				if (pending_f) {
@@ -737,7 +740,9 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 				else if (h_abs < min_step) h_abs = min_step;
 				bool rejected = false;
 				while (true) {
-					if (h_abs < min_step || !(h_abs == h_abs)) { status = JB_STEP_TOO_SMALL; break; }
+					if (!(fabs(h_abs) <= 1.79769313486231571e308)) { status = JB_NONFINITE; break; }   // NaN or ∞ (non-finite state)
+					if (h_abs < min_step) { status = JB_STEP_TOO_SMALL; break; }
+					if (++attempts_here > ATTEMPT_CAP) { status = JB_TOO_MANY_STEPS; break; }
 					double t_new = t + h_abs;
 					if (t_new - t_bound > 0.0) t_new = t_bound;
 					const double h = t_new - t;

@@ -12,6 +12,11 @@ GOLDEN = ROOT / "tests" / "golden"
 
 def pytest_configure(config):
 	config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+	# a GPU test that hangs inside a CUDA call cannot be interrupted by a signal: let the watchdog thread end the run
+	if config.pluginmanager.hasplugin("timeout"):
+		config.option.timeout_method = "thread"
+		if not getattr(config.option, "timeout", None):
+			config.option.timeout = 600
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,176 @@
+"""
+Edge cases of the hot path on the GPU, each against the CPU oracle (the reference's integrators):
+ragged batch sizes in every storage mode, per-component atol, max_step / first_step, the step limit,
+parameter changes between calls, integrator swaps that keep the state, NaN inputs.
+"""
+
+import numpy as np
+import pytest
+import sympy
+import torch
+from numpy.testing import assert_allclose
+
+import workloads as W
+from jitcode_b200 import UnsuccessfulIntegration, jitcode, t, y
+from oracle import c_rhs, ensemble, wrappers
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-6, 1e-12
+
+
+def within_tolerance(result, expected, factor=10.0):
+	excess = np.abs(result - expected) - factor * (ATOL + RTOL * np.abs(expected))
+	assert np.all(excess <= 0), f"max excess {excess.max():.3e}"
+
+
+def make(system):
+	return jitcode(system["f_sym"], helpers=system["helpers"], n=system["n"], control_pars=system["control_pars"], verbose=False)
+
+
+def oracle(system, name, Y0, times, pars=None, **params):
+	handle = c_rhs.build_rhs(system["f_sym"], system["helpers"], system["control_pars"], system["n"])
+	return ensemble.run_ensemble(handle, name, Y0, times, pars=pars, processes=2, **params)["y"]
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 65])
+@pytest.mark.parametrize("storage", ["registers", "global"])
+def test_ragged_batches_thread_storage(B, storage):
+	system = W.fhn()
+	Y0 = W.FHN_Y0 + 0.01 * np.random.default_rng(B).normal(size=(B, 4))
+	ODE = make(system)
+	ODE.set_integrator("dopri5", storage=storage, rtol=RTOL, atol=ATOL)
+	ODE.set_initial_value(Y0, 0.0)
+	result = ODE.integrate(30.0)
+	assert result.shape == (B, 4)
+	within_tolerance(result, oracle(system, "dopri5", Y0, [30.0], rtol=RTOL, atol=ATOL)[0])
+
+
+@pytest.mark.parametrize("B", [1, 7, 148 * 13 + 5])
+def test_ragged_batches_warp_storage(B):
+	system = W.roessler_network(100)
+	Y0, pars = W.roessler_ensemble(B, seed=B)
+	ODE = make(system)
+	ODE.set_integrator("dopri5", storage="warp", rtol=RTOL, atol=ATOL)
+	ODE.set_parameters(pars[:, 0])
+	ODE.set_initial_value(Y0, 0.0)
+	result = ODE.integrate(2.0)
+	assert result.shape == (B, 300)
+	ref = oracle(system, "dopri5", Y0[:5], [2.0], pars=pars[:5], rtol=RTOL, atol=ATOL)[0]
+	assert_allclose(result[:5], ref, rtol=1e-7, atol=1e-9)
+	# every trajectory was integrated (none left at its initial value), also in the last partial block
+	assert np.all(np.abs(result - Y0).max(axis=1) > 1e-3)
+
+
+@pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("RK45", True), ("RK45", False)])
+def test_vector_atol_and_max_step(name, interpolate):
+	system = W.lotka_volterra()
+	Y0, _ = W.lotka_volterra_ensemble(40, seed=3)
+	# SciPy 1.18.1's compiled dopri5 only takes a scalar atol ("only length-1 arrays …"); solve_ivp takes one per component
+	atol = np.array([1e-9, 1e-9]) if name == "dopri5" else np.array([1e-9, 1e-5])
+	params = {"rtol": 1e-7, "atol": atol, "max_step": 0.37}
+	ODE = make(system)
+	ODE.set_integrator(name, interpolate=interpolate, **params)
+	ODE.set_initial_value(Y0, 0.0)
+	result = ODE.integrate(12.0)
+	handle = c_rhs.build_rhs(system["f_sym"], n=2)
+	if name == "dopri5":
+		params["atol"] = 1e-9
+	ref = ensemble.run_ensemble(handle, name, Y0, [12.0], interpolate=interpolate, processes=2, **params)
+	bound = 10 * (atol + 1e-7 * np.abs(ref["y"][0]))
+	assert np.all(np.abs(result - ref["y"][0]) <= bound)
+	attempts = sum(ODE.step_counts())
+	assert attempts >= 40 * int(12.0 / 0.37)                      # max_step is honoured
+	assert abs(attempts - ref["attempts"]) <= 0.05 * ref["attempts"]
+
+
+def test_first_step_and_step_limit():
+	system = W.lotka_volterra()
+	Y0, _ = W.lotka_volterra_ensemble(8, seed=4)
+	ODE = make(system)
+	ODE.set_integrator("dopri5", rtol=RTOL, atol=ATOL, first_step=1e-3)
+	ODE.set_initial_value(Y0, 0.0)
+	within_tolerance(ODE.integrate(5.0), oracle(system, "dopri5", Y0, [5.0], rtol=RTOL, atol=ATOL, first_step=1e-3)[0])
+	# nsteps: the reference raises UnsuccessfulIntegration when the limit is hit (integrator_tools.py:137-140)
+	ODE.set_integrator("dopri5", nsteps=5, rtol=RTOL, atol=ATOL)
+	ODE.set_initial_value(Y0, 0.0)
+	with pytest.raises(UnsuccessfulIntegration) as failure:
+		ODE.integrate(100.0)
+	assert len(failure.value.indices) == 8 and set(failure.value.status) == {2}
+	backend = wrappers.make_backend("dopri5", c_rhs.build_rhs(system["f_sym"], n=2).f, nsteps=5, rtol=RTOL, atol=ATOL)
+	backend.set_initial_value(Y0[0], 0.0)
+	with pytest.raises(wrappers.UnsuccessfulIntegration):
+		backend.integrate(100.0)
+
+
+def test_parameters_can_change_between_calls():
+	system = W.lotka_volterra(gamma_as_parameter=True)
+	Y0, gam = W.lotka_volterra_ensemble(12, seed=6, gamma_as_parameter=True)
+	for name in ("dopri5", "RK45"):
+		ODE = make(system)
+		ODE.set_integrator(name, rtol=RTOL, atol=ATOL)
+		ODE.set_parameters(gam[:, 0])
+		ODE.set_initial_value(Y0, 0.0)
+		middle = ODE.integrate(5.0)
+		ODE.set_parameters(0.5)                              # one value for all trajectories from here on
+		final = ODE.integrate(9.0)
+		first = oracle(system, name, Y0, [5.0], pars=gam, rtol=RTOL, atol=ATOL)[0]
+		within_tolerance(middle, first)
+		handle = c_rhs.build_rhs(system["f_sym"], control_pars=system["control_pars"], n=2)
+		second = ensemble.run_ensemble(handle, name, first, [9.0], pars=np.full((12, 1), 0.5), t0=5.0, processes=1, rtol=RTOL, atol=ATOL)["y"][0]
+		within_tolerance(final, second, factor=30.0)
+
+
+def test_integrator_swap_keeps_state_and_time():
+	# reference _jitcode.py:619-626
+	system = W.lotka_volterra()
+	Y0, _ = W.lotka_volterra_ensemble(10, seed=8)
+	ODE = make(system)
+	ODE.set_initial_value(Y0, 0.0)                       # before any integrator exists (empty_integrator holds it)
+	ODE.set_integrator("dopri5", rtol=RTOL, atol=ATOL)
+	middle = ODE.integrate(4.0)
+	ODE.set_integrator("RK45", rtol=RTOL, atol=ATOL)
+	assert ODE.t == 4.0
+	assert_allclose(ODE.y, middle, rtol=0, atol=0)
+	final = ODE.integrate(8.0)
+	within_tolerance(final, oracle(system, "dopri5", Y0, [8.0], rtol=RTOL, atol=ATOL)[0], factor=30.0)
+	assert set(ODE.y_dict) == {y(0), y(1)}
+
+
+def test_explicit_time_dependence_and_helpers():
+	# reference tests/test_sympy_input.py: dy/dt = cos(t)·y  →  y(t) = y0·exp(sin t); plus a helper
+	h = sympy.Symbol("h")
+	ODE = jitcode([h * y(0)], helpers=[(h, sympy.cos(t))], verbose=False)
+	ODE.set_integrator("dopri5", rtol=1e-10, atol=1e-12)
+	start = np.linspace(0.5, 2.0, 37).reshape(-1, 1)
+	ODE.set_initial_value(start, 0.0)
+	assert_allclose(ODE.integrate(10.0), start * np.exp(np.sin(10.0)), rtol=1e-8)
+
+
+def test_non_finite_input_is_reported_not_hung():
+	system = W.lotka_volterra()
+	Y0, _ = W.lotka_volterra_ensemble(6, seed=9)
+	Y0[2, 0] = np.nan
+	for name in ("dopri5", "RK45"):
+		ODE = make(system)
+		ODE.set_integrator(name, rtol=RTOL, atol=ATOL)
+		ODE.set_initial_value(Y0, 0.0)
+		with pytest.raises(UnsuccessfulIntegration) as failure:
+			ODE.integrate(3.0)
+		assert list(failure.value.indices) == [2]
+		healthy = ODE.integrator.y_device.cpu().numpy()[[0, 1, 3, 4, 5]]
+		assert np.all(np.isfinite(healthy))
+
+
+def test_torch_cpu_round_trip_and_out_buffer():
+	system = W.lotka_volterra()
+	Y0, _ = W.lotka_volterra_ensemble(100, seed=10)
+	ODE = make(system)
+	ODE.set_integrator("dopri5", rtol=RTOL, atol=ATOL)
+	ODE.set_initial_value(torch.as_tensor(Y0), 0.0)
+	result = ODE.integrate(3.0)
+	assert isinstance(result, torch.Tensor) and not result.is_cuda
+	out = torch.empty((100, 2), dtype=torch.float64).pin_memory()
+	ODE.set_initial_value(torch.as_tensor(Y0).pin_memory(), 0.0)
+	assert ODE.integrate(3.0, out=out) is out
+	assert_allclose(out.numpy(), result.numpy(), rtol=0, atol=0)
