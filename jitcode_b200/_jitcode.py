@@ -74,9 +74,12 @@ def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None
 	row_bytes = (n + 2) // 2 * 2 * 8
 	available = SHARED_MEMORY_PER_BLOCK - table_bytes - 4 * n - 64
 
+	last_stage = 6 if method == _codegen.JB_DP5 else 12      # K[S]: its row doubles as the staging row while k <= S
+
 	def warps(k):
-		by_shared = available // ((2 + dense + stages - k) * row_bytes)
-		registers = 90 + 2 * passes * (1 + k) if k else 96       # measured on the Rössler network (profiles/)
+		rows = 1 + (1 if (k == 0 or k > last_stage) else 0) + dense + stages - k       # WarpStore::ROWS
+		by_shared = available // (rows * row_bytes)
+		registers = 80 + 2 * passes * (1 + k) if k else 96       # measured on the Rössler network (profiles/)
 		if registers > 255:
 			return 0
 		return max(0, min(16, by_shared, 65536 // (32 * registers)))

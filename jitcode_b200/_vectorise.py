@@ -61,8 +61,26 @@ def _is_dynvar(expr):
 	return isinstance(expr, AppliedUndef) and expr.func.__name__ == "y"
 
 
-def analyse(expr, allow_loops=True):
-	"""canonical tree of a SymPy expression."""
+def _first(node, kind):
+	if node.kind == kind:
+		return node.value
+	for child in node.children:
+		found = _first(child, kind)
+		if found is not None:
+			return found
+	return None
+
+
+def _role(node, own):
+	"""tie-break between equally shaped children of a commutative operation, chosen so that the same ROLE lands in
+	the same slot in every statement of a group: the distance of the first dynamical variable to the statement's
+	own component (a·y(i+1) + ω·y(i) vs ω'·y(j) + a·y(j+1)), then the first constant."""
+	index, constant = _first(node, "y"), _first(node, "const")
+	return (0 if index is None else 1, 0 if index is None else (index - own if own is not None else index), 0.0 if constant is None else constant)
+
+
+def analyse(expr, allow_loops=True, own=None):
+	"""canonical tree of a SymPy expression (`own`: index of the component whose equation this is)."""
 	if expr.is_Number:
 		return Node("const", float(expr))
 	if _is_dynvar(expr):
@@ -70,9 +88,9 @@ def analyse(expr, allow_loops=True):
 	if expr.is_Symbol:
 		return Node("sym", expr)
 	if expr.is_Pow and expr.exp.is_Number:
-		return Node("pow", expr.exp, [analyse(expr.base, allow_loops)])
+		return Node("pow", expr.exp, [analyse(expr.base, allow_loops, own)])
 	if expr.is_Add or expr.is_Mul:
-		children = sorted((analyse(arg, allow_loops) for arg in expr.args), key=lambda node: node.key)
+		children = sorted((analyse(arg, allow_loops, own) for arg in expr.args), key=lambda node: (node.key, _role(node, own)))
 		if expr.is_Add and allow_loops:
 			runs = OrderedDict()
 			for child in children:
@@ -84,10 +102,10 @@ def analyse(expr, allow_loops=True):
 					children.append(Node("loop", None, members))
 				else:
 					children.extend(members)
-			children.sort(key=lambda node: node.key)
+			children.sort(key=lambda node: (node.key, _role(node, own) if node.kind != "loop" else ()))
 		return Node("op", expr.func, children)
 	if isinstance(expr, sympy.Function) or isinstance(expr, AppliedUndef):
-		return Node("op", expr.func, [analyse(arg, allow_loops) for arg in expr.args])
+		return Node("op", expr.func, [analyse(arg, allow_loops, own) for arg in expr.args])
 	raise NotImplementedError(f"cannot vectorise {expr!r}")
 
 
@@ -237,7 +255,7 @@ def make_plan(f, helpers, control_pars):
 		plan.helpers.append((sympy.Symbol(f"jb_helper_{k}"), group))
 	groups = OrderedDict()
 	for i, entry in enumerate(f):
-		node = analyse(sympy.sympify(entry))
+		node = analyse(sympy.sympify(entry), own=i)
 		if node.key not in groups:
 			groups[node.key] = Group(node.key, node, f"jb_g{len(groups)}_")
 		groups[node.key].add(i, node)
@@ -399,6 +417,43 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 		# as small as it gets: 16-bit byte offsets, two per 32-bit word (one wavefront per 64 gathers), and every
 		# pass of 32 statements is padded only to ITS longest statement.
 		n_pass = (size + 31) // 32
+		per_statement = [indices[0][loop.start[m]:loop.start[m+1]] for m in range(size)]
+
+		# Diagonals: in lattice-like networks most statements read the SAME relative neighbours (m+1, m-1, m+2 …
+		# within a ring of positions lo … lo+L-1).  Such a neighbour needs no table at all — lane m reads position
+		# lo + (m + d) mod L, consecutive lanes read consecutive words (no bank conflict), and where no lane of a
+		# pass wraps around the ring the address is the lane's own base plus a compile-time offset.  A bit mask per
+		# statement says which diagonals it really has.  Everything else stays in the padded pair table.
+		diagonals, lo, ring = [], 0, 0
+		gathered = [p for terms in per_statement for p in terms]
+		if gathered and min(group.outs) >= 0:
+			lo, ring = min(gathered), max(gathered) - min(gathered) + 1
+			popularity = {}
+			for m, terms in enumerate(per_statement):
+				for p in terms:
+					d = (p - lo - m) % ring
+					popularity[d] = popularity.get(d, 0) + 1
+			diagonals = sorted(d for d, count in popularity.items() if count >= 0.6 * size)[:32]
+			if len(diagonals) < 4 or ring > 32767:
+				diagonals = []
+		masks = []
+		if diagonals:
+			where = {d: k for k, d in enumerate(diagonals)}
+			remainder = []
+			for m, terms in enumerate(per_statement):
+				mask, rest, seen = 0, [], set()
+				for p in terms:
+					d = (p - lo - m) % ring
+					if d in where and d not in seen:
+						mask |= 1 << where[d]
+						seen.add(d)
+					else:
+						rest.append(p)
+				masks.append(mask)
+				remainder.append(rest)
+			per_statement = remainder
+		lengths = [len(terms) for terms in per_statement]
+
 		words, bases, widths = [], [], []
 		for p in range(n_pass):
 			members = range(32*p, min(size, 32*p + 32))
@@ -409,29 +464,48 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 			for kp in range(pass_width // 2):
 				for lane in range(32):
 					m = 32*p + lane
-					pair = []
 					for k in (2*kp, 2*kp + 1):
 						inside = m < size and k < lengths[m]
-						pair.append(8 * (indices[0][loop.start[m] + k] if inside else zero_slot))
-					words.extend(pair)
-		offset = tables.add_u(words, align=2)
+						words.append(8 * (per_statement[m][k] if inside else zero_slot))
+		offset = tables.add_u(words, align=2) if words else 0
 		for c, values in enumerate(consts):
 			lines.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
 		term = printer.doprint(loop.body)
 		reads = f"y({loop.prefix}i0)"
 		assert reads in term
-		lines.append(f"\tdouble {name}_a = 0.0, {name}_b = 0.0;")
-		lines.append("\t{")
-		lines.append(f"\t\tconstexpr int pass_base[{n_pass}] = {{ {', '.join(map(str, bases))} }}, pass_pairs[{n_pass}] = {{ {', '.join(map(str, widths))} }};")
-		lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
-		lines.append("#pragma unroll")
-		lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
-		lines.append("\t\t\tconst unsigned pair = pairs[k * 32];")
-		lines.append(f"\t\t\t{name}_a += {term.replace(reads, 'y.at(pair & 0xffffu)')};")
-		lines.append(f"\t\t\t{name}_b += {term.replace(reads, 'y.at(pair >> 16)')};")
-		lines.append("\t\t}")
-		lines.append("\t}")
-		lines.append(f"\tconst double {name} = {name}_a + {name}_b;")
+		lines.append(f"\tdouble {name}_a = 0.0, {name}_b = 0.0, {name}_c = 0.0, {name}_d = 0.0;")
+		if diagonals:
+			full = (1 << len(diagonals)) - 1
+			all_present = all(mask == full for mask in masks)
+			lines.append("\t{")
+			if not all_present:
+				# the mask is split into two 16-bit table entries
+				low = tables.add_u([mask & 0xffff for mask in masks])
+				high = tables.add_u([mask >> 16 for mask in masks])
+				lines.append(f"\t\tconst unsigned present = JB_TU[{low} + m] | ((unsigned) JB_TU[{high} + m] << 16);")
+			for k, d in enumerate(diagonals):
+				# 32·pass + 31 + d < ring: no lane of this pass wraps; 32·pass + d >= ring: all of them do (pass is a constant after unrolling)
+				index = (f"((32 * pass + 31 + {d} < {ring}) ? m + {d} : ((32 * pass + {d} >= {ring}) ? m + {d} - {ring} : "
+						f"(m + {d} >= {ring} ? m + {d} - {ring} : m + {d})))")
+				value = term.replace(reads, f"y({lo} + {index})")
+				accumulator = f"{name}_{'abcd'[k % 4]}"
+				if all_present:
+					lines.append(f"\t\t{accumulator} += {value};")
+				else:
+					lines.append(f"\t\tif (present & {1 << k}u) {accumulator} += {value};")
+			lines.append("\t}")
+		if words:
+			lines.append("\t{")
+			lines.append(f"\t\tconstexpr int pass_base[{n_pass}] = {{ {', '.join(map(str, bases))} }}, pass_pairs[{n_pass}] = {{ {', '.join(map(str, widths))} }};")
+			lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
+			lines.append("#pragma unroll")
+			lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
+			lines.append("\t\t\tconst unsigned pair = pairs[k * 32];")
+			lines.append(f"\t\t\t{name}_c += {term.replace(reads, 'y.at(pair & 0xffffu)')};")
+			lines.append(f"\t\t\t{name}_d += {term.replace(reads, 'y.at(pair >> 16)')};")
+			lines.append("\t\t}")
+			lines.append("\t}")
+		lines.append(f"\tconst double {name} = ({name}_a + {name}_b) + ({name}_c + {name}_d);")
 		return
 
 	# general terms: one ELL table per varying slot; padding terms vanish, or are skipped by a per-lane count

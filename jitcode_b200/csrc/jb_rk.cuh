@@ -250,8 +250,11 @@ struct WarpStore {          // one warp per trajectory, lanes across components
 	static constexpr int KR = L::KR;
 	static constexpr bool CACHED = KREGS > 0;           // Y and K[0 … KREGS) live in registers, lane-strided
 	static constexpr int NP = (N + 31) / 32;            // passes of a lane-strided loop
-	// shared-memory rows of one warp: Z, [staging row of the right-hand side], [Y], [y_old], K[KREGS … KR)
-	static constexpr int ROWS = 1 + (CACHED ? 1 : 1) + (L::DENSE ? 1 : 0) + (KR - KREGS);
+	// The staging row through which the right-hand side fills a register row shares the row of K[S]: register rows
+	// are only filled while K[S] (f at the end of the last step) is dead — it moves to K[0] before the next stage 1.
+	static constexpr bool F_ALIASED = CACHED && KREGS <= Tab::NSTAGE;
+	// shared-memory rows of one warp: Z, [staging row], [Y], [y_old], K[KREGS … KR)
+	static constexpr int ROWS = 1 + (CACHED ? (F_ALIASED ? 0 : 1) : 1) + (L::DENSE ? 1 : 0) + (KR - KREGS);
 	using IVec = SVec;
 	using UVec = PVec<typename Sys::TU>;
 
@@ -265,8 +268,9 @@ struct WarpStore {          // one warp per trajectory, lanes across components
 	{
 		int row = 0;
 		pZ = smem + NROW * row++;
-		if constexpr (CACHED) { pF = smem + NROW * row++; pY = nullptr; }
-		else { pY = smem + NROW * row++; pF = nullptr; }
+		pY = pF = nullptr;
+		if constexpr (!CACHED) pY = smem + NROW * row++;
+		else if constexpr (!F_ALIASED) pF = smem + NROW * row++;
 		pYO = L::DENSE ? smem + NROW * row++ : nullptr;
 #pragma unroll
 		for (int j = 0; j < KR; ++j) pK[j] = j < KREGS ? nullptr : smem + NROW * (row + j - KREGS);
@@ -329,8 +333,9 @@ struct WarpStore {          // one warp per trajectory, lanes across components
 	template <int J> __device__ __forceinline__ void call(double t, const double *in)
 	{
 		if constexpr (J < KREGS) {
-			rhs_warp_outlined<Sys>(t, in, pF, par, tables);
-			for_each([&](int i, auto r) { rk[J][r] = pF[i]; });
+			double *const staging = F_ALIASED ? pK[Tab::NSTAGE] : pF;
+			rhs_warp_outlined<Sys>(t, in, staging, par, tables);
+			for_each([&](int i, auto r) { rk[J][r] = staging[i]; });
 		} else {
 			rhs_warp_outlined<Sys>(t, in, pK[J], par, tables);
 		}

@@ -166,7 +166,13 @@ def test_module_builds_loads_and_exports_every_symbol():
 	"""the C ABI: every function declared in include/jitcode_b200.h is exported by a compiled module."""
 	header = (ROOT / "include" / "jitcode_b200.h").read_text()
 	declared = set(re.findall(r"\b(jb_[a-z_]+)\s*\(", header))
-	assert declared == set(_build.EXPORTS)
+	from jitcode_b200 import _dense
+	assert declared == set(_build.EXPORTS) | set(_dense.DENSE_EXPORTS)
+	dense = _dense.dense_library()                    # the dense sine-coupling library: built once, loaded without a GPU
+	for name in _dense.DENSE_EXPORTS:
+		assert hasattr(dense, name), name
+	assert dense.jb_dense_work_vectors() == 12 and dense.jb_dense_control_scalars() == 9
+	declared -= set(_dense.DENSE_EXPORTS)
 	ODE = jitcode(W.lotka_volterra(gamma_as_parameter=True)["f_sym"], n=2, control_pars=W.lotka_volterra(gamma_as_parameter=True)["control_pars"], verbose=False)
 	module = ODE.compile_cuda()
 	lib = ctypes.CDLL(module.path)
@@ -179,6 +185,36 @@ def test_module_builds_loads_and_exports_every_symbol():
 	# argument validation happens before any CUDA call
 	assert lib.jb_integrate(None) == -2
 	assert b"ABI" in ctypes.cast(lib.jb_last_error, ctypes.CFUNCTYPE(ctypes.c_char_p))()
+
+
+def test_dense_struct_layout_and_detection():
+	import subprocess, tempfile
+	from jitcode_b200 import _dense
+	probe = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "jitcode_b200.h"
+int main(void) {
+	printf("%zu %zu %zu %zu %zu\n", sizeof(jb_dense_args), offsetof(jb_dense_args, W), offsetof(jb_dense_args, t), offsetof(jb_dense_args, host_flag), offsetof(jb_dense_args, stream));
+	return 0;
+}'''
+	with tempfile.TemporaryDirectory() as tmp:
+		src = Path(tmp) / "probe.c"
+		src.write_text(probe)
+		subprocess.run(["gcc", f"-I{ROOT/'include'}", str(src), "-o", str(Path(tmp)/"probe")], check=True)
+		out = subprocess.run([str(Path(tmp)/"probe")], capture_output=True, text=True, check=True).stdout.split()
+	A = _dense.DenseArgs
+	assert [int(v) for v in out] == [ctypes.sizeof(A), A.W.offset, A.t.offset, A.host_flag.offset, A.stream.offset]
+	# structure detection: the reference's written-out Kuramoto network → (W, omega); anything else → None
+	system = W.kuramoto(12)
+	f, _ = _symbolic.handle_input(system["f_sym"], 12)
+	Wm, omega = _dense.detect_sine_coupling(f)
+	expected = system["c"] / 11 * system["A"].T.astype(float)
+	np.fill_diagonal(expected, 0.0)
+	np.testing.assert_allclose(Wm, expected, rtol=1e-14)
+	np.testing.assert_allclose(omega, system["omega"], rtol=1e-14)
+	assert _dense.detect_sine_coupling(_symbolic.handle_input(fhn_list())[0]) is None
+	assert _dense.detect_sine_coupling([sympy.sin(y(0) - y(1)) + y(0), sympy.sin(y(0) - y(1))]) is None
 
 
 def test_struct_layout_matches_header():
