@@ -72,6 +72,11 @@ def _run_chunk(task):
 	return out, nfev, failed, lyaps
 
 
+def _warm_up(handle):
+	handle.f      # imports the compiled right-hand side in the worker
+	return os.getpid()
+
+
 def available_cores():
 	return len(os.sched_getaffinity(0))
 
@@ -97,13 +102,18 @@ def run_ensemble(handle, method, Y0, times, pars=None, t0=0.0, interpolate=True,
 		(handle, method, interpolate, params, Y0[a:b], pars[a:b], t0, times, lyap)
 		for a, b in zip(bounds[:-1], bounds[1:]) if b > a
 	]
-	start = time.perf_counter()
 	if P == 1:
+		start = time.perf_counter()
 		results = [_run_chunk(task) for task in tasks]
+		seconds = time.perf_counter() - start
 	else:
-		with mp.get_context("fork").Pool(P) as pool:
+		# forkserver: the workers descend from a clean helper process, not from this one — the caller may hold a
+		# CUDA context and torch threads (GPU tests, bench.py), and forking that aborts in the children now and then
+		with mp.get_context("forkserver").Pool(P) as pool:
+			pool.map(_warm_up, [handle] * P, chunksize=1)     # start-up of the workers is not integration time
+			start = time.perf_counter()
 			results = pool.map(_run_chunk, tasks, chunksize=1)
-	seconds = time.perf_counter() - start
+			seconds = time.perf_counter() - start
 	nfev = np.concatenate([r[1] for r in results])
 	return {
 		"y": np.concatenate([r[0] for r in results], axis=1),
