@@ -238,6 +238,9 @@ def run_ours(args):
 	def host_step():
 		if pars_host is not None:
 			ODE.set_parameters(pars_host)
+		if hasattr(integrator, "integrate_streamed") and B >= 65536:
+			# the public call for host-resident ensembles: uploads and downloads overlap the kernels chunk by chunk
+			return ODE.integrate_streamed(Y0_host, wl["T"], out_host, 0.0, chunks=args.chunks)
 		ODE.set_initial_value(Y0_host, 0.0)
 		return ODE.integrate(wl["T"], out=out_host)
 
@@ -349,6 +352,7 @@ def main():
 	parser.add_argument("--trajectories", type=int, default=1 << 20, help="per GPU")
 	parser.add_argument("--storage", default=None, choices=[None, "registers", "global", "warp"])
 	parser.add_argument("--kregs", type=int, default=None)
+	parser.add_argument("--chunks", type=int, default=8, help="pieces of the host-resident ensemble in the end-to-end arm")
 	parser.add_argument("--cpu-sample-per-core", type=int, default=None)
 	parser.add_argument("--no-cpu-baseline", action="store_true")
 	args = parser.parse_args()

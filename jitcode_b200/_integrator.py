@@ -370,6 +370,88 @@ class CudaEnsembleIntegrator:
 			return out
 		return out.cpu() if self._out_kind == "torch" else out.cpu().numpy()
 
+	# ------------------------------------------------------------------ host-resident ensembles: copies overlapped with kernels
+
+	def _vector_offset(self, b0, rows):
+		"""element offset of trajectory b0 (a multiple of 32) in an array of `rows`-component vectors"""
+		return b0 * rows           # tiled: (b0/32)·rows·32; row layout: b0·rows
+
+	def integrate_streamed(self, initial_value, T, out, time=0.0, chunks=8):
+		"""
+		`set_initial_value(initial_value, time)` followed by `integrate(T, out=out)` for an ensemble that lives in
+		(pinned) host memory, with the copies hidden behind the kernels: the batch is cut into `chunks` pieces; while
+		piece c is integrated, piece c+1 is uploaded and the result of piece c-1 is downloaded on separate streams.
+		initial_value, out : (B, n) float64 CPU tensors (pinned for truly asynchronous copies).  Returns `out`.
+		"""
+		if self.post != JB_POST_NONE:
+			raise NotImplementedError("integrate_streamed does not run Lyapunov post-steps.")
+		host = initial_value
+		if not (isinstance(host, torch.Tensor) and not host.is_cuda and host.dtype == torch.float64 and host.dim() == 2 and host.shape[1] == self.n):
+			raise ValueError("integrate_streamed needs a (B, n) float64 CPU tensor.")
+		T, B, n = float(T), host.shape[0], self.n
+		if T < time:
+			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
+		if self.B != B:
+			self._alloc(B)
+		self._out_kind, self._single = "torch", False
+		self.tt.fill_(float(time))
+		self.status.zero_()
+		self._sampled = False
+		if self.sstate is not None:
+			self.sstate.zero_()
+		self._upload_parameters()
+		step = max(JB_TILE, (-(-B // max(1, chunks)) + JB_TILE - 1) // JB_TILE * JB_TILE)
+		bounds = [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
+		main = torch.cuda.current_stream(self.device)
+		if not hasattr(self, "_copy_streams"):
+			self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+		stream_in, stream_out = self._copy_streams
+		rows = torch.empty((B, n), dtype=torch.float64, device=self.device)
+		result = torch.empty((B, n), dtype=torch.float64, device=self.device)
+		stream_in.wait_stream(main)
+		stream_out.wait_stream(main)
+		self._times_host[0] = T
+		times_dev = self._times_host.to(self.device, non_blocking=True)
+		source = self.Yres if self.driver == JB_DRV_IVP_DENSE else self.Y
+		size = ctypes.sizeof(ctypes.c_double)
+		for b0, b1 in bounds:
+			with torch.cuda.stream(stream_in):
+				rows[b0:b1].copy_(host[b0:b1], non_blocking=True)
+				uploaded = stream_in.record_event()
+			main.wait_event(uploaded)
+			count, ld_chunk = b1 - b0, padded(b1 - b0)
+			offset = self._vector_offset(b0, n)
+			self.module.pack(rows[b0:b1].data_ptr(), self.Y.data_ptr() + size * offset, count, n, ld_chunk, self.stream)
+			a = self._args(times_dev, 1)
+			a.B = count
+			a.t, a.Y = self.tt.data_ptr() + size * b0, self.Y.data_ptr() + size * offset
+			a.P = self.P.data_ptr() + size * self._vector_offset(b0, max(1, self.n_params))
+			for name, tensor in (("state", self.state), ("work", self.work), ("Yres", self.Yres)):
+				if tensor is not None:
+					setattr(a, name, tensor.data_ptr() + size * offset)
+			if self.sstate is not None:
+				a.sstate = self.sstate.data_ptr() + size * b0
+			a.status = self.status.data_ptr() + 4 * b0
+			a.n_accepted, a.n_rejected = self.n_accepted.data_ptr() + 8 * b0, self.n_rejected.data_ptr() + 8 * b0
+			if self.kernel_events is not None:
+				start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+				start.record()
+				self.module.integrate(a)
+				end.record()
+				self.kernel_events.append((start, end))
+			else:
+				self.module.integrate(a)
+			self.module.unpack(source.data_ptr() + size * offset, result[b0:b1].data_ptr(), count, n, ld_chunk, self.stream)
+			integrated = main.record_event()
+			with torch.cuda.stream(stream_out):
+				stream_out.wait_event(integrated)
+				out[b0:b1].copy_(result[b0:b1], non_blocking=True)
+		stream_out.synchronize()
+		main.synchronize()
+		self.time, self._rows, self._sampled = T, result, True
+		self._check_failures()
+		return out
+
 	# ------------------------------------------------------------------ counters (the benchmark metric)
 
 	def step_counts(self):

@@ -551,6 +551,15 @@ class jitcode:
 			raise RuntimeError("You must call set_integrator first.")
 		return self.integrator.integrate_many(times)
 
+	def integrate_streamed(self, initial_value, target_time, out, time=0.0, chunks=8):
+		"""`set_initial_value` + `integrate` for an ensemble in pinned host memory, uploads and downloads overlapped with
+		the kernels (see CudaEnsembleIntegrator.integrate_streamed)."""
+		if not isinstance(self.integrator, CudaEnsembleIntegrator):
+			raise RuntimeError("You must call set_integrator first (generic kernels only).")
+		if initial_value.shape[-1] != self.n:
+			raise ValueError("The dimension of the initial value does not match the dimension of your differential equations.")
+		return self.integrator.integrate_streamed(initial_value, target_time, out, time, chunks)
+
 	def successful(self):
 		raise NotImplementedError("JiTCODE doesn’t support ODE’s `successful`. Instead the exception `UnsuccessfulIntegration` is raised in case of an unsuccessful integration (its `indices` attribute names the failing trajectories).")
 

@@ -174,3 +174,29 @@ def test_torch_cpu_round_trip_and_out_buffer():
 	ODE.set_initial_value(torch.as_tensor(Y0).pin_memory(), 0.0)
 	assert ODE.integrate(3.0, out=out) is out
 	assert_allclose(out.numpy(), result.numpy(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("case", ["lotka_volterra", "roessler", "fhn_rk45_dense"])
+def test_streamed_host_ensemble_equals_plain_calls(case):
+	"""integrate_streamed (chunked, copies overlapped with kernels) gives exactly what set_initial_value + integrate give."""
+	if case == "roessler":
+		system, (Y0, pars), T, name = W.roessler_network(100), W.roessler_ensemble(1000, seed=5), 1.5, "dopri5"
+	elif case == "lotka_volterra":
+		system, (Y0, pars), T, name = W.lotka_volterra(gamma_as_parameter=True), W.lotka_volterra_ensemble(5003, seed=5, gamma_as_parameter=True), 9.0, "dopri5"
+	else:
+		system, T, name = W.fhn(), 25.0, "RK45"
+		Y0, pars = W.FHN_Y0 + 0.01 * np.random.default_rng(1).normal(size=(777, 4)), np.empty((777, 0))
+	ODE = make(system)
+	ODE.set_integrator(name, rtol=RTOL, atol=ATOL)
+	if pars.shape[1]:
+		ODE.set_parameters(pars[:, 0])
+	ODE.set_initial_value(Y0, 0.0)
+	plain = ODE.integrate(T)
+	counts = ODE.step_counts()
+	ODE.integrator.reset_step_counts()
+	host = torch.as_tensor(Y0).pin_memory()
+	out = torch.empty_like(host).pin_memory()
+	assert ODE.integrate_streamed(host, T, out, chunks=5) is out
+	assert_allclose(out.numpy(), plain, rtol=0, atol=0)
+	assert ODE.step_counts() == counts and ODE.t == T
+	assert_allclose(ODE.y.numpy(), plain, rtol=0, atol=0)
