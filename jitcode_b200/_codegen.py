@@ -15,7 +15,6 @@ import sympy
 from sympy.core.function import AppliedUndef
 from sympy.printing.c import C99CodePrinter
 
-from ._symbolic import t as TIME
 
 JB_DP5, JB_DOP853 = 0, 1
 JB_DRV_ODE, JB_DRV_IVP_DENSE, JB_DRV_IVP_LAND = 0, 1, 2
@@ -127,10 +126,6 @@ def rhs_statements(f, helpers, control_pars, do_cse=False):
 	return lines
 
 
-def uses_time(f, helpers):
-	return any(TIME in expr.free_symbols for expr in list(f) + [d for _, d in helpers])
-
-
 def _c_array(values, per_line=16):
 	values = list(values) or ["0"]
 	return ",\n\t".join(", ".join(values[k:k+per_line]) for k in range(0, len(values), per_line))
@@ -156,10 +151,7 @@ def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, met
 	body = "\n".join("\t\t" + line for line in statements)
 	warp = storage == JB_STORE_WARP
 	tf = [repr(float(v)) for v in tables.f64] if warp else []
-	if len(tf) % 2:
-		tf.append("0.0")
 	tu = [str(int(v)) for v in tables.u] if warp else []
-	to = [str(int(v)) for v in tables.offsets] if warp else []
 	tu_type = "unsigned short" if (not tu or max(max(int(v) for v in tu), n) < 65536) else "unsigned int"
 	components = [str(int(c)) for c in (component_of if warp else range(n))]
 	n_row = (n + 2) // 2 * 2 if warp else n
@@ -168,10 +160,9 @@ def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, met
 	static __device__ __forceinline__ void rhs_warp(const double t, const VI &y, VO &dy, const Par &par, const int lane, const void *jb_tables)
 	{{
 		const double *const JB_TF = static_cast<const double *>(jb_tables);
-		const unsigned *const JB_TO = reinterpret_cast<const unsigned *>(JB_TF + TF_COUNT);
-		const TU *const JB_TU = reinterpret_cast<const TU *>(JB_TO + TO_COUNT);
+		const TU *const JB_TU = reinterpret_cast<const TU *>(JB_TF + TF_COUNT);
 {body}
-		(void) t; (void) par; (void) JB_TF; (void) JB_TO; (void) JB_TU;
+		(void) t; (void) par; (void) JB_TF; (void) JB_TU;
 	}}"""
 	else:
 		function = f"""	template <class VI, class VO>
@@ -189,9 +180,6 @@ namespace jb_generated {{
 __device__ const double jb_tf[{max(1, len(tf))}] = {{
 	{_c_array(tf, 8)}
 }};
-__device__ const unsigned jb_to[{max(1, len(to))}] = {{
-	{_c_array(to, 16)}
-}};
 __device__ const {tu_type} jb_tu[{max(1, len(tu))}] = {{
 	{_c_array(tu, 24)}
 }};
@@ -206,12 +194,12 @@ struct Sys {{
 	static constexpr int NB = {n_basic};     // dimension of the underlying system
 	static constexpr int NL = {n_lyap};     // tangent vectors
 	static constexpr int NT = {len(tangent_indices)};     // transversal tangent coordinates
-	static constexpr int TF_COUNT = {len(tf)}, TO_COUNT = {len(to)}, TU_COUNT = {len(tu)};   // TF padded: offsets stay 16-byte aligned
+	static constexpr int TF_COUNT = {len(tf)}, TU_COUNT = {len(tu)};
 	static constexpr int NROW = {n_row};   // shared-memory row length (warp storage): position N holds 0
 	typedef {tu_type} TU;
 	static __device__ __forceinline__ const TU *components(const void *tables)
 	{{
-		return reinterpret_cast<const TU *>(reinterpret_cast<const unsigned *>(static_cast<const double *>(tables) + TF_COUNT) + TO_COUNT) + TU_COUNT;
+		return reinterpret_cast<const TU *>(static_cast<const double *>(tables) + TF_COUNT) + TU_COUNT;
 	}}
 	struct Par {{ double v[NP > 0 ? NP : 1]; }};
 {tangent}

@@ -324,7 +324,6 @@ class Tables:
 	"""two flat tables (doubles, unsigned integers) that the kernel stages in shared memory."""
 	def __init__(self):
 		self.f64, self.u = [], []
-		self.offsets = []      # byte offsets (32 bit) into a shared-memory vector, read four at a time
 
 	def add_f64(self, values):
 		offset = len(self.f64)
@@ -338,19 +337,13 @@ class Tables:
 		self.u.extend(int(v) for v in values)
 		return offset
 
-	def add_offsets(self, positions):
-		assert len(self.offsets) % 4 == 0 and len(positions) % 4 == 0
-		offset = len(self.offsets)
-		self.offsets.extend(8 * int(p) for p in positions)
-		return offset
-
 	@property
 	def wide(self):
 		return bool(self.u) and max(self.u) >= 65536
 
 	@property
 	def nbytes(self):
-		return 8 * len(self.f64) + 4 * len(self.offsets) + ((4 if self.wide else 2) * len(self.u) + 7) // 8 * 8 + 16
+		return 8 * len(self.f64) + ((4 if self.wide else 2) * len(self.u) + 7) // 8 * 8 + 16
 
 
 def _uniform(values):

@@ -8,8 +8,8 @@
 //   JB_MODULE_THREADS          threads per block of the integrate kernel
 //   JB_MODULE_KREGS            warp storage: how many stage rows (plus the state) are cached in registers
 // and, for JB_STORE_WARP, the tables of the vectorised right-hand side: jb_generated::jb_tf (doubles),
-// jb_generated::jb_to (32-bit byte offsets), jb_generated::jb_tu (unsigned indices of type Sys::TU),
-// jb_generated::jb_component, Sys::TF_COUNT, Sys::TO_COUNT, Sys::TU_COUNT.
+// jb_generated::jb_tu (unsigned indices / 16-bit byte offsets of type Sys::TU), jb_generated::jb_component,
+// Sys::TF_COUNT, Sys::TU_COUNT.
 // It replaces the module table and entry points of the reference's jitced_template.c:213-240.
 #pragma once
 
@@ -34,7 +34,7 @@ template <class S, bool W> struct WarpShared {
 	static constexpr size_t BYTES = 0, EVAL_BYTES = 0;
 };
 template <class S> struct WarpShared<S, true> {
-	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) ((S::TO_COUNT * sizeof(unsigned) + (S::TU_COUNT + S::N) * sizeof(typename S::TU) + 15) / 16) * 2;
+	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) (((S::TU_COUNT + S::N) * sizeof(typename S::TU) + 15) / 16) * 2;
 	static constexpr int ROWS = WarpStore<S, Tab, JB_MODULE_DRIVER, JB_MODULE_KREGS>::ROWS;
 	static constexpr int WARPS = JB_MODULE_THREADS / 32;
 	static constexpr size_t BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * ROWS * S::NROW);
@@ -46,9 +46,7 @@ template <class S>
 __device__ __forceinline__ void stage_tables(double *smem)
 {
 	for (int i = threadIdx.x; i < S::TF_COUNT; i += blockDim.x) smem[i] = jb_generated::jb_tf[i];
-	unsigned *to = reinterpret_cast<unsigned *>(smem + S::TF_COUNT);
-	for (int i = threadIdx.x; i < S::TO_COUNT; i += blockDim.x) to[i] = jb_generated::jb_to[i];
-	typename S::TU *tu = reinterpret_cast<typename S::TU *>(to + S::TO_COUNT);
+	typename S::TU *tu = reinterpret_cast<typename S::TU *>(smem + S::TF_COUNT);
 	for (int i = threadIdx.x; i < S::TU_COUNT; i += blockDim.x) tu[i] = jb_generated::jb_tu[i];
 	for (int i = threadIdx.x; i < S::N; i += blockDim.x) tu[S::TU_COUNT + i] = jb_generated::jb_component[i];
 	__syncthreads();
