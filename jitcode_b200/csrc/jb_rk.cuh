@@ -663,7 +663,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 							: pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
 					h = fmin(fmin(100.0 * fabs(h), h1), hmax);
 				}
-				double facold = 1e-4;
+				double log_facold = -9.210340371976182;      // facold = 1e-4
 				bool reject = false, last = false;
 				int64_t nstep = 0;
 				const int64_t nmax = a.nsteps > 0 ? a.nsteps : 100000;
@@ -674,12 +674,13 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					if (t + 1.01 * h - T > 0.0) { h = T - t; last = true; }
 					++nstep;
 					const double err = st.attempt(t, h);
-					const double fac11 = pow(err, a.expo1);
-					double fac = a.beta > 0.0 ? fac11 / pow(facold, a.beta) : fac11;
-					fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
-					double hnew = h / fac;
+					// fac11 = err^expo1 and facold^beta through one logarithm per attempt (facold is the previous error)
+					const double log_err = log(err);
 					if (err <= 1.0) {
-						facold = fmax(err, 1e-4);
+						double fac = exp(a.expo1 * log_err - a.beta * log_facold);
+						fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
+						double hnew = h / fac;
+						log_facold = fmax(log_err, -9.210340371976182);     // facold = max(err, 1e-4)
 						++n_acc;
 						st.finish_accepted(t, h);
 						st.accept_y();
@@ -689,16 +690,16 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 						if (reject) hnew = fmin(fabs(hnew), fabs(h));
 						reject = false;
 						if (last) break;
+						h = hnew;
 					} else {
 						if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
-							hnew = h / fmin(a.facc1, fac11 / a.safety);
+							h = h / fmin(a.facc1, exp(a.expo1 * log_err) / a.safety);
 						else
-							hnew = h / a.facc1;
+							h = h / a.facc1;
 						reject = true;
 						last = false;
 						++n_rej;
 					}
-					h = hnew;
 				}
 			}
 		} else {
@@ -754,7 +755,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					h_abs = fabs(h);
 					const double err = st.attempt(t, h);
 					if (err < 1.0) {
-						double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(err, -1.0 / (Tab::ERR_ORDER + 1)));
+						double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * exp(log(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
 						if (rejected) factor = fmin(1.0, factor);
 						h_abs *= factor;
 						++n_acc;
@@ -768,7 +769,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 						interpolant = false;
 						break;
 					}
-					h_abs *= fmax(0.2, 0.9 * pow(err, -1.0 / (Tab::ERR_ORDER + 1)));
+					h_abs *= fmax(0.2, 0.9 * exp(log(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
 					rejected = true;
 					++n_rej;
 				}
