@@ -131,7 +131,7 @@ def _c_array(values, per_line=16):
 	return ",\n\t".join(", ".join(values[k:k+per_line]) for k in range(0, len(values), per_line))
 
 
-def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None, component_of=None, kregs=0):
+def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None, component_of=None, kregs=0, min_blocks=1):
 	"""the complete translation unit of one module (what _render_template produces from
 	jitced_template.c in the reference, _jitcode.py:397-406).
 
@@ -213,5 +213,6 @@ struct Sys {{
 #define JB_MODULE_STORAGE {STORAGE_NAMES[storage]}
 #define JB_MODULE_THREADS {int(threads)}
 #define JB_MODULE_KREGS {int(kregs)}
+#define JB_MODULE_MIN_BLOCKS {int(min_blocks)}
 #include "jb_module.cuh"
 """

@@ -7,6 +7,7 @@
 //   JB_MODULE_STORAGE          JB_STORE_REGISTERS | JB_STORE_GLOBAL | JB_STORE_WARP
 //   JB_MODULE_THREADS          threads per block of the integrate kernel
 //   JB_MODULE_KREGS            warp storage: how many stage rows (plus the state) are cached in registers
+//   JB_MODULE_MIN_BLOCKS       resident blocks per SM the integrate kernel is compiled for (caps its registers)
 // and, for JB_STORE_WARP, the tables of the vectorised right-hand side: jb_generated::jb_tf (doubles),
 // jb_generated::jb_tu (unsigned indices / 16-bit byte offsets of type Sys::TU), jb_generated::jb_component,
 // Sys::TF_COUNT, Sys::TU_COUNT.
@@ -53,7 +54,7 @@ __device__ __forceinline__ void stage_tables(double *smem)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(JB_MODULE_THREADS)
+__global__ void __launch_bounds__(JB_MODULE_THREADS, JB_MODULE_MIN_BLOCKS)
 jb_integrate_kernel(const __grid_constant__ Params a)
 {
 	if constexpr (MODE == JB_STORE_WARP) {
