@@ -58,6 +58,12 @@ def workload(name, B, seed_offset=0):
 		Y0, pars = W.lotka_volterra_ensemble(B, seed=42 + seed_offset)
 		return {"system": system, "Y0": Y0, "pars": pars, "T": 100.0, "integrator": "dopri5",
 				"label": "Lotka-Volterra ensemble (n=2), random initial conditions"}
+	if name == "fhn_lyap":
+		# config 4: FitzHugh–Nagumo pair with all 4 Lyapunov exponents (n = 20), re-orthonormalised every Δt = 10
+		system = dict(W.fhn(), lyap=4)
+		return {"system": system, "Y0": W.fhn_lyap_ensemble(B, seed=42 + seed_offset), "pars": np.empty((B, 0)), "T": 200.0,
+				"times": [10.0 * (i + 1) for i in range(20)], "integrator": "dopri5",
+				"label": "double_fhn_lyapunov: FHN pair + 4 tangent vectors (n=20), QR every dt=10, 20 calls"}
 	if name == "kuramoto":
 		# config 5: 1000 oscillators, dense adjacency; the symbolic form has 2·10^5 sine terms (SymPy needs minutes to
 		# build it), so the system enters through its data — same kernels as the recognised symbolic form
@@ -77,6 +83,9 @@ def cpu_reference_handle(system, label):
 	else the oracle's port of it."""
 	from oracle import build_ref, c_rhs
 	handle = None
+	if system.get("lyap"):
+		full, helpers = c_rhs.lyapunov_system(system["f_sym"], system["lyap"], system["helpers"], system["n"])
+		system = {"f_sym": full, "helpers": helpers, "control_pars": [], "n": len(full)}
 	try:
 		handle = build_ref.build_ref_rhs(system["f_sym"], system["helpers"], system["control_pars"], system["n"])
 		if handle is not None:
@@ -90,7 +99,15 @@ def cpu_reference_handle(system, label):
 def cpu_run(wl, handle, n_sample):
 	from oracle import ensemble
 	Y0, pars = wl["Y0"][:n_sample], wl["pars"][:n_sample]
-	result = ensemble.run_ensemble(handle, wl["integrator"], Y0, [wl["T"]], pars=pars, rtol=RTOL, atol=ATOL)
+	lyap = None
+	if wl["system"].get("lyap"):
+		# jitcode_lyap: random unit tangent vectors appended to the state, QR after every call (_jitcode.py:723-775)
+		k, n = wl["system"]["lyap"], wl["system"]["n"]
+		tangents = np.random.default_rng(1).normal(size=(len(Y0), k, n))
+		tangents /= np.linalg.norm(tangents, axis=2, keepdims=True)
+		Y0 = np.hstack([Y0, tangents.reshape(len(Y0), k * n)])
+		lyap = (n, k)
+	result = ensemble.run_ensemble(handle, wl["integrator"], Y0, wl.get("times", [wl["T"]]), pars=pars, lyap=lyap, rtol=RTOL, atol=ATOL)
 	return result["attempts"], result["seconds"], result["cores"]
 
 
@@ -209,7 +226,13 @@ def run_ours(args):
 	system = wl["system"]
 	n = system["n"]
 	dense = "sine_coupling" in system
-	if dense:
+	lyap = system.get("lyap")
+	if lyap:
+		from jitcode_b200 import jitcode_lyap
+		ODE = jitcode_lyap(system["f_sym"], n_lyap=lyap, verbose=False, seed=1)
+		ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=ATOL)
+		n = ODE.n
+	elif dense:
 		ODE = jitcode.from_sine_coupling(*system["sine_coupling"])
 		ODE.set_integrator(wl["integrator"], rtol=RTOL, atol=1e-9)
 	else:
@@ -233,9 +256,15 @@ def run_ours(args):
 		if pars_dev is not None:
 			ODE.set_parameters(pars_dev)
 		ODE.set_initial_value(Y0_dev, 0.0)
+		if lyap:
+			return ODE.integrate_many(wl["times"])       # the 20 calls of the example's loop as one launch
 		return ODE.integrate(wl["T"])
 
 	def host_step():
+		if lyap:
+			ODE.set_initial_value(Y0_host, 0.0)
+			states, exponents = ODE.integrate_many(wl["times"])
+			return exponents
 		if pars_host is not None:
 			ODE.set_parameters(pars_host)
 		if hasattr(integrator, "integrate_streamed") and B >= 65536:
@@ -307,6 +336,8 @@ def run_ours(args):
 		import sympy
 		from jitcode_b200 import _peaks
 		rhs_flops = float(sum(sympy.count_ops(entry) for entry in ODE._f_list)) if not dense else 4.0 * n * n
+		if lyap:
+			line_extra = {"d2h_bytes_per_step": int(len(wl["times"]) * B * (system["n"] + lyap) * 8)}
 		flops_per_step = 72.0 * n + 6.0 * rhs_flops
 		fp64_peak = _peaks.fp64_fma_tflops(device)
 		fp64_achieved = flops_per_step * own_attempts / kernel_s / 1e12
@@ -330,6 +361,8 @@ def run_ours(args):
 					"fp64": {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
 							"flops_per_trajectory_step": flops_per_step, "peak_source": "DFMA microbenchmark measured in this run (jitcode_b200/_peaks.py)"}},
 		}
+		if lyap:
+			line["e2e"]["d2h_bytes_per_step"] = line_extra["d2h_bytes_per_step"]
 		if dense:
 			# the contraction is the kernel: FP64 tensor cores against the measured FP64 peak
 			line["roofline"].update({"bound": "tensor", "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
@@ -348,7 +381,7 @@ def main():
 	parser.add_argument("--steps", type=int, default=5)
 	parser.add_argument("--warmup", type=int, default=3)
 	parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
-	parser.add_argument("--workload", default="roessler", choices=["roessler", "lv", "kuramoto"])
+	parser.add_argument("--workload", default="roessler", choices=["roessler", "lv", "fhn_lyap", "kuramoto"])
 	parser.add_argument("--trajectories", type=int, default=1 << 20, help="per GPU")
 	parser.add_argument("--storage", default=None, choices=[None, "registers", "global", "warp"])
 	parser.add_argument("--kregs", type=int, default=None)
@@ -358,9 +391,11 @@ def main():
 	args = parser.parse_args()
 	if args.workload == "kuramoto" and args.trajectories == 1 << 20:
 		args.trajectories = 4096
+	if args.workload == "fhn_lyap" and args.trajectories == 1 << 20:
+		args.trajectories = 100_000
 	args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 	if args.cpu_sample_per_core is None:
-		args.cpu_sample_per_core = 2048 if args.workload == "roessler" else 16384
+		args.cpu_sample_per_core = {"roessler": 2048, "lv": 16384, "fhn_lyap": 4096}.get(args.workload, 256)
 	if args.impl == "reference":
 		run_reference(args)
 	else:
