@@ -150,8 +150,8 @@ int64_t jb_launch_count(void);
  *     dy_i/dt = omega_i + sum_j W_ij sin(y_j - y_i)
  * — what the reference writes out as n*deg sine terms (examples/kuramoto_network.py:19-26) — as one FP64
  * tensor-core GEMM per right-hand-side evaluation for the whole ensemble.  Replaces, for such systems, the same
- * reference entry points as jb_eval_f / jb_integrate with driver JB_DRV_ODE ("dopri5", ODE_wrapper.integrate,
- * integrator_tools.py:134-144).  Layout: plain structure of arrays, X[i*ld + b], ld a multiple of 64.
+ * reference entry points as jb_eval_f / jb_integrate with driver JB_DRV_ODE ("dopri5" / "dop853",
+ * ODE_wrapper.integrate, integrator_tools.py:134-144).  Layout: plain structure of arrays, X[i*ld + b], ld a multiple of 64.
  */
 typedef struct jb_dense_args {
 	uint32_t struct_size;      /* sizeof(jb_dense_args), checked */
@@ -172,7 +172,7 @@ typedef struct jb_dense_args {
 	int32_t *scratch;          /* [ld/32 + 2] device scratch */
 	int32_t *host_flag;        /* one int32 in (pinned) host memory: the host polls the number of unfinished trajectories */
 	int32_t  rounds_per_check; /* lock-step rounds between two polls; 0 = default */
-	int32_t  reserved;
+	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1) */
 	int64_t *rounds_out;       /* host: number of lock-step rounds of this call, or NULL */
 	void    *stream;
 } jb_dense_args;

@@ -71,7 +71,7 @@ class DenseArgs(ctypes.Structure):
 		("t", ctypes.c_void_p), ("Y", ctypes.c_void_p), ("work", ctypes.c_void_p), ("ctrl", ctypes.c_void_p),
 		("status", ctypes.c_void_p), ("n_accepted", ctypes.c_void_p), ("n_rejected", ctypes.c_void_p),
 		("scratch", ctypes.c_void_p), ("host_flag", ctypes.c_void_p),
-		("rounds_per_check", ctypes.c_int32), ("reserved", ctypes.c_int32),
+		("rounds_per_check", ctypes.c_int32), ("method_flags", ctypes.c_int32),
 		("rounds_out", ctypes.c_void_p),
 		("stream", ctypes.c_void_p),
 	]
@@ -125,10 +125,10 @@ class DenseModule:
 
 
 class CudaDenseSineIntegrator:
-	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5")."""
+	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5") or DOP853 ("dop853")."""
 
-	def __init__(self, W, omega, *, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
-			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, rounds_per_check=4):
+	def __init__(self, W, omega, *, method=0, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
+			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=4):
 		self.device = require_cuda(device)
 		self.n = len(omega)
 		self.module = DenseModule(self.n)
@@ -143,6 +143,7 @@ class CudaDenseSineIntegrator:
 		self.nsteps = int(nsteps)
 		self.controller = (float(safety), float(ifactor), float(dfactor), float(beta))
 		self.rounds_per_check = int(rounds_per_check)
+		self.method_flags = int(method) | (256 if verbatim_dop853_reject else 0)
 		self.B = None
 		self.time = None
 		self._rows = None
@@ -183,6 +184,7 @@ class CudaDenseSineIntegrator:
 		a.status, a.n_accepted, a.n_rejected = self.status.data_ptr(), self.n_accepted.data_ptr(), self.n_rejected.data_ptr()
 		a.scratch, a.host_flag = self.scratch.data_ptr(), self.host_flag.data_ptr()
 		a.rounds_per_check = self.rounds_per_check
+		a.method_flags = self.method_flags
 		a.rounds_out = self.rounds_host.ctypes.data
 		a.stream = self.stream
 		return a

@@ -143,7 +143,7 @@ class jitcode:
 		The system  dy_i/dt = omega[i] + Σ_j W[i, j]·sin(y_j − y_i)  given by its data instead of by n·deg symbolic
 		sine terms (which SymPy needs minutes to build for a dense network of 1000 oscillators).  Equivalent to
 		`jitcode(f_sym)` with that f_sym — the symbolic input is recognised and ends up in the same kernels — and
-		only available with `set_integrator("dopri5")`.
+		only available with `set_integrator("dopri5")` and `set_integrator("dop853")`.
 		"""
 		W, omega = np.asarray(W, dtype=float), np.asarray(omega, dtype=float)
 		if W.shape != (len(omega), len(omega)):
@@ -508,15 +508,15 @@ class jitcode:
 		if isinstance(storage, str):
 			storage = STORAGE_BY_NAME[storage]
 		old_integrator = self.integrator
-		dense = storage == "dense" or (storage is None and name == "dopri5" and self.n >= DENSE_MINIMUM_N and self._dense_coupling() is not None)
+		dense = storage == "dense" or (storage is None and backend == "ode" and self.n >= DENSE_MINIMUM_N and self._dense_coupling() is not None)
 		if dense:
-			if name != "dopri5" or self._dense_coupling() is None:
-				raise NotImplementedError("The dense engine integrates sine-coupled phase oscillators with \"dopri5\" only.")
+			if backend != "ode" or self._dense_coupling() is None:
+				raise NotImplementedError("The dense engine integrates sine-coupled phase oscillators with \"dopri5\" or \"dop853\" only.")
 			_dense.dense_library()                                       # compiling needs no GPU …
 			require_cuda(device)                                         # … running does
 			integrator_params.pop("verbosity", None)
 			self._integrator_config = None
-			self.integrator = _dense.CudaDenseSineIntegrator(*self._dense_coupling(), device=device, nsteps=nsteps, **integrator_params)
+			self.integrator = _dense.CudaDenseSineIntegrator(*self._dense_coupling(), method=method, device=device, nsteps=nsteps, **integrator_params)
 			self._restore_state(old_integrator)
 			return
 		module = self._module(method, driver, storage, threads, kregs, min_blocks)   # compiling needs no GPU …

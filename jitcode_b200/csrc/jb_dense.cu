@@ -29,6 +29,7 @@
 namespace jbd {
 
 using jb::DP5;
+using jb::DOP853;
 using jb::Idx;
 using jb::static_for;
 
@@ -131,10 +132,19 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
 // ---------------------------------------------------------------------------------------------
 // per-trajectory control block (structure of arrays, ctrl[k*ld + b])
 
-enum { C_H = 0, C_HMAX, C_FACOLD, C_ERR2, C_DNF, C_DNY, C_DER2, C_FLAGS, C_NSTEP, C_COUNT };
+enum { C_H = 0, C_HMAX, C_FACOLD, C_ERR2, C_DNF, C_DNY, C_DER2, C_FLAGS, C_NSTEP, C_ERR3, C_COUNT };
 enum { F_ACTIVE = 1, F_LAST = 2, F_REJECT = 4, F_ACCEPTED = 8 };      // C_FLAGS (stored as a double holding a small int)
 // work vectors, work[k*n*ld + i*ld + b]
-enum { W_Z = 0, W_K0 = 1 /* … W_K0+6 */, W_XS = 8 /* sin | cos: 2 vectors */, W_G = 10 /* G_s | G_c: 2 vectors */, W_COUNT = 12 };
+enum { W_Z = 0, W_K0 = 1 /* … W_K0+12 */, W_XS = 14 /* sin | cos: 2 vectors */, W_G = 16 /* G_s | G_c: 2 vectors */, W_COUNT = 18 };
+
+// coefficient access as constant expressions (both pairs; jb_tableaux.cuh)
+template <class Tab> struct Coef;
+template <> struct Coef<DP5> {
+	static __host__ __device__ constexpr double a(int s, int j) { return DP5::A[s][j]; }
+};
+template <> struct Coef<DOP853> {
+	static __host__ __device__ constexpr double a(int s, int j) { return jb::dop853::A[s][j]; }
+};
 
 struct Dense {
 	int64_t B, ld;
@@ -143,6 +153,7 @@ struct Dense {
 	double T, rtol, atol, max_step, first_step;
 	int64_t nmax;
 	double safety, facc1, facc2, beta, expo1;
+	int reject_by_dfactor;      // dop853: shrink by exactly dfactor on a rejection, like SciPy 1.18.1's compiled code
 	double *t, *Y, *work, *ctrl;
 	int32_t *status;
 	int64_t *n_accepted, *n_rejected;
@@ -289,12 +300,13 @@ __global__ void __launch_bounds__(256) setup_kernel(const Dense d)
 		d.ctrl[C_HMAX * d.ld + b] = d.max_step > 0.0 ? d.max_step : fabs(d.T - d.t[b]);
 		d.ctrl[C_FACOLD * d.ld + b] = 1e-4;
 		d.ctrl[C_NSTEP * d.ld + b] = 0.0;
-		d.ctrl[C_DNF * d.ld + b] = d.ctrl[C_DNY * d.ld + b] = d.ctrl[C_DER2 * d.ld + b] = d.ctrl[C_ERR2 * d.ld + b] = 0.0;
+		d.ctrl[C_DNF * d.ld + b] = d.ctrl[C_DNY * d.ld + b] = d.ctrl[C_DER2 * d.ld + b] = d.ctrl[C_ERR2 * d.ld + b] = d.ctrl[C_ERR3 * d.ld + b] = 0.0;
 	}
 	publish_activity(d, b, active);
 }
 
 // HINIT's result (or first_step) and the first pass through the top of the step loop
+template <class Tab>
 __global__ void __launch_bounds__(256) first_step_kernel(const Dense d, int have_probe)
 {
 	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(256) first_step_kernel(const Dense d, int have
 				h0 = fmin(h0, hmax);
 				const double der2 = sqrt(d.ctrl[C_DER2 * d.ld + b]) / h0;
 				const double der12 = fmax(fabs(der2), sqrt(dnf));
-				const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h0) * 1e-3) : pow(0.01 / der12, 1.0 / DP5::HAIRER_ORDER);
+				const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h0) * 1e-3) : pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
 				h = fmin(fmin(100.0 * fabs(h0), h1), hmax);
 			}
 			double nstep = 0.0;
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(256) first_step_kernel(const Dense d, int have
 			d.ctrl[C_H * d.ld + b] = h;
 			d.ctrl[C_NSTEP * d.ld + b] = nstep;
 			d.ctrl[C_FLAGS * d.ld + b] = flags;
-			d.ctrl[C_ERR2 * d.ld + b] = 0.0;
+			d.ctrl[C_ERR2 * d.ld + b] = d.ctrl[C_ERR3 * d.ld + b] = 0.0;
 			active = flags & F_ACTIVE;
 		}
 	}
@@ -328,19 +340,24 @@ __global__ void __launch_bounds__(256) first_step_kernel(const Dense d, int have
 }
 
 // stage ROW of an attempt: (ROW > 1: K[ROW-1] = f from the last GEMM;)  Z = Y + h Σ_j a(ROW, j) K[j];  XS = sincos(Z)
-// ROW == 1 also applies the outcome of the previous round: accepted trajectories take Y ← Z, K[0] ← K[6].
-template <int ROW>
+// ROW == 1 also applies the outcome of the previous round: accepted trajectories take Y ← Z, K[0] ← K[S].
+// ROW == S of the 8th-order pair (whose error estimate does not need f(t+h, y_new)) also sums the error terms.
+template <class Tab, int ROW>
 __global__ void __launch_bounds__(256) stage_kernel(const Dense d)
 {
+	constexpr int S = Tab::NSTAGE;
+	constexpr bool SUMS_ERROR = !Tab::ERR_NEEDS_FSAL && ROW == S;
+	const int64_t bb = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	double s5 = 0.0, s3 = 0.0;
 	for_rows(d, [&](int i, int64_t b, int64_t at) {
 		const int flags = flags_of(d, b);
-		double k[7];
+		double k[S + 1];
 		double y = d.Y[at];
 		if constexpr (ROW == 1) {
 			if (flags & F_ACCEPTED) {
 				y = vec(d, W_Z)[at];
 				d.Y[at] = y;
-				k[0] = vec(d, W_K0 + 6)[at];
+				k[0] = vec(d, W_K0 + S)[at];
 				vec(d, W_K0)[at] = k[0];
 			} else {
 				k[0] = vec(d, W_K0)[at];
@@ -349,47 +366,71 @@ __global__ void __launch_bounds__(256) stage_kernel(const Dense d)
 		} else {
 			if (!(flags & F_ACTIVE)) return;
 			static_for<0, ROW - 1>([&](auto j) {
-				constexpr double a = DP5::A[ROW][j];
-				if constexpr (a != 0.0) k[j] = vec(d, W_K0 + j)[at];
+				constexpr double a = Coef<Tab>::a(ROW, j);
+				constexpr bool in_error = SUMS_ERROR && (jb::dop853::E5[j] != 0.0 || jb::dop853::E3[j] != 0.0);
+				if constexpr (a != 0.0 || in_error) k[j] = vec(d, W_K0 + j)[at];
 			});
 			k[ROW - 1] = finish_rhs<ROW - 1>(d, i, b, at);
 		}
 		const double h = d.ctrl[C_H * d.ld + b];
 		double acc = 0.0;
 		static_for<0, ROW>([&](auto j) {
-			constexpr double a = DP5::A[ROW][j];
+			constexpr double a = Coef<Tab>::a(ROW, j);
 			if constexpr (a != 0.0) acc = fma(a, k[j], acc);
 		});
 		const double z = fma(h, acc, y);
 		vec(d, W_Z)[at] = z;
 		sincos(z, &xs_sin(d, i, b), &xs_cos(d, i, b));
+		if constexpr (SUMS_ERROR) {
+			double e5 = 0.0, e3 = 0.0;
+			static_for<0, S>([&](auto j) {
+				constexpr double w5 = jb::dop853::E5[j], w3 = jb::dop853::E3[j];
+				if constexpr (w5 != 0.0) e5 = fma(w5, k[j], e5);
+				if constexpr (w3 != 0.0) e3 = fma(w3, k[j], e3);
+			});
+			const double sk = fma(d.rtol, fmax(fabs(y), fabs(z)), d.atol);
+			e5 /= sk;
+			e3 /= sk;
+			s5 = fma(e5, e5, s5);
+			s3 = fma(e3, e3, s3);
+		}
 	});
+	if constexpr (SUMS_ERROR) {
+		const bool active = bb < d.B && (flags_of(d, bb) & F_ACTIVE);
+		reduce_to(d.ctrl + C_ERR2 * d.ld, bb, active, s5);
+		reduce_to(d.ctrl + C_ERR3 * d.ld, bb, active, s3);
+	}
 }
 
-// after the GEMM of f(t+h, y_new): K[6] = f; error sum Σ (h Σ_j E_j K_j / sk)²
+// after the GEMM of f(t+h, y_new): K[S] = f; for the 5th-order pair also the error sum Σ (h Σ_j E_j K_j / sk)²
+template <class Tab>
 __global__ void __launch_bounds__(256) error_kernel(const Dense d)
 {
+	constexpr int S = Tab::NSTAGE;
 	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
 	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
 	double sum = 0.0;
 	if (active) {
 		const double h = d.ctrl[C_H * d.ld + b];
 		for_rows(d, [&](int i, int64_t, int64_t at) {
-			const double k6 = finish_rhs<6>(d, i, b, at);
-			double e = DP5::E[6] * k6;
-			static_for<0, 6>([&](auto j) {
-				constexpr double w = DP5::E[j];
-				if constexpr (w != 0.0) e = fma(w, vec(d, W_K0 + j)[at], e);
-			});
-			const double sk = fma(d.rtol, fmax(fabs(d.Y[at]), fabs(vec(d, W_Z)[at])), d.atol);
-			const double q = h * e / sk;
-			sum = fma(q, q, sum);
+			const double last = finish_rhs<S>(d, i, b, at);
+			if constexpr (Tab::ERR_NEEDS_FSAL) {
+				double e = DP5::E[S] * last;
+				static_for<0, S>([&](auto j) {
+					constexpr double w = DP5::E[j];
+					if constexpr (w != 0.0) e = fma(w, vec(d, W_K0 + j)[at], e);
+				});
+				const double sk = fma(d.rtol, fmax(fabs(d.Y[at]), fabs(vec(d, W_Z)[at])), d.atol);
+				const double q = h * e / sk;
+				sum = fma(q, q, sum);
+			}
 		});
 	}
-	reduce_to(d.ctrl + C_ERR2 * d.ld, b, active, sum);
+	if constexpr (Tab::ERR_NEEDS_FSAL) reduce_to(d.ctrl + C_ERR2 * d.ld, b, active, sum);
 }
 
 // one thread per trajectory: accept or reject, new step size, and the top of the next pass of the step loop
+template <class Tab>
 __global__ void __launch_bounds__(256) control_kernel(const Dense d)
 {
 	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,7 +442,15 @@ __global__ void __launch_bounds__(256) control_kernel(const Dense d)
 			double t = d.t[b], h = d.ctrl[C_H * d.ld + b], facold = d.ctrl[C_FACOLD * d.ld + b];
 			const double hmax = d.ctrl[C_HMAX * d.ld + b];
 			double nstep = d.ctrl[C_NSTEP * d.ld + b];
-			const double err = sqrt(d.ctrl[C_ERR2 * d.ld + b] / d.n);
+			double err;
+			if constexpr (Tab::ERR_NEEDS_FSAL) {
+				err = sqrt(d.ctrl[C_ERR2 * d.ld + b] / d.n);
+			} else {
+				const double s5 = d.ctrl[C_ERR2 * d.ld + b], s3 = d.ctrl[C_ERR3 * d.ld + b];
+				double deno = fma(0.01, s3, s5);
+				if (deno <= 0.0) deno = 1.0;
+				err = (s5 == 0.0 && s3 == 0.0) ? 0.0 : fabs(h) * s5 * sqrt(1.0 / (deno * d.n));
+			}
 			const double fac11 = pow(err, d.expo1);
 			double fac = d.beta > 0.0 ? fac11 / pow(facold, d.beta) : fac11;
 			fac = fmax(d.facc2, fmin(d.facc1, fac / d.safety));
@@ -416,7 +465,7 @@ __global__ void __launch_bounds__(256) control_kernel(const Dense d)
 				flags &= ~F_REJECT;
 				if (flags & F_LAST) flags &= ~F_ACTIVE;
 			} else {
-				hnew = h / fmin(d.facc1, fac11 / d.safety);
+				hnew = (Tab::ERR_NEEDS_FSAL || !d.reject_by_dfactor) ? h / fmin(d.facc1, fac11 / d.safety) : h / d.facc1;
 				flags |= F_REJECT;
 				flags &= ~F_LAST;
 				d.n_rejected[b] += 1;
@@ -427,7 +476,7 @@ __global__ void __launch_bounds__(256) control_kernel(const Dense d)
 			d.ctrl[C_H * d.ld + b] = h;
 			d.ctrl[C_FACOLD * d.ld + b] = facold;
 			d.ctrl[C_NSTEP * d.ld + b] = nstep;
-			d.ctrl[C_ERR2 * d.ld + b] = 0.0;
+			d.ctrl[C_ERR2 * d.ld + b] = d.ctrl[C_ERR3 * d.ld + b] = 0.0;
 			active = flags & F_ACTIVE;
 		}
 		d.ctrl[C_FLAGS * d.ld + b] = flags;
@@ -537,8 +586,23 @@ int jb_dense_eval_f(const jb_dense_args *x, double *dY)
 	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_eval_f");
 }
 
-// advance every trajectory to x->T (Hairer's DOPRI5, fresh start, lands exactly on T)
-int jb_dense_integrate(const jb_dense_args *x)
+}  // extern "C"
+
+namespace jbd {
+
+template <class Tab, int ROW = 1>
+static void launch_stages(const Dense &d, dim3 egrid, dim3 eblock, cudaStream_t stream)
+{
+	if constexpr (ROW <= Tab::NSTAGE) {
+		JBD_LAUNCH((stage_kernel<Tab, ROW>), egrid, eblock, d);
+		gemm(d, stream);
+		launch_stages<Tab, ROW + 1>(d, egrid, eblock, stream);
+	}
+}
+
+// advance every trajectory to x->T (Hairer's DOPRI5 / DOP853, fresh start, lands exactly on T)
+template <class Tab>
+static int integrate(const jb_dense_args *x)
 {
 	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_integrate: argument block has the wrong size");
 	if (x->B <= 0) return 0;
@@ -550,10 +614,18 @@ int jb_dense_integrate(const jb_dense_args *x)
 	d.T = x->T; d.rtol = x->rtol; d.atol = x->atol; d.max_step = x->max_step; d.first_step = x->first_step;
 	d.nmax = x->nsteps > 0 ? x->nsteps : 100000;
 	d.safety = x->safety > 0.0 ? x->safety : 0.9;
-	d.facc1 = 1.0 / (x->dfactor > 0.0 ? x->dfactor : 0.2);
-	d.facc2 = 1.0 / (x->ifactor > 0.0 ? x->ifactor : 10.0);
-	d.beta = x->beta == 0.0 ? 0.04 : (x->beta < 0.0 ? 0.0 : x->beta);
-	d.expo1 = 0.2 - d.beta * 0.75;
+	// scipy.integrate.ode's defaults for the two codes (scipy _ode.py:1112-1236)
+	constexpr bool dp5 = Tab::ERR_NEEDS_FSAL;
+	d.facc1 = 1.0 / (x->dfactor > 0.0 ? x->dfactor : (dp5 ? 0.2 : 0.3));
+	d.facc2 = 1.0 / (x->ifactor > 0.0 ? x->ifactor : (dp5 ? 10.0 : 6.0));
+	if (dp5) {
+		d.beta = x->beta == 0.0 ? 0.04 : (x->beta < 0.0 ? 0.0 : x->beta);
+		d.expo1 = 0.2 - d.beta * 0.75;
+	} else {
+		d.beta = x->beta <= 0.0 ? 0.0 : x->beta;
+		d.expo1 = 1.0 / 8.0 - d.beta * 0.2;
+	}
+	d.reject_by_dfactor = (x->method_flags >> 8) & 1;
 	d.t = x->t; d.Y = x->Y; d.work = x->work; d.ctrl = x->ctrl; d.status = x->status;
 	d.n_accepted = x->n_accepted; d.n_rejected = x->n_rejected;
 	d.tile_skip = x->scratch; d.active_count = x->scratch + x->ld / 32 + 1;
@@ -586,22 +658,17 @@ int jb_dense_integrate(const jb_dense_args *x)
 		JBD_LAUNCH(jbd::probe_finish_kernel, egrid, eblock, d);
 	}
 	reset_count();
-	JBD_LAUNCH(jbd::first_step_kernel, tgrid, 256, d, have_probe);
+	JBD_LAUNCH(jbd::first_step_kernel<Tab>, tgrid, 256, d, have_probe);
 
 	// ---- rounds: one step attempt of every unfinished trajectory; the host looks at the counter every few rounds
 	const int check_every = x->rounds_per_check > 0 ? x->rounds_per_check : 4;
 	int64_t rounds = 0;
 	while (true) {
 		for (int r = 0; r < check_every; ++r) {
-			JBD_LAUNCH(jbd::stage_kernel<1>, egrid, eblock, d); jbd::gemm(d, stream);
-			JBD_LAUNCH(jbd::stage_kernel<2>, egrid, eblock, d); jbd::gemm(d, stream);
-			JBD_LAUNCH(jbd::stage_kernel<3>, egrid, eblock, d); jbd::gemm(d, stream);
-			JBD_LAUNCH(jbd::stage_kernel<4>, egrid, eblock, d); jbd::gemm(d, stream);
-			JBD_LAUNCH(jbd::stage_kernel<5>, egrid, eblock, d); jbd::gemm(d, stream);
-			JBD_LAUNCH(jbd::stage_kernel<6>, egrid, eblock, d); jbd::gemm(d, stream);
-			JBD_LAUNCH(jbd::error_kernel, egrid, eblock, d);
+			launch_stages<Tab>(d, egrid, eblock, stream);
+			JBD_LAUNCH(jbd::error_kernel<Tab>, egrid, eblock, d);
 			reset_count();
-			JBD_LAUNCH(jbd::control_kernel, tgrid, 256, d);
+			JBD_LAUNCH(jbd::control_kernel<Tab>, tgrid, 256, d);
 			++rounds;
 		}
 		err = active_trajectories(&active);
@@ -614,6 +681,16 @@ int jb_dense_integrate(const jb_dense_args *x)
 	if (x->rounds_out) *x->rounds_out = rounds;
 	err = cudaGetLastError();
 	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_integrate");
+}
+
+}  // namespace jbd
+
+extern "C" {
+
+int jb_dense_integrate(const jb_dense_args *x)
+{
+	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_integrate: argument block has the wrong size");
+	return (x->method_flags & 0xff) == JB_DOP853 ? jbd::integrate<jbd::DOP853>(x) : jbd::integrate<jbd::DP5>(x);
 }
 
 }  // extern "C"

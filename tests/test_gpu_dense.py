@@ -59,7 +59,8 @@ def test_structure_detection_and_rhs():
 	assert_allclose(dense, generic, rtol=1e-11, atol=1e-12)
 
 
-def test_dense_integration_matches_generic_kernels_and_oracle():
+@pytest.mark.parametrize("name", ["dopri5", "dop853"])
+def test_dense_integration_matches_generic_kernels_and_oracle(name):
 	from oracle import c_rhs, ensemble
 	n, B = 40, 150
 	system = W.kuramoto(n)
@@ -68,7 +69,7 @@ def test_dense_integration_matches_generic_kernels_and_oracle():
 	results, counts = {}, {}
 	for storage in ("dense", None):
 		ODE = jitcode(system["f_sym"], n=n, verbose=False)
-		ODE.set_integrator("dopri5", rtol=RTOL, atol=ATOL, storage=storage)
+		ODE.set_integrator(name, rtol=RTOL, atol=ATOL, storage=storage)
 		ODE.set_initial_value(Y0, 0.0)
 		results[storage] = np.stack([ODE.integrate(T) for T in times])
 		counts[storage] = ODE.step_counts()
@@ -77,8 +78,27 @@ def test_dense_integration_matches_generic_kernels_and_oracle():
 	within_tolerance(results["dense"], results[None])
 	assert abs(sum(counts["dense"]) - sum(counts[None])) <= 0.02 * sum(counts[None])
 	handle = c_rhs.build_rhs(system["f_sym"], n=n)
-	ref = ensemble.run_ensemble(handle, "dopri5", Y0[:24], times, rtol=RTOL, atol=ATOL)
+	ref = ensemble.run_ensemble(handle, name, Y0[:24], times, rtol=RTOL, atol=ATOL)
 	within_tolerance(results["dense"][:, :24], ref["y"])
+
+
+def test_dense_example_settings():
+	"""the example's own integrator settings (examples/kuramoto_network.py:29): dop853, atol 1e-6, rtol 0"""
+	from oracle import c_rhs, ensemble
+	n, B = 40, 64
+	system = W.kuramoto(n)
+	Y0 = W.kuramoto_ensemble(B, n, seed=3)
+	ODE = jitcode(system["f_sym"], n=n, verbose=False)
+	ODE.set_integrator("dop853", atol=1e-6, rtol=0, storage="dense")
+	ODE.set_initial_value(Y0, 0.0)
+	result = ODE.integrate(10.0)
+	handle = c_rhs.build_rhs(system["f_sym"], n=n)
+	ref = ensemble.run_ensemble(handle, "dop853", Y0, [10.0], atol=1e-6, rtol=0)
+	assert np.abs(result - ref["y"][0]).max() <= 10 * 1e-6
+	# the oracle counts right-hand-side calls / 12; SciPy's dop853 spends 11 on a rejected attempt and now and then one
+	# more at the start of a call (tests/test_oracle_pin.py), so the comparison of attempts is loose
+	attempts = sum(ODE.step_counts())
+	assert abs(attempts - ref["attempts"]) <= 0.15 * ref["attempts"]
 
 
 def test_dense_kuramoto_1000():
