@@ -131,7 +131,7 @@ def _c_array(values, per_line=16):
 	return ",\n\t".join(", ".join(values[k:k+per_line]) for k in range(0, len(values), per_line))
 
 
-def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None, component_of=None, kregs=0, min_blocks=1):
+def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None, component_of=None, kregs=0, min_blocks=1, team_warps=1):
 	"""the complete translation unit of one module (what _render_template produces from
 	jitced_template.c in the reference, _jitcode.py:397-406).
 
@@ -157,12 +157,12 @@ def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, met
 	n_row = (n + 2) // 2 * 2 if warp else n
 	if warp:
 		function = f"""	template <class VI, class VO>
-	static __device__ __forceinline__ void rhs_warp(const double t, const VI &y, VO &dy, const Par &par, const int lane, const void *jb_tables)
+	static __device__ __forceinline__ void rhs_warp(const double t, const VI &y, VO &dy, const Par &par, const int lane, const void *jb_tables, double *jb_scratch)
 	{{
 		const double *const JB_TF = static_cast<const double *>(jb_tables);
 		const TU *const JB_TU = reinterpret_cast<const TU *>(JB_TF + TF_COUNT);
 {body}
-		(void) t; (void) par; (void) JB_TF; (void) JB_TU;
+		(void) t; (void) par; (void) JB_TF; (void) JB_TU; (void) jb_scratch;
 	}}"""
 	else:
 		function = f"""	template <class VI, class VO>
@@ -196,6 +196,7 @@ struct Sys {{
 	static constexpr int NT = {len(tangent_indices)};     // transversal tangent coordinates
 	static constexpr int TF_COUNT = {len(tf)}, TU_COUNT = {len(tu)};
 	static constexpr int NROW = {n_row};   // shared-memory row length (warp storage): position N holds 0
+	static constexpr int TEAM_WARPS = {int(team_warps)};   // warps that share one trajectory (warp storage)
 	typedef {tu_type} TU;
 	static __device__ __forceinline__ const TU *components(const void *tables)
 	{{

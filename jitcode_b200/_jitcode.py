@@ -61,36 +61,50 @@ def _storage_for(n, method, driver):
 	return _codegen.JB_STORE_REGISTERS if rows * n <= 88 else _codegen.JB_STORE_GLOBAL
 
 
-def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None):
-	"""(kregs, threads) of a warp-storage module.
+def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None, team_warps=None):
+	"""(kregs, threads, team_warps) of a warp-storage module.
 
-	kregs : how many stage rows K[0 … kregs) — plus the state — every lane keeps in registers (its share: every
-		32nd component) instead of shared memory.  Shared memory is the bottleneck of this kernel (gathers of the
-		vectorised right-hand side), so as many rows as the register file allows are taken out of it.
-	threads : 32 × the number of trajectories (warps) per block; one block per SM."""
+	team_warps : how many warps (1, 2, 4, 8) integrate ONE trajectory together.  One is best while many trajectories
+		fit an SM's shared memory; larger systems get more warps per trajectory so that the SM still has enough
+		warps in flight to hide the latency of the shared-memory gathers.
+	kregs : how many stage rows K[0 … kregs) — plus the state — every thread keeps in registers (its share of the
+		components) instead of shared memory.  Shared memory is the bottleneck of this kernel, so rows are taken
+		out of it as long as that does not cost resident warps.
+	threads : threads per block (one persistent block per SM) = 32 · team_warps · trajectories per block."""
 	stages = _stage_rows(method, driver)
-	passes = (n + 31) // 32
 	dense = 1 if driver == _codegen.JB_DRV_IVP_DENSE else 0
 	row_bytes = (n + 2) // 2 * 2 * 8
 	available = SHARED_MEMORY_PER_BLOCK - table_bytes - 4 * n - 64
-
 	last_stage = 6 if method == _codegen.JB_DP5 else 12      # K[S]: its row doubles as the staging row while k <= S
 
-	def warps(k):
+	def teams(k, w):
+		"""trajectories per SM with k cached rows and w warps per trajectory"""
+		passes = (n + 32 * w - 1) // (32 * w)
 		rows = 1 + (1 if (k == 0 or k > last_stage) else 0) + dense + stages - k       # WarpStore::ROWS
-		by_shared = available // (rows * row_bytes)
+		by_shared = available // (rows * row_bytes + 64)
 		registers = 80 + 2 * passes * (1 + k) if k else 96       # measured on the Rössler network (profiles/)
 		if registers > 255:
 			return 0
-		return max(0, min(16, by_shared, 65536 // (32 * registers)))
+		by_registers = 65536 // (32 * w * registers)
+		limit = 15 if w > 1 else 16                              # named barriers 1 … 15 / warps per block
+		return max(0, min(limit, 1024 // (32 * w), by_shared, by_registers))
 
-	if kregs is None:
-		# most trajectories per SM first (latency hiding), then most rows out of shared memory
-		kregs = max(range(stages + 1), key=lambda k: (warps(k), k))
-	kregs = max(0, min(int(kregs), stages))
+	def best_rows(w):
+		"""cached rows for teams of w warps: most trajectories per SM first, then most rows out of shared memory"""
+		options = (kregs,) if kregs is not None else range(stages + 1)
+		return max((max(0, min(int(k), stages)) for k in options), key=lambda k: (teams(k, w), k))
+
+	if team_warps is None:
+		# Measured on Rössler networks (profiles/README.md): a single warp per trajectory wins as long as it keeps ~6+
+		# warps resident (n = 600: 8 single warps beat 7 teams of 2 by 15 %) — block-level barriers and coarser passes
+		# cost more than the extra warps hide; beyond that, the smallest team that brings 8+ warps (n = 1500: teams of
+		# 8 warps run 10× faster than the thread-per-trajectory kernel, single warps do not fit at all).
+		choices = {w: teams(best_rows(w), w) * w for w in (1, 2, 4, 8)}
+		team_warps = 1 if choices[1] >= 6 else max(choices, key=lambda w: (min(choices[w], 16), -w))
+	kregs = best_rows(team_warps)
 	if threads is None:
-		threads = 32 * warps(kregs)
-	return kregs, threads
+		threads = 32 * team_warps * teams(kregs, team_warps)
+	return kregs, threads, team_warps
 
 
 class jitcode:
@@ -255,7 +269,7 @@ class jitcode:
 		raise NotImplementedError("There is no CPU fallback: the derivative only exists as CUDA code.")
 
 	def compile_cuda(self, extra_compile_args=None, extra_link_args=None, verbose=False, modulename=None, omp=None,
-			method=_codegen.JB_DP5, driver=_codegen.JB_DRV_ODE, storage=None, threads=None, kregs=None):
+			method=_codegen.JB_DP5, driver=_codegen.JB_DRV_ODE, storage=None, threads=None, kregs=None, min_blocks=None, team_warps=None):
 		if isinstance(storage, str):
 			storage = STORAGE_BY_NAME[storage]
 		"""
@@ -271,40 +285,44 @@ class jitcode:
 		if extra_link_args is not None:
 			self._compile_options["extra_link_args"] = tuple(extra_link_args)
 		self._compile_options["verbose"] = verbose
-		return self._module(method, driver, storage, threads, kregs)
+		return self._module(method, driver, storage, threads, kregs, min_blocks, team_warps)
 
 	compile_C = compile_cuda
 
-	def _warp_plan(self):
-		"""the vectorised form of the right-hand side (None if it cannot be vectorised)."""
-		if not hasattr(self, "_plan"):
-			self._plan = None
+	def _warp_plan(self, team_warps=1):
+		"""the vectorised form of the right-hand side, printed for teams of `team_warps` warps per trajectory
+		(None if the system cannot be vectorised)."""
+		if not hasattr(self, "_plans"):
+			self._plans = {}
+		if team_warps not in self._plans:
+			self._plans[team_warps] = None
 			if self._f_list and self._post == JB_POST_NONE:
 				try:
-					plan = _vectorise.make_plan(self._f_list, self.helpers, self.control_pars)
-					lines, tables, component_of = _vectorise.warp_statements(plan)
-					self._plan = (plan, lines, tables, component_of)
+					if not hasattr(self, "_plan_tree"):
+						self._plan_tree = _vectorise.make_plan(self._f_list, self.helpers, self.control_pars)
+					lines, tables, component_of = _vectorise.warp_statements(self._plan_tree, team_warps)
+					self._plans[team_warps] = (self._plan_tree, lines, tables, component_of)
 				except NotImplementedError:
 					pass
-		return self._plan
+		return self._plans[team_warps]
 
 	def _choose_storage(self, method, driver):
 		storage = _storage_for(self.n, method, driver)
 		if storage == _codegen.JB_STORE_GLOBAL and self.n >= 64:
 			plan = self._warp_plan()
 			if plan is not None and plan[0].efficiency >= 0.5:
-				if _warp_configuration(self.n, method, driver, plan[2].nbytes)[1] >= 64:
+				if _warp_configuration(self.n, method, driver, plan[2].nbytes)[1] >= 128:
 					storage = _codegen.JB_STORE_WARP
 		return storage
 
-	def _module(self, method, driver, storage=None, threads=None, kregs=None, min_blocks=None):
+	def _module(self, method, driver, storage=None, threads=None, kregs=None, min_blocks=None, team_warps=None):
 		if storage is None:
 			if (method, driver, None) in self._modules:
 				return self._modules[(method, driver, None)]
 			storage = self._choose_storage(method, driver) if self._f_list else None
 			if storage is None:
 				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
-		key = (method, driver, storage) if (threads is None and kregs is None and min_blocks is None) else (method, driver, storage, threads, kregs, min_blocks)
+		key = (method, driver, storage) if (threads is None and kregs is None and min_blocks is None and team_warps is None) else (method, driver, storage, threads, kregs, min_blocks, team_warps)
 		if key not in self._modules:
 			if not self._f_list:
 				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
@@ -314,10 +332,10 @@ class jitcode:
 				if plan is None:
 					raise NotImplementedError("This system cannot be vectorised for warp storage (or it has a Lyapunov post-step).")
 				self.check()
-				_, statements, tables, component_of = plan
-				kregs, threads = _warp_configuration(self.n, method, driver, tables.nbytes, kregs, threads)
-				if threads < 32:
+				kregs, threads, team_warps = _warp_configuration(self.n, method, driver, plan[2].nbytes, kregs, threads, team_warps)
+				if threads < 32 * team_warps:
 					raise ValueError("The system is too large for warp storage: one trajectory does not fit shared memory.")
+				_, statements, tables, component_of = self._warp_plan(team_warps)
 			else:
 				if self._statements is None:
 					self.generate_f_cuda()
@@ -330,7 +348,7 @@ class jitcode:
 				statements, self.n, len(self.control_pars),
 				self._n_basic_module, self._n_lyap_module, self._tangent_indices_module,
 				method, driver, storage, threads, tables=tables, component_of=component_of, kregs=kregs or 0,
-				min_blocks=min_blocks or 1,
+				min_blocks=min_blocks or 1, team_warps=team_warps or 1,
 			)
 			path = _build.compile_module(
 				source, self._compile_options["extra_compile_args"], self._compile_options["extra_link_args"],
@@ -482,7 +500,7 @@ class jitcode:
 	_post = JB_POST_NONE
 	_proj = None
 
-	def set_integrator(self, name, nsteps=10**6, interpolate=True, *, device=None, storage=None, threads=None, kregs=None, min_blocks=None, **integrator_params):
+	def set_integrator(self, name, nsteps=10**6, interpolate=True, *, device=None, storage=None, threads=None, kregs=None, min_blocks=None, team_warps=None, **integrator_params):
 		"""
 		As in the reference (_jitcode.py:560-626).
 
@@ -519,9 +537,9 @@ class jitcode:
 			self.integrator = _dense.CudaDenseSineIntegrator(*self._dense_coupling(), method=method, device=device, nsteps=nsteps, **integrator_params)
 			self._restore_state(old_integrator)
 			return
-		module = self._module(method, driver, storage, threads, kregs, min_blocks)   # compiling needs no GPU …
+		module = self._module(method, driver, storage, threads, kregs, min_blocks, team_warps)   # compiling needs no GPU …
 		require_cuda(device)                                      # … running does
-		self._integrator_config = (method, driver, storage, threads, kregs, min_blocks)
+		self._integrator_config = (method, driver, storage, threads, kregs, min_blocks, team_warps)
 		self._f_module = module
 		integrator_params.pop("verbosity", None)
 		self.integrator = CudaEnsembleIntegrator(

@@ -387,7 +387,7 @@ def _ell(values, start, size, width, pad):
 	return out
 
 
-def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
+def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team):
 	"""one variable-length sum of a group, in ELL form: all lanes run the same (unrolled) number of terms."""
 	size = group.size
 	lengths = [loop.start[m+1] - loop.start[m] for m in range(size)]
@@ -409,7 +409,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 		# bare gather Σ g(y[idx]).  Shared-memory bandwidth is what this kernel runs out of, so the table is
 		# as small as it gets: 16-bit byte offsets, two per 32-bit word (one wavefront per 64 gathers), and every
 		# pass of 32 statements is padded only to ITS longest statement.
-		n_pass = (size + 31) // 32
+		n_pass = (size + team - 1) // team
 		per_statement = [indices[0][loop.start[m]:loop.start[m+1]] for m in range(size)]
 
 		# Diagonals: in lattice-like networks most statements read the SAME relative neighbours (m+1, m-1, m+2 …
@@ -449,14 +449,14 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 
 		words, bases, widths = [], [], []
 		for p in range(n_pass):
-			members = range(32*p, min(size, 32*p + 32))
+			members = range(team*p, min(size, team*p + team))
 			pass_width = max(lengths[m] for m in members)
 			pass_width += pass_width % 2
 			bases.append(len(words) // 2)      # in 32-bit words
 			widths.append(pass_width // 2)
 			for kp in range(pass_width // 2):
-				for lane in range(32):
-					m = 32*p + lane
+				for lane in range(team):
+					m = team*p + lane
 					for k in (2*kp, 2*kp + 1):
 						inside = m < size and k < lengths[m]
 						words.append(8 * (per_statement[m][k] if inside else zero_slot))
@@ -477,8 +477,8 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 				high = tables.add_u([mask >> 16 for mask in masks])
 				lines.append(f"\t\tconst unsigned present = JB_TU[{low} + m] | ((unsigned) JB_TU[{high} + m] << 16);")
 			for k, d in enumerate(diagonals):
-				# 32·pass + 31 + d < ring: no lane of this pass wraps; 32·pass + d >= ring: all of them do (pass is a constant after unrolling)
-				index = (f"((32 * pass + 31 + {d} < {ring}) ? m + {d} : ((32 * pass + {d} >= {ring}) ? m + {d} - {ring} : "
+				# first case: no thread of this pass wraps around the ring; second: all of them do (pass is a constant after unrolling)
+				index = (f"(({team} * pass + {team - 1} + {d} < {ring}) ? m + {d} : (({team} * pass + {d} >= {ring}) ? m + {d} - {ring} : "
 						f"(m + {d} >= {ring} ? m + {d} - {ring} : m + {d})))")
 				value = term.replace(reads, f"y({lo} + {index})")
 				accumulator = f"{name}_{'abcd'[k % 4]}"
@@ -493,7 +493,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 			lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
 			lines.append("#pragma unroll")
 			lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
-			lines.append("\t\t\tconst unsigned pair = pairs[k * 32];")
+			lines.append(f"\t\t\tconst unsigned pair = pairs[k * {team}];")
 			lines.append(f"\t\t\t{name}_c += {term.replace(reads, 'y.at(pair & 0xffffu)')};")
 			lines.append(f"\t\t\t{name}_d += {term.replace(reads, 'y.at(pair >> 16)')};")
 			lines.append("\t\t}")
@@ -528,9 +528,11 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot):
 	lines.append("\t}")
 
 
-def warp_statements(plan):
+def warp_statements(plan, team_warps=1):
 	"""returns (lines of the body of Sys::rhs_warp, Tables, component_of) where component_of[q] is the
-	component stored at position q of the kernel's vectors; position n is a slot that always holds 0."""
+	component stored at position q of the kernel's vectors; position n is a slot that always holds 0.
+	team_warps: how many warps share one trajectory (`lane` in the printed code is the rank within that team)."""
+	team = 32 * team_warps
 	printer = CudaPrinter()
 	tables = Tables()
 	lines = []
@@ -578,11 +580,11 @@ def warp_statements(plan):
 		for loop in group.loops:
 			count = loop.start[1]
 			lines.append(f"\tdouble {loop.symbol.name}_acc = 0.0;")
-			lines.append(f"\tfor (int k = lane; k < {count}; k += 32) {{")
+			lines.append(f"\tfor (int k = lane; k < {count}; k += {team}) {{")
 			slot_preamble(loop.prefix, loop.consts, loop.indices, "k", "\t\t")
 			lines.append(f"\t\t{loop.symbol.name}_acc += {printer.doprint(loop.body)};")
 			lines.append("\t}")
-			lines.append(f"\tconst double {loop.symbol.name} = jb::warp_sum({loop.symbol.name}_acc);")
+			lines.append(f"\tconst double {loop.symbol.name} = jb::Team<{team_warps}>::sum({loop.symbol.name}_acc, jb_scratch);")
 		slot_preamble(group.prefix, group.consts, group.indices, "0", "\t")
 		lines.append(f"\t{symbol.name} = {printer.doprint(group.body)};")
 		lines.append("}")
@@ -593,18 +595,18 @@ def warp_statements(plan):
 	for g, group in enumerate(plan.groups):
 		base = position[group.outs[0]]
 		lines.append(f"// group {g}: {group.size} statement(s), components at positions {base} … {base + group.size - 1}")
-		n_pass = (group.size + 31) // 32
+		n_pass = (group.size + team - 1) // team
 		if group.loops and n_pass <= 16:
 			# passes unrolled: every pass knows its own trip counts at compile time
 			lines.append("#pragma unroll")
 			lines.append(f"for (int pass = 0; pass < {n_pass}; ++pass) {{")
-			lines.append("\tconst int m = lane + 32 * pass;")
+			lines.append(f"\tconst int m = lane + {team} * pass;")
 			lines.append(f"\tif (m >= {group.size}) break;")
 		else:
-			lines.append(f"for (int m = lane; m < {group.size}; m += 32) {{")
-			lines.append("\tconst int pass = m >> 5; (void) pass;")
+			lines.append(f"for (int m = lane; m < {group.size}; m += {team}) {{")
+			lines.append(f"\tconst int pass = m / {team}; (void) pass;")
 		for loop in group.loops:
-			_print_loop(printer, loop, group, position, tables, lines, zero_slot)
+			_print_loop(printer, loop, group, position, tables, lines, zero_slot, team)
 		slot_preamble(group.prefix, group.consts, group.indices, "m", "\t")
 		lines.append(f"\tdy.set({base} + m, {printer.doprint(group.body)});")
 		lines.append("}")

@@ -31,15 +31,17 @@ using ModuleLayout = Layout<Tab, JB_MODULE_DRIVER>;
 
 // ---- warp storage: shared memory of a block = [tables of the right-hand side][stage vectors of warp 0][of warp 1]…
 template <class S, bool W> struct WarpShared {
-	static constexpr int TABLE_DOUBLES = 0, ROWS = 0, WARPS = 1;
+	static constexpr int TABLE_DOUBLES = 0, ROWS = 0, WARPS = 1, TEAM = 32, SCRATCH = 0;
 	static constexpr size_t BYTES = 0, EVAL_BYTES = 0;
 };
 template <class S> struct WarpShared<S, true> {
 	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) (((S::TU_COUNT + S::N) * sizeof(typename S::TU) + 15) / 16) * 2;
 	static constexpr int ROWS = WarpStore<S, Tab, JB_MODULE_DRIVER, JB_MODULE_KREGS>::ROWS;
-	static constexpr int WARPS = JB_MODULE_THREADS / 32;
-	static constexpr size_t BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * ROWS * S::NROW);
-	static constexpr size_t EVAL_BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * 2 * S::NROW);
+	static constexpr int TEAM = 32 * S::TEAM_WARPS;              // threads that share one trajectory
+	static constexpr int WARPS = JB_MODULE_THREADS / TEAM;       // trajectories (teams) per block
+	static constexpr int SCRATCH = 8;                            // doubles per team for its reductions
+	static constexpr size_t BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * (ROWS * S::NROW + SCRATCH));
+	static constexpr size_t EVAL_BYTES = sizeof(double) * (TABLE_DOUBLES + (size_t) WARPS * (2 * S::NROW + SCRATCH));
 };
 using Shared = WarpShared<Sys, MODULE_WARP>;
 
@@ -58,15 +60,16 @@ __global__ void __launch_bounds__(JB_MODULE_THREADS, JB_MODULE_MIN_BLOCKS)
 jb_integrate_kernel(const __grid_constant__ Params a)
 {
 	if constexpr (MODE == JB_STORE_WARP) {
-		// persistent blocks; every warp integrates trajectories b, b + (warps in the grid), …
+		// persistent blocks; every team of warps integrates trajectories b, b + (teams in the grid), …
 		extern __shared__ __align__(16) double jb_smem[];
 		stage_tables<Sys>(jb_smem);
-		const int warp = threadIdx.x >> 5;
-		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * Shared::ROWS * Sys::NROW;
+		using T = Team<Sys::TEAM_WARPS>;
+		const int team = T::index();
+		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) team * (Shared::ROWS * Sys::NROW + Shared::SCRATCH);
 		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
-		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < a.B; b += stride) {
+		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + team; b < a.B; b += stride) {
 			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
-			__syncwarp();
+			T::sync();
 		}
 	} else {
 		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,20 +86,22 @@ jb_eval_f_kernel(const double *t, const double *Y, const double *P, double *dY, 
 	if constexpr (MODE == JB_STORE_WARP) {
 		extern __shared__ __align__(16) double jb_smem[];
 		stage_tables<S>(jb_smem);
-		const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-		double *const in = jb_smem + Shared::TABLE_DOUBLES + (size_t) warp * 2 * S::NROW;
+		using T = Team<S::TEAM_WARPS>;
+		const int team = T::index(), rank = T::rank();
+		double *const in = jb_smem + Shared::TABLE_DOUBLES + (size_t) team * (2 * S::NROW + Shared::SCRATCH);
 		double *const out = in + S::NROW;
+		double *const scratch = out + S::NROW;
 		const typename S::TU *const comp = S::components(jb_smem);
-		if (lane == 0) for (int i = S::N; i < S::NROW; ++i) in[i] = 0.0;
+		if (rank == 0) for (int i = S::N; i < S::NROW; ++i) in[i] = 0.0;
 		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
-		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + warp; b < B; b += stride) {
+		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + team; b < B; b += stride) {
 			typename S::Par par;
 #pragma unroll
 			for (int k = 0; k < S::NP; ++k) par.v[k] = P[b * S::NP + k];
-			for (int i = lane; i < S::N; i += 32) in[i] = Y[b * S::N + comp[i]];
-			rhs_warp_outlined<S>(t[b], in, out, par, jb_smem);
-			for (int i = lane; i < S::N; i += 32) dY[b * S::N + comp[i]] = out[i];
-			__syncwarp();
+			for (int i = rank; i < S::N; i += T::SIZE) in[i] = Y[b * S::N + comp[i]];
+			rhs_warp_outlined<S>(t[b], in, out, par, jb_smem, scratch);
+			for (int i = rank; i < S::N; i += T::SIZE) dY[b * S::N + comp[i]] = out[i];
+			T::sync();
 		}
 	} else {
 		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;

@@ -80,6 +80,35 @@ __device__ __forceinline__ double warp_sum(double v)
 	return v;
 }
 
+// A team: the W warps (W = 1, 2, 4, 8) that integrate ONE trajectory together in warp storage, lanes across
+// components.  One warp suffices while a trajectory's rows leave room for many trajectories per SM; for larger
+// systems several warps share the rows, so that the SM still has enough warps in flight.
+template <int W>
+struct Team {
+	static constexpr int SIZE = 32 * W;
+	static __device__ __forceinline__ int rank() { return W == 1 ? (threadIdx.x & 31) : (threadIdx.x % SIZE); }
+	static __device__ __forceinline__ int index() { return threadIdx.x / SIZE; }      // team within the block
+	static __device__ __forceinline__ void sync()
+	{
+		if constexpr (W == 1) __syncwarp();
+		else asm volatile("bar.sync %0, %1;" :: "r"(1 + index()), "r"(SIZE) : "memory");   // named barrier per team
+	}
+	// Σ over the team, known to all its threads; `scratch`: W doubles of shared memory owned by the team
+	static __device__ __forceinline__ double sum(double v, double *scratch)
+	{
+		v = warp_sum(v);
+		if constexpr (W > 1) {
+			if ((threadIdx.x & 31) == 0) scratch[(threadIdx.x % SIZE) >> 5] = v;
+			sync();
+			v = 0.0;
+#pragma unroll
+			for (int w = 0; w < W; ++w) v += scratch[w];
+			sync();
+		}
+		return v;
+	}
+};
+
 // dst takes the value of src; src becomes scratch (registers: copy; global: pointer swap)
 template <int N>
 __device__ __forceinline__ void take(RVec<N> &dst, RVec<N> &src)
@@ -162,16 +191,18 @@ __device__ __noinline__ void rhs_outlined(double t, const double *__restrict__ i
 	GVec vo{out};
 	Sys::rhs(t, vi, vo, par);
 }
-// warp: one out-of-line copy of the vectorised right-hand side; lanes read what other lanes wrote
+// warp storage: one out-of-line copy of the vectorised right-hand side; threads read what other threads of their
+// team wrote, hence the team barriers around it
 template <class Sys>
 __device__ __noinline__ void rhs_warp_outlined(double t, const double *__restrict__ in, double *__restrict__ out,
-		const typename Sys::Par par, const void *tables)
+		const typename Sys::Par par, const void *tables, double *scratch)
 {
-	__syncwarp();
+	using T = Team<Sys::TEAM_WARPS>;
+	T::sync();
 	const SVec vi{const_cast<double *>(in)};
 	SVec vo{out};
-	Sys::rhs_warp(t, vi, vo, par, (int) (threadIdx.x & 31), tables);
-	__syncwarp();
+	Sys::rhs_warp(t, vi, vo, par, T::rank(), tables, scratch);
+	T::sync();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -241,7 +272,8 @@ struct ThreadStore {        // one thread per trajectory: registers (MODE 0) or 
 };
 
 template <class Sys, class Tab, int DRIVER, int KREGS>
-struct WarpStore {          // one warp per trajectory, lanes across components
+struct WarpStore {          // one team of warps per trajectory, lanes across components
+	using T = Team<Sys::TEAM_WARPS>;
 	static constexpr int N = Sys::N;
 	static constexpr int NROW = Sys::NROW;
 	using L = Layout<Tab, DRIVER>;
@@ -249,7 +281,7 @@ struct WarpStore {          // one warp per trajectory, lanes across components
 	static constexpr bool WARP = true;
 	static constexpr int KR = L::KR;
 	static constexpr bool CACHED = KREGS > 0;           // Y and K[0 … KREGS) live in registers, lane-strided
-	static constexpr int NP = (N + 31) / 32;            // passes of a lane-strided loop
+	static constexpr int NP = (N + T::SIZE - 1) / T::SIZE;   // passes of a loop strided over the team
 	// The staging row through which the right-hand side fills a register row shares the row of K[S]: register rows
 	// are only filled while K[S] (f at the end of the last step) is dead — it moves to K[0] before the next stage 1.
 	static constexpr bool F_ALIASED = CACHED && KREGS <= Tab::NSTAGE;
@@ -261,11 +293,13 @@ struct WarpStore {          // one warp per trajectory, lanes across components
 	double ry[CACHED ? NP : 1];
 	double rk[CACHED ? KREGS : 1][CACHED ? NP : 1];
 	double *pY, *pZ, *pYO, *pF, *pK[KR];
+	double *scratch;            // T::W doubles for team reductions
 	typename Sys::Par par;
 	const void *tables;
 
 	__device__ __forceinline__ void bind(double *smem)
 	{
+		scratch = smem + NROW * ROWS;
 		int row = 0;
 		pZ = smem + NROW * row++;
 		pY = pF = nullptr;
@@ -275,34 +309,34 @@ struct WarpStore {          // one warp per trajectory, lanes across components
 #pragma unroll
 		for (int j = 0; j < KR; ++j) pK[j] = j < KREGS ? nullptr : smem + NROW * (row + j - KREGS);
 		// position N … NROW-1 of every row holds 0: padding target of the vectorised loops
-		for (int r = threadIdx.x & 31; r < ROWS; r += 32)
+		for (int r = T::rank(); r < ROWS; r += T::SIZE)
 			for (int i = N; i < NROW; ++i) smem[r * NROW + i] = 0.0;
 	}
 
 	template <class F> __device__ __forceinline__ void for_each(F &&body)
 	{
-		const int lane = threadIdx.x & 31;
+		const int rank = T::rank();
 		if constexpr (CACHED) {
 			static_for<0, NP>([&](auto r) {
-				const int i = lane + 32 * r;
-				if (32 * (r + 1) <= N || i < N) body(i, r);
+				const int i = rank + T::SIZE * r;
+				if (T::SIZE * (r + 1) <= N || i < N) body(i, r);
 			});
 		} else {
-			for (int i = lane; i < N; i += 32) body(i, Idx<0>{});
+			for (int i = rank; i < N; i += T::SIZE) body(i, Idx<0>{});
 		}
 	}
 	template <class F> __device__ __forceinline__ double sum(F &&value)
 	{
 		double total = 0.0;
 		for_each([&](int i, auto r) { total += value(i, r); });
-		return warp_sum(total);
+		return T::sum(total, scratch);
 	}
 	template <class F> __device__ __forceinline__ void sum2(F &&value, double &s0, double &s1)
 	{
 		double a = 0.0, b = 0.0;
 		for_each([&](int i, auto r) { value(i, r, a, b); });
-		s0 = warp_sum(a);
-		s1 = warp_sum(b);
+		s0 = T::sum(a, scratch);
+		s1 = T::sum(b, scratch);
 	}
 
 	template <class R> __device__ __forceinline__ double y(int i, R r) const
@@ -334,10 +368,10 @@ struct WarpStore {          // one warp per trajectory, lanes across components
 	{
 		if constexpr (J < KREGS) {
 			double *const staging = F_ALIASED ? pK[Tab::NSTAGE] : pF;
-			rhs_warp_outlined<Sys>(t, in, staging, par, tables);
+			rhs_warp_outlined<Sys>(t, in, staging, par, tables, scratch);
 			for_each([&](int i, auto r) { rk[J][r] = staging[i]; });
 		} else {
-			rhs_warp_outlined<Sys>(t, in, pK[J], par, tables);
+			rhs_warp_outlined<Sys>(t, in, pK[J], par, tables, scratch);
 		}
 	}
 	template <int J> __device__ __forceinline__ void rhs_z(double t) { call<J>(t, pZ); }
@@ -574,7 +608,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	const int64_t ld = a.ld;
 	const int64_t vec = (int64_t) N * ld;                                   // one caller-visible vector
 	const int64_t off = WARP ? b * (int64_t) N : tile_offset(b, N);         // this trajectory inside it
-	const bool leader = !WARP || (threadIdx.x & 31) == 0;                   // writes the per-trajectory scalars
+	bool leader = true;                                                     // writes the per-trajectory scalars
+	if constexpr (WARP) leader = Team<Sys::TEAM_WARPS>::rank() == 0;
 
 	ST st;
 	st.rtol = a.rtol;

@@ -156,6 +156,40 @@ def test_warp_storage_matches_global_storage(name, interpolate):
 	assert abs(sum(counts["warp"]) - sum(counts["global"])) <= 0.001 * sum(counts["global"])
 
 
+@pytest.mark.parametrize("team_warps", [2, 4])
+def test_teams_of_warps_match_single_warps(team_warps):
+	"""warp storage with several warps per trajectory (larger systems) runs the same arithmetic as one warp per trajectory"""
+	system = W.roessler_network(100)
+	Y0, pars = W.roessler_ensemble(97, seed=12)
+	results, counts = {}, {}
+	for team in (1, team_warps):
+		ODE = make(system)
+		ODE.set_integrator("RK45", storage="warp", team_warps=team, **TOL)
+		ODE.set_parameters(pars[:, 0])
+		ODE.set_initial_value(Y0, 0.0)
+		results[team] = np.stack([ODE.integrate(T) for T in (0.7, 1.0, 4.0)])
+		counts[team] = ODE.step_counts()
+	assert_allclose(results[team_warps], results[1], rtol=1e-10, atol=1e-12)
+	assert counts[team_warps] == counts[1]
+
+
+def test_large_network_uses_teams():
+	"""n = 1500 (the size of the reference's examples/SW_of_Roesslers.py, N = 500): a trajectory no longer fits one
+	warp's share of an SM; several warps share it.  Checked against the thread-per-trajectory kernel."""
+	system = W.roessler_network(500)
+	Y0, pars = W.roessler_ensemble(40, N=500, seed=13)
+	results = {}
+	for storage in ("warp", "global"):
+		ODE = make(system)
+		ODE.set_integrator("dopri5", storage=storage, **TOL)
+		ODE.set_parameters(pars[:, 0])
+		ODE.set_initial_value(Y0, 0.0)
+		results[storage] = ODE.integrate(2.0)
+		if storage == "warp":
+			assert ODE.integrator.module.info.threads_per_block >= 256
+	assert_allclose(results["warp"], results["global"], rtol=1e-9, atol=1e-11)
+
+
 # ------------------------------------------------------------------ against the CPU oracle on seeded ensembles
 
 @pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("RK45", True), ("RK45", False), ("dop853", True)])
