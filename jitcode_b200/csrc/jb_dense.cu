@@ -129,6 +129,101 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
 	}
 }
 
+// The same product, software-pipelined: tiles travel global → shared memory with cp.async (16-byte copies, zero
+// fill beyond the matrix edges) three chunks ahead of the tensor cores, so that the loads of chunk c+2 overlap
+// the DMMAs of chunk c.  Needs 16-byte aligned rows (K and N even); the kernel above is the fallback.
+constexpr int STAGES = 3;
+constexpr size_t PIPELINED_SHARED_BYTES = sizeof(double) * STAGES * (BM * LDA + BK * LDB);
+
+__device__ __forceinline__ void cp_async_16(double *smem, const double *global, int bytes)
+{
+	const unsigned target = (unsigned) __cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(target), "l"(global), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+dgemm_dmma_pipelined_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
+		int M, int N, int K, const int *__restrict__ tile_skip, int64_t ld)
+{
+	if (tile_skip) {
+		const int64_t first = (((int64_t) blockIdx.x * BN) % ld) / 32;
+		if (tile_skip[first] && tile_skip[first + 1]) return;
+	}
+	extern __shared__ __align__(16) double gemm_shared[];
+	double *const sA = gemm_shared;                                  // [STAGES][BM * LDA]
+	double *const sB = gemm_shared + STAGES * BM * LDA;               // [STAGES][BK * LDB]
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int wm = warp >> 1, wn = warp & 1;
+	const int64_t m0 = (int64_t) blockIdx.y * BM, n0 = (int64_t) blockIdx.x * BN;
+
+	double acc[4][4][2];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+#pragma unroll
+		for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+	auto issue = [&](int stage, int k0) {
+		// A tile: 128 rows × 8 chunks of 2 doubles; 4 chunks per thread
+#pragma unroll
+		for (int c = tid; c < BM * (BK / 2); c += 256) {
+			const int row = c / (BK / 2), kk = (c % (BK / 2)) * 2;
+			const int64_t gm = m0 + row;
+			const int gk = k0 + kk;
+			const int bytes = (gm < M && gk < K) ? 16 : 0;
+			cp_async_16(sA + stage * BM * LDA + row * LDA + kk, A + (bytes ? gm * K + gk : 0), bytes);
+		}
+		// B tile: 16 rows × 32 chunks; 2 chunks per thread
+#pragma unroll
+		for (int c = tid; c < BK * (BN / 2); c += 256) {
+			const int row = c / (BN / 2), col = (c % (BN / 2)) * 2;
+			const int gk = k0 + row;
+			const int64_t gn = n0 + col;
+			const int bytes = (gk < K && gn < N) ? 16 : 0;
+			cp_async_16(sB + stage * BK * LDB + row * LDB + col, B + (bytes ? (int64_t) gk * N + gn : 0), bytes);
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+
+	const int chunks = (K + BK - 1) / BK;
+#pragma unroll
+	for (int s = 0; s < STAGES - 1; ++s) {
+		if (s < chunks) issue(s, s * BK);
+		else asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+	for (int chunk = 0; chunk < chunks; ++chunk) {
+		asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 2) : "memory");
+		__syncthreads();                                           // chunk's tiles have landed; everybody is done with chunk-1's
+		const int ahead = chunk + STAGES - 1;
+		if (ahead < chunks) issue(ahead % STAGES, ahead * BK);
+		else asm volatile("cp.async.commit_group;" ::: "memory");
+		const int stage = chunk % STAGES;
+		const double *a = sA + stage * BM * LDA + (wm * 32 + (lane >> 2)) * LDA + (lane & 3);
+		const double *b = sB + stage * BK * LDB + (lane & 3) * LDB + wn * 32 + (lane >> 2);
+#pragma unroll
+		for (int kk = 0; kk < BK; kk += 4) {
+			double fa[4], fb[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) fa[i] = a[i * 8 * LDA + kk];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) fb[j] = b[kk * LDB + j * 8];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+#pragma unroll
+				for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int64_t gm = m0 + wm * 32 + i * 8 + (lane >> 2);
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int64_t gn = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
+			if (gm < M && gn < N) C[gm * N + gn] = acc[i][j][0];
+			if (gm < M && gn + 1 < N) C[gm * N + gn + 1] = acc[i][j][1];
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-trajectory control block (structure of arrays, ctrl[k*ld + b])
 
@@ -528,10 +623,15 @@ static void launch_gemm(const double *A, const double *B, double *C, int M, int 
 	static bool configured = false;
 	if (!configured) {
 		cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SHARED_BYTES);
+		cudaFuncSetAttribute(dgemm_dmma_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PIPELINED_SHARED_BYTES);
 		configured = true;
 	}
 	const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-	dgemm_dmma_kernel<<<grid, 256, GEMM_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
+	const bool aligned = K % 2 == 0 && N % 2 == 0 && (((uintptr_t) A | (uintptr_t) B) & 15) == 0;
+	if (aligned)
+		dgemm_dmma_pipelined_kernel<<<grid, 256, PIPELINED_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
+	else
+		dgemm_dmma_kernel<<<grid, 256, GEMM_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
 	launch_counter.fetch_add(1, std::memory_order_relaxed);
 }
 
