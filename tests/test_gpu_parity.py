@@ -190,6 +190,35 @@ def test_large_network_uses_teams():
 	assert_allclose(results["warp"], results["global"], rtol=1e-9, atol=1e-11)
 
 
+def test_full_size_roessler_sweep(golden):
+	"""BASELINE config 3 at its full size — 2^20 trajectories of the 300-dimensional network — through properties
+	that need no reference run: the fixture's trajectories sit at the front of the ensemble and must come out as in
+	the golden file; a random sample must equal what the other large-system kernel computes for it alone (every
+	trajectory is independent of its position in the batch); every trajectory is finite and took a plausible number
+	of steps."""
+	g = golden("roessler_100")
+	B = 1 << 20
+	system = W.roessler_network(100)
+	Y0, pars = W.roessler_ensemble(B, seed=77)
+	Y0[:6], pars[:6] = g["Y0"], g["pars"]
+	ODE = make(system)
+	ODE.set_integrator("dopri5", **TOL)
+	assert ODE.integrator.module.info.storage == 2
+	ODE.set_parameters(torch.as_tensor(pars).cuda())
+	ODE.set_initial_value(torch.as_tensor(Y0).cuda(), 0.0)
+	result = ODE.integrate(10.0)
+	assert result.shape == (B, 300) and bool(torch.isfinite(result).all())
+	assert_allclose(result[:6].cpu().numpy(), g["dopri5"][0], rtol=1e-6, atol=1e-8)
+	attempts = (ODE.integrator.n_accepted[:B] + ODE.integrator.n_rejected[:B]).cpu().numpy()
+	assert attempts.min() > 40 and attempts.max() < 400
+	sample = np.random.default_rng(5).choice(B, 300, replace=False)
+	check = make(system)
+	check.set_integrator("dopri5", storage="global", **TOL)
+	check.set_parameters(pars[sample, 0])
+	check.set_initial_value(Y0[sample], 0.0)
+	assert_allclose(result[torch.as_tensor(sample).cuda()].cpu().numpy(), check.integrate(10.0), rtol=1e-8, atol=1e-10)
+
+
 # ------------------------------------------------------------------ against the CPU oracle on seeded ensembles
 
 @pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("RK45", True), ("RK45", False), ("dop853", True)])
