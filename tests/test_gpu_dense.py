@@ -52,6 +52,7 @@ def test_structure_detection_and_rhs():
 	assert_allclose(Wm, expected, rtol=1e-14)
 	assert_allclose(omega, system["omega"], rtol=1e-14)
 	Y = W.kuramoto_ensemble(70, n)
+	ODE.compile_cuda()
 	generic = ODE.f(0.0, Y)                           # generated code of the written-out form
 	ODE.set_integrator("dopri5", storage="dense")
 	dense = ODE.f(0.0, Y)
@@ -67,7 +68,7 @@ def test_dense_integration_matches_generic_kernels_and_oracle(name):
 	Y0 = W.kuramoto_ensemble(B, n)
 	times = [1.0, 5.0]
 	results, counts = {}, {}
-	for storage in ("dense", None):
+	for storage in ("dense", "global"):
 		ODE = jitcode(system["f_sym"], n=n, verbose=False)
 		ODE.set_integrator(name, rtol=RTOL, atol=ATOL, storage=storage)
 		ODE.set_initial_value(Y0, 0.0)
@@ -75,8 +76,11 @@ def test_dense_integration_matches_generic_kernels_and_oracle(name):
 		counts[storage] = ODE.step_counts()
 		with pytest.raises(ValueError):
 			ODE.integrate(0.5)
-	within_tolerance(results["dense"], results[None])
-	assert abs(sum(counts["dense"]) - sum(counts[None])) <= 0.02 * sum(counts[None])
+	within_tolerance(results["dense"], results["global"])
+	assert abs(sum(counts["dense"]) - sum(counts["global"])) <= 0.02 * sum(counts["global"])
+	auto = jitcode(system["f_sym"], n=n, verbose=False)       # 20 % density: the dense engine is the default
+	auto.set_integrator(name, rtol=RTOL, atol=ATOL)
+	assert type(auto.integrator).__name__ == "CudaDenseSineIntegrator"
 	handle = c_rhs.build_rhs(system["f_sym"], n=n)
 	ref = ensemble.run_ensemble(handle, name, Y0[:24], times, rtol=RTOL, atol=ATOL)
 	within_tolerance(results["dense"][:, :24], ref["y"])
