@@ -242,7 +242,10 @@ def make_plan(f, helpers, control_pars):
 	f = [entry.xreplace(subs) for entry in f]
 	everything = helper_defs + f
 	plan = Plan(len(f), len(control_pars))
-	for k, call in enumerate(_repeated_function_calls(everything)):
+	# shared temporaries are evaluated by EVERY lane, which pays off for sin(t) but not for sin(y(3) − y(24)):
+	# calls that depend on the state stay inside their statements
+	uniform_calls = [call for call in _repeated_function_calls(everything) if not any(_is_dynvar(atom) for atom in call.atoms(AppliedUndef))]
+	for k, call in enumerate(uniform_calls):
 		symbol = sympy.Symbol(f"jb_call_{k}")
 		everything = [expr.xreplace({call: symbol}) for expr in everything]
 		plan.temporaries = [(s, d.xreplace({call: symbol})) for s, d in plan.temporaries]
