@@ -200,3 +200,25 @@ def test_streamed_host_ensemble_equals_plain_calls(case):
 	assert_allclose(out.numpy(), plain, rtol=0, atol=0)
 	assert ODE.step_counts() == counts and ODE.t == T
 	assert_allclose(ODE.y.numpy(), plain, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("name,interpolate", [("RK45", True), ("RK45", False), ("DOP853", True)])
+def test_warp_storage_options(name, interpolate):
+	"""per-component atol (goes through the component permutation of warp storage), max_step, and the loop over
+	sample times as one launch — all against the thread-per-trajectory kernel"""
+	system = W.roessler_network(100)
+	Y0, pars = W.roessler_ensemble(50, seed=21)
+	atol = 10.0 ** np.random.default_rng(3).uniform(-12, -7, 300)
+	times = [0.3, 0.35, 1.0, 2.5]
+	results = {}
+	for storage in ("warp", "global"):
+		ODE = make(system)
+		ODE.set_integrator(name, interpolate=interpolate, storage=storage, rtol=1e-7, atol=atol, max_step=0.05)
+		ODE.set_parameters(pars[:, 0])
+		ODE.set_initial_value(Y0, 0.0)
+		results[storage] = ODE.integrate_many(times)
+		assert sum(ODE.step_counts()) >= 50 * 50              # max_step 0.05 over t = 0 … 2.5
+		ODE.set_initial_value(Y0, 0.0)
+		looped = np.stack([ODE.integrate(T) for T in times])
+		assert_allclose(results[storage], looped, rtol=1e-12, atol=1e-14)
+	assert_allclose(results["warp"], results["global"], rtol=1e-9, atol=1e-12)
