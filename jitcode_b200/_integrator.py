@@ -347,15 +347,20 @@ class CudaEnsembleIntegrator:
 		self._check_failures()
 		return self._export(self._rows, out)
 
-	def integrate_many(self, times):
-		"""the loop `for T in times: integrate(T)` as ONE launch; returns (len(times), B, n)."""
+	def integrate_many(self, times, record_states=True):
+		"""the loop `for T in times: integrate(T)` as ONE launch; returns (len(times), B, n).
+		record_states=False keeps only the last state (returned as (1, B, n)) — for Lyapunov runs, whose result is
+		the exponents (`last_lyaps`), this saves recording, un-tiling and copying every intermediate state."""
 		times = list(times)
-		Yrec, lyap_rec = self._launch(times, record=True)
+		Yrec, lyap_rec = self._launch(times, record=record_states)
 		n_times = len(times)
-		out = torch.empty((n_times, self.B, self.n), dtype=torch.float64, device=self.device)
-		vec = self.n * self.ld
-		for i in range(n_times):
-			self.module.unpack(Yrec[i*vec:(i+1)*vec].data_ptr(), out[i].data_ptr(), self.B, self.n, self.ld, self.stream)
+		if record_states:
+			out = torch.empty((n_times, self.B, self.n), dtype=torch.float64, device=self.device)
+			vec = self.n * self.ld
+			for i in range(n_times):
+				self.module.unpack(Yrec[i*vec:(i+1)*vec].data_ptr(), out[i].data_ptr(), self.B, self.n, self.ld, self.stream)
+		else:
+			out = self._current_rows()[None]
 		self._rows = out[-1]
 		if self.n_out:
 			lv = self.n_out * self.ld

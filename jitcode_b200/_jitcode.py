@@ -670,13 +670,12 @@ class jitcode_lyap(jitcode):
 		basic, tangents = self._split(state)
 		return basic, lyaps, tangents
 
-	def integrate_many(self, times, discard=0):
+	def integrate_many(self, times, discard=0, record_states=True):
 		"""All calls of `integrate` for `times` in one launch: returns (states (T, B, n), local exponents
-		(T, B, n_lyap)); running sums of the exponents from sample `discard` on are kept on the device
-		(`lyapunov_statistics`)."""
+		(T, B, n_lyap)); with record_states=False only the last state is returned, as (1, B, n)."""
 		integrator = self.integrator
 		integrator.lyap_discard = discard
-		states = integrator.integrate_many(times)
+		states = integrator.integrate_many(times, record_states)
 		lyaps = integrator.last_lyaps
 		if integrator._single:
 			lyaps = lyaps[:, 0]

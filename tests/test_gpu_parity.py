@@ -339,7 +339,8 @@ def test_lyapunov_spectrum_golden():
 	ODE = jitcode_lyap(W.fhn()["f_sym"], n_lyap=4, verbose=False, seed=1)
 	ODE.set_integrator("dopri5")
 	ODE.set_initial_value(np.tile(W.FHN_Y0, (B, 1)) + 1e-3*np.random.default_rng(2).normal(size=(B, 4)), 0.0)
-	_, lyaps = ODE.integrate_many(np.arange(1, calls+1) * 10.0, discard=discard)
+	last, lyaps = ODE.integrate_many(np.arange(1, calls+1) * 10.0, discard=discard, record_states=False)
+	assert last.shape == (1, B, 4) and lyaps.shape == (calls, B, 4)
 	kept = lyaps[discard:]                       # (calls-discard, B, 4)
 	mean = kept.mean(axis=(0, 1))
 	per_trajectory = kept.mean(axis=0)
