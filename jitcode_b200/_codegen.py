@@ -202,6 +202,10 @@ struct Sys {{
 	{{
 		return reinterpret_cast<const TU *>(static_cast<const double *>(tables) + TF_COUNT) + TU_COUNT;
 	}}
+	static __device__ __forceinline__ const TU *positions(const void *tables)      // component → position
+	{{
+		return components(tables) + N;
+	}}
 	struct Par {{ double v[NP > 0 ? NP : 1]; }};
 {tangent}
 {function}

@@ -78,7 +78,7 @@ def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None
 	stages = _stage_rows(method, driver)
 	dense = 1 if driver == _codegen.JB_DRV_IVP_DENSE else 0
 	row_bytes = (n + 2) // 2 * 2 * 8
-	available = SHARED_MEMORY_PER_BLOCK - table_bytes - 4 * n - 64
+	available = SHARED_MEMORY_PER_BLOCK - table_bytes - 8 * n - 64
 	last_stage = 6 if method == _codegen.JB_DP5 else 12      # K[S]: its row doubles as the staging row while k <= S
 
 	def teams(k, w):
@@ -300,7 +300,7 @@ class jitcode:
 			self._plans = {}
 		if team_warps not in self._plans:
 			self._plans[team_warps] = None
-			if self._f_list and self._post == JB_POST_NONE:
+			if self._f_list:
 				try:
 					if not hasattr(self, "_plan_tree"):
 						self._plan_tree = _vectorise.make_plan(self._f_list, self.helpers, self.control_pars)
@@ -334,7 +334,7 @@ class jitcode:
 			if storage == _codegen.JB_STORE_WARP:
 				plan = self._warp_plan()
 				if plan is None:
-					raise NotImplementedError("This system cannot be vectorised for warp storage (or it has a Lyapunov post-step).")
+					raise NotImplementedError("This system cannot be vectorised for warp storage.")
 				self.check()
 				kregs, threads, team_warps = _warp_configuration(self.n, method, driver, plan[2].nbytes, kregs, threads, team_warps)
 				if threads < 32 * team_warps:

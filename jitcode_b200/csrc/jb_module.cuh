@@ -35,7 +35,7 @@ template <class S, bool W> struct WarpShared {
 	static constexpr size_t BYTES = 0, EVAL_BYTES = 0;
 };
 template <class S> struct WarpShared<S, true> {
-	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) (((S::TU_COUNT + S::N) * sizeof(typename S::TU) + 15) / 16) * 2;
+	static constexpr int TABLE_DOUBLES = S::TF_COUNT + (int) (((S::TU_COUNT + 2 * S::N) * sizeof(typename S::TU) + 15) / 16) * 2;
 	static constexpr int ROWS = WarpStore<S, Tab, JB_MODULE_DRIVER, JB_MODULE_KREGS>::ROWS;
 	static constexpr int TEAM = 32 * S::TEAM_WARPS;              // threads that share one trajectory
 	static constexpr int WARPS = JB_MODULE_THREADS / TEAM;       // trajectories (teams) per block
@@ -51,7 +51,11 @@ __device__ __forceinline__ void stage_tables(double *smem)
 	for (int i = threadIdx.x; i < S::TF_COUNT; i += blockDim.x) smem[i] = jb_generated::jb_tf[i];
 	typename S::TU *tu = reinterpret_cast<typename S::TU *>(smem + S::TF_COUNT);
 	for (int i = threadIdx.x; i < S::TU_COUNT; i += blockDim.x) tu[i] = jb_generated::jb_tu[i];
-	for (int i = threadIdx.x; i < S::N; i += blockDim.x) tu[S::TU_COUNT + i] = jb_generated::jb_component[i];
+	for (int i = threadIdx.x; i < S::N; i += blockDim.x) {
+		const typename S::TU component = jb_generated::jb_component[i];
+		tu[S::TU_COUNT + i] = component;                               // position → component
+		tu[S::TU_COUNT + S::N + component] = (typename S::TU) i;         // component → position
+	}
 	__syncthreads();
 }
 
@@ -264,8 +268,6 @@ int jb_integrate(const jb_integrate_args *x)
 			|| (jb::ModuleLayout::DENSE && !x->Yres))
 		return jb::fail(JB_E_BAD_ARGUMENT, "jb_integrate: missing or inconsistent buffers");
 	if (x->post != JB_POST_NONE) {
-		if (jb::MODULE_WARP)
-			return jb::fail(JB_E_UNSUPPORTED, "jb_integrate: Lyapunov post-steps are not available with warp storage");
 		if (jb::Sys::NL <= 0 || (x->post == JB_POST_LYAP_TRANSVERSAL && jb::Sys::NT <= 0)
 				|| (x->post == JB_POST_LYAP_RESTRICTED && (jb::Sys::NL != 1 || (x->n_proj > 0 && !x->proj))))
 			return jb::fail(JB_E_UNSUPPORTED, "jb_integrate: this module has no tangent vectors for the requested post-step");

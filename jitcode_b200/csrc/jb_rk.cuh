@@ -586,6 +586,62 @@ __device__ __forceinline__ double lyap_transversal(Vec &Y)
 	return norm;
 }
 
+// The same three post-steps for warp storage: the state sits in one shared-memory row `v` (component c at
+// v[where[c]]), the threads of the team stride over the components of a tangent vector, and every scalar product
+// is a shuffle reduction (two-level for teams of several warps) — the warp-level batched Gram–Schmidt of the
+// north star.  All threads of the team return the same norms.
+template <class Sys, class WT>
+__device__ __forceinline__ void team_lyap(int post, double *v, const WT *where, const double *proj, int n_proj,
+		double *norms, double *scratch)
+{
+	using T = Team<Sys::TEAM_WARPS>;
+	constexpr int NB = Sys::NB;
+	const int rank = T::rank();
+	auto dot = [&](auto &&left, auto &&right, int count) {
+		double partial = 0.0;
+		for (int i = rank; i < count; i += T::SIZE) partial = fma(left(i), right(i), partial);
+		return T::sum(partial, scratch);
+	};
+	auto tangent = [&](int k) { return [=](int i) -> double & { return v[where[NB * (1 + k) + i]]; }; };
+	T::sync();
+	if (post == JB_POST_LYAP_QR) {
+		for (int k = 0; k < Sys::NL; ++k) {
+			auto vk = tangent(k);
+			for (int j = 0; j < k; ++j) {
+				auto vj = tangent(j);
+				const double overlap = dot(vj, vk, NB);
+				for (int i = rank; i < NB; i += T::SIZE) vk(i) = fma(-overlap, vj(i), vk(i));
+				T::sync();
+			}
+			const double norm = sqrt(dot(vk, vk, NB));
+			norms[k] = norm;
+			const double inverse = 1.0 / norm;
+			for (int i = rank; i < NB; i += T::SIZE) vk(i) *= inverse;
+			T::sync();
+		}
+	} else if (post == JB_POST_LYAP_RESTRICTED) {
+		auto v0 = tangent(0);
+		for (int p = 0; p < n_proj; ++p) {
+			const double *plane = proj + (int64_t) p * NB;
+			const double overlap = dot([&](int i) { return plane[i]; }, v0, NB);
+			for (int i = rank; i < NB; i += T::SIZE) v0(i) = fma(-overlap, plane[i], v0(i));
+			T::sync();
+		}
+		const double norm = sqrt(dot(v0, v0, NB));
+		norms[0] = norm;
+		const double inverse = 1.0 / norm;
+		for (int i = rank; i < NB; i += T::SIZE) v0(i) *= inverse;
+		T::sync();
+	} else if (post == JB_POST_LYAP_TRANSVERSAL) {
+		auto vt = [=](int k) -> double & { return v[where[Sys::tangent_index(k)]]; };
+		const double norm = sqrt(dot(vt, vt, Sys::NT));
+		norms[0] = norm;
+		const double inverse = 1.0 / norm;
+		for (int k = rank; k < Sys::NT; k += T::SIZE) vt(k) *= inverse;
+		T::sync();
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // Everything one trajectory does during one launch.  Thread storage: called by the trajectory's
 // thread.  Warp storage: called by all 32 lanes of the trajectory's warp with identical scalar
@@ -900,10 +956,15 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			}
 		}
 
-		if constexpr (!WARP) {
-			if (a.post != JB_POST_NONE) {
-				double norms[NLY];
-				if constexpr (Sys::NL > 0) {
+		if (a.post != JB_POST_NONE) {
+			double norms[NLY];
+			if constexpr (Sys::NL > 0) {
+				if constexpr (WARP) {
+					// through the Z row: the state may live in registers, the tangent vectors are needed by every thread
+					st.for_each([&](int i, auto r) { st.set_z(i, r, st.y(i, r)); });
+					team_lyap<Sys>(a.post, st.pZ, Sys::positions(tables), a.proj, a.n_proj, norms, st.scratch);
+					st.for_each([&](int i, auto r) { st.set_y(i, r, st.z(i, r)); });
+				} else {
 					if (a.post == JB_POST_LYAP_QR)
 						lyap_orthonormalise<Sys::NB, Sys::NL, REG>(st.Y, norms);
 					else if (a.post == JB_POST_LYAP_RESTRICTED)
@@ -911,22 +972,25 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					else if (a.post == JB_POST_LYAP_TRANSVERSAL)
 						norms[0] = lyap_transversal<Sys, REG>(st.Y);
 				}
-				const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
-				for (int k = 0; k < NLY; ++k) {
-					if (k >= n_out) break;
-					const double lyap = log(norms[k]) / dt_lyap;
-					if (a.lyap_rec) a.lyap_rec[(int64_t) it * n_out * ld + tile_offset(b, n_out) + k * TILE] = lyap;
-					if (it >= a.lyap_discard) {
-						lyap_sum[k] += lyap;
-						lyap_sq[k] = fma(lyap, lyap, lyap_sq[k]);
-					}
+			}
+			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+			for (int k = 0; k < NLY; ++k) {
+				if (k >= n_out) break;
+				const double lyap = log(norms[k]) / dt_lyap;
+				if (a.lyap_rec && leader) {
+					if constexpr (WARP) a.lyap_rec[((int64_t) it * ld + b) * n_out + k] = lyap;
+					else a.lyap_rec[(int64_t) it * n_out * ld + tile_offset(b, n_out) + k * TILE] = lyap;
 				}
-				if constexpr (IVP) {
-					// the tangent vectors changed: the stepper restarts from the new state
-					initialised = false;
-					interpolant = false;
-					pending_f = have_f = false;
+				if (it >= a.lyap_discard) {
+					lyap_sum[k] += lyap;
+					lyap_sq[k] = fma(lyap, lyap, lyap_sq[k]);
 				}
+			}
+			if constexpr (IVP) {
+				// the tangent vectors changed: the stepper restarts from the new state
+				initialised = false;
+				interpolant = false;
+				pending_f = have_f = false;
 			}
 		}
 		if constexpr (!DENSE) {
@@ -966,11 +1030,14 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 		if (a.n_accepted) a.n_accepted[b] += n_acc;
 		if (a.n_rejected) a.n_rejected[b] += n_rej;
 	}
-	if constexpr (!WARP) {
-		if (a.lyap_acc && a.post != JB_POST_NONE) {
-			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
-			for (int k = 0; k < NLY; ++k) {
-				if (k >= n_out) break;
+	if (a.lyap_acc && a.post != JB_POST_NONE && leader) {
+		const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+		for (int k = 0; k < NLY; ++k) {
+			if (k >= n_out) break;
+			if constexpr (WARP) {
+				a.lyap_acc[b * n_out + k] += lyap_sum[k];
+				a.lyap_acc[((int64_t) ld + b) * n_out + k] += lyap_sq[k];
+			} else {
 				a.lyap_acc[tile_offset(b, n_out) + k * TILE] += lyap_sum[k];
 				a.lyap_acc[(int64_t) n_out * ld + tile_offset(b, n_out) + k * TILE] += lyap_sq[k];
 			}

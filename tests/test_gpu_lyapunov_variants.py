@@ -7,9 +7,11 @@ strength is a per-trajectory control parameter) and all 999 `integrate` calls as
 import numpy as np
 import pytest
 import sympy
+from numpy.testing import assert_allclose
 from scipy.stats import sem
 
-from jitcode_b200 import jitcode_restricted_lyap, jitcode_transversal_lyap, y
+import workloads as W
+from jitcode_b200 import jitcode, jitcode_lyap, jitcode_restricted_lyap, jitcode_transversal_lyap, y
 
 pytestmark = pytest.mark.gpu
 
@@ -95,3 +97,77 @@ def test_restricted_and_transversal_agree(name, average_dynamics):
 		assert abs(mean1 - mean2) < max(margin1, margin2, 1e-4), (coupling, mean1, margin1, mean2, margin2)
 		checked += 1
 	assert checked >= 2, "the dynamics left the synchronisation manifold for almost every coupling"
+
+
+# ------------------------------------------------------------------ warp storage: Gram–Schmidt as shuffle reductions
+
+def _with_tangents(states, n_lyap, seed):
+	rng = np.random.default_rng(seed)
+	B, n = states.shape
+	tangents = rng.normal(size=(B, n_lyap, n))
+	tangents /= np.linalg.norm(tangents, axis=2, keepdims=True)
+	return np.hstack([states, tangents.reshape(B, n_lyap * n)])
+
+
+@pytest.mark.parametrize("name", ["dopri5", "RK45"])
+def test_lyapunov_qr_in_warp_storage_small(name):
+	"""the FHN pair with 4 tangent vectors (n = 20) forced into warp storage against the thread-per-trajectory kernel"""
+	B = 70
+	full = _with_tangents(W.FHN_Y0 + 1e-3 * np.random.default_rng(1).normal(size=(B, 4)), 4, 2)
+	results = {}
+	for storage in ("warp", "global"):
+		ODE = jitcode_lyap(W.fhn()["f_sym"], n_lyap=4, verbose=False)
+		ODE.set_integrator(name, storage=storage)
+		jitcode.set_initial_value(ODE, full, 0.0)
+		results[storage] = [ODE.integrate(T) for T in (5.0, 10.0)]
+		assert ODE.integrator.module.info.storage == {"warp": 2, "global": 1}[storage]
+	for (s1, l1, v1), (s2, l2, v2) in zip(results["warp"], results["global"]):
+		assert_allclose(s1, s2, rtol=1e-9, atol=1e-12)
+		assert_allclose(l1, l2, rtol=1e-8, atol=1e-10)
+		assert_allclose(v1, v2, rtol=1e-7, atol=1e-9)
+
+
+def test_lyapunov_of_a_network_uses_warp_storage():
+	"""two Lyapunov exponents of the 100-oscillator Rössler network: a 900-dimensional system that vectorises
+	(tangent equations of all oscillators and both vectors have the same shapes) and runs with teams of warps"""
+	system = W.roessler_network(100, k_as_parameter=False)
+	B = 24
+	Y0, _ = W.roessler_ensemble(B, seed=4)
+	full = _with_tangents(Y0, 2, 5)
+	results = {}
+	for storage in (None, "global"):
+		ODE = jitcode_lyap(system["f_sym"], n_lyap=2, helpers=system["helpers"], n=300, verbose=False)
+		ODE.set_integrator("dopri5", storage=storage, rtol=1e-6, atol=1e-12)
+		jitcode.set_initial_value(ODE, full, 0.0)
+		results[storage] = ODE.integrate(1.0)
+		if storage is None:
+			assert ODE.integrator.module.info.storage == 2
+	(s1, l1, v1), (s2, l2, v2) = results[None], results["global"]
+	assert_allclose(s1, s2, rtol=1e-8, atol=1e-10)
+	assert_allclose(l1, l2, rtol=1e-6, atol=1e-9)
+	assert_allclose(np.einsum("bki,bli->bkl", v1, v1), np.broadcast_to(np.eye(2), (B, 2, 2)), atol=1e-12)
+	assert_allclose(v1, v2, rtol=1e-6, atol=1e-8)
+
+
+def test_restricted_and_transversal_in_warp_storage():
+	scenario = SCENARIOS["grouped by oscillators"]
+	ks = np.array([0.1, 0.2, -0.1])
+	rng = np.random.default_rng(3)
+	initial = rng.random((3, 6))
+	tangent = rng.normal(size=(3, 6))
+	tangent /= np.linalg.norm(tangent, axis=1, keepdims=True)
+	outcomes = {}
+	for storage in ("warp", "global"):
+		ODE1 = jitcode_restricted_lyap(scenario["f"], vectors=scenario["vectors"], verbose=False, control_pars=[k])
+		ODE1.set_integrator("dopri5", storage=storage)
+		ODE1.set_parameters(ks)
+		jitcode.set_initial_value(ODE1, np.hstack([initial, tangent]), 0.0)
+		ODE2 = jitcode_transversal_lyap(scenario["f"], groups=scenario["groups"], verbose=False, control_pars=[k], seed=7)
+		ODE2.set_integrator("dopri5", storage=storage)
+		ODE2.set_parameters(ks)
+		ODE2.set_initial_value(initial[:, :2], 0.0)
+		outcomes[storage] = (ODE1.integrate(50.0), ODE2.integrate(50.0))
+	for got, expected in zip(outcomes["warp"][0], outcomes["global"][0]):
+		assert_allclose(got, expected, rtol=1e-8, atol=1e-10)
+	for got, expected in zip(outcomes["warp"][1], outcomes["global"][1]):
+		assert_allclose(got, expected, rtol=1e-8, atol=1e-10)
