@@ -128,15 +128,15 @@ def test_lyapunov_qr_in_warp_storage_small(name):
 
 
 def test_lyapunov_of_a_network_uses_warp_storage():
-	"""two Lyapunov exponents of the 100-oscillator Rössler network: a 900-dimensional system that vectorises
-	(tangent equations of all oscillators and both vectors have the same shapes) and runs with teams of warps"""
-	system = W.roessler_network(100, k_as_parameter=False)
+	"""two Lyapunov exponents of a 40-oscillator Rössler network: a 360-dimensional system that vectorises (the
+	tangent equations of all oscillators and of both vectors have the same shapes) and therefore runs in warp storage"""
+	system = W.roessler_network(40, k_as_parameter=False)
 	B = 24
-	Y0, _ = W.roessler_ensemble(B, seed=4)
+	Y0, _ = W.roessler_ensemble(B, N=40, seed=4)
 	full = _with_tangents(Y0, 2, 5)
 	results = {}
 	for storage in (None, "global"):
-		ODE = jitcode_lyap(system["f_sym"], n_lyap=2, helpers=system["helpers"], n=300, verbose=False)
+		ODE = jitcode_lyap(system["f_sym"], n_lyap=2, helpers=system["helpers"], n=120, verbose=False)
 		ODE.set_integrator("dopri5", storage=storage, rtol=1e-6, atol=1e-12)
 		jitcode.set_initial_value(ODE, full, 0.0)
 		results[storage] = ODE.integrate(1.0)
