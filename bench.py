@@ -125,10 +125,9 @@ def cpu_baseline(wl, per_core):
 def run_reference(args):
 	rank = int(os.environ.get("RANK", "0"))
 	if rank != 0:
-		return
+		return None
 	if args.workload == "kuramoto":
-		print(json.dumps({"impl": "reference", "unavailable": "the reference's written-out form of the dense 1000-oscillator network (2e5 sine terms of generated C) is not built by the default run"}))
-		return
+		return {"impl": "reference", "unavailable": "the reference's written-out form of the dense 1000-oscillator network (2e5 sine terms of generated C) is not built by the default run"}
 	per_core = args.cpu_sample_per_core
 	from oracle import ensemble
 	cores = ensemble.available_cores()
@@ -153,7 +152,7 @@ def run_reference(args):
 		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 		"gpu_launches": 0,
 	}
-	print(json.dumps(line))
+	return line
 
 
 # ------------------------------------------------------------------ clocks
@@ -370,9 +369,21 @@ def run_ours(args):
 			line["config"]["lock_step_rounds_per_step"] = integrator.rounds / max(1, args.steps)
 		if world == 1 and not args.no_cpu_baseline and not dense:
 			line["cpu_baseline"] = cpu_baseline(wl, args.cpu_sample_per_core)
-		print(json.dumps(line))
+	else:
+		line = None
 	if world > 1:
 		dist.destroy_process_group()
+	return line
+
+
+def keep_stdout_for_the_result():
+	"""Libraries print to stdout now and then (NCCL announces its version there); the contract is ONE JSON line.
+	Everything written to file descriptor 1 from here on goes to stderr; the returned writer is the real stdout."""
+	sys.stdout.flush()
+	real = os.fdopen(os.dup(1), "w")
+	os.dup2(2, 1)
+	sys.stdout = os.fdopen(os.dup(2), "w")
+	return real
 
 
 def main():
@@ -396,10 +407,11 @@ def main():
 	args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 	if args.cpu_sample_per_core is None:
 		args.cpu_sample_per_core = {"roessler": 2048, "lv": 16384, "fhn_lyap": 4096}.get(args.workload, 256)
-	if args.impl == "reference":
-		run_reference(args)
-	else:
-		run_ours(args)
+	result = keep_stdout_for_the_result()
+	line = run_reference(args) if args.impl == "reference" else run_ours(args)
+	if line is not None:
+		result.write(json.dumps(line) + "\n")
+		result.flush()
 
 
 if __name__ == "__main__":
