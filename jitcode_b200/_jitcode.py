@@ -101,8 +101,9 @@ def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None
 	if team_warps is None:
 		# Measured on Rössler networks (profiles/README.md): a single warp per trajectory wins as long as it keeps ~6+
 		# warps resident (n = 600: 8 single warps beat 7 teams of 2 by 15 %) — block-level barriers and coarser passes
-		# cost more than the extra warps hide; beyond that, the smallest team that brings 8+ warps (n = 1500: teams of
-		# 8 warps run 10× faster than the thread-per-trajectory kernel, single warps do not fit at all).
+		# cost more than the extra warps hide.  Beyond that, the team size that keeps most warps resident (up to 16),
+		# the smaller team on a tie (n = 1500: 2 teams of 8 warps run 10× faster than the thread-per-trajectory
+		# kernel; single warps do not fit at all).
 		choices = {w: teams(best_rows(w), w) * w for w in (1, 2, 4, 8)}
 		team_warps = 1 if choices[1] >= 6 else max(choices, key=lambda w: (min(choices[w], 16), -w))
 	kregs = best_rows(team_warps)
