@@ -54,7 +54,7 @@ extern "C" {
 #define JB_ABI_VERSION 5
 #define JB_TILE 32
 
-enum jb_method  { JB_DP5 = 0, JB_DOP853 = 1 };
+enum jb_method  { JB_DP5 = 0, JB_DOP853 = 1, JB_RK23 = 2 /* solve_ivp drivers only */ };
 enum jb_driver  {
 	JB_DRV_ODE = 0,        /* Hairer controller; fresh start per sample time; lands exactly on it */
 	JB_DRV_IVP_DENSE = 1,  /* scipy solve_ivp controller; persistent stepper; dense output at the sample time */

@@ -16,11 +16,11 @@ from sympy.core.function import AppliedUndef
 from sympy.printing.c import C99CodePrinter
 
 
-JB_DP5, JB_DOP853 = 0, 1
+JB_DP5, JB_DOP853, JB_RK23 = 0, 1, 2
 JB_DRV_ODE, JB_DRV_IVP_DENSE, JB_DRV_IVP_LAND = 0, 1, 2
 JB_STORE_REGISTERS, JB_STORE_GLOBAL, JB_STORE_WARP = 0, 1, 2
 
-METHOD_NAMES = {JB_DP5: "JB_DP5", JB_DOP853: "JB_DOP853"}
+METHOD_NAMES = {JB_DP5: "JB_DP5", JB_DOP853: "JB_DOP853", JB_RK23: "JB_RK23"}
 DRIVER_NAMES = {JB_DRV_ODE: "JB_DRV_ODE", JB_DRV_IVP_DENSE: "JB_DRV_IVP_DENSE", JB_DRV_IVP_LAND: "JB_DRV_IVP_LAND"}
 STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL", JB_STORE_WARP: "JB_STORE_WARP"}
 

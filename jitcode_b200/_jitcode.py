@@ -12,9 +12,9 @@ and that every state has a batch axis:
   * the code generator emits CUDA (generate_f_cuda, alias generate_f_C), nvcc compiles it for
     sm_100a into a cached shared object (compile_cuda, alias compile_C) that is loaded through
     ctypes (include/jitcode_b200.h); the Runge–Kutta steppers are part of that module;
-  * only the explicit Dormand–Prince pairs exist: "dopri5"/"dop853" (Hairer's controller, the
-    reference's `ode` back end) and "RK45"/"DOP853" (SciPy's solve_ivp controller, with or
-    without interpolation); no lambdified fallback, no Python callbacks, no implicit solvers.
+  * only explicit Runge–Kutta pairs exist: "dopri5"/"dop853" (Hairer's controller, the reference's
+    `ode` back end) and "RK45"/"DOP853"/"RK23" (SciPy's solve_ivp controller, with or without
+    interpolation); no lambdified fallback, no Python callbacks, no implicit solvers.
 """
 
 import shutil
@@ -39,8 +39,9 @@ INTEGRATORS = {
 	"dop853": (_codegen.JB_DOP853, "ode"),
 	"RK45": (_codegen.JB_DP5, "ivp"),
 	"DOP853": (_codegen.JB_DOP853, "ivp"),
+	"RK23": (_codegen.JB_RK23, "ivp"),
 }
-NOT_REBUILT = ("RK23", "Radau", "BDF", "LSODA", "vode", "lsoda", "zvode")
+NOT_REBUILT = ("Radau", "BDF", "LSODA", "vode", "lsoda", "zvode")
 
 _used_module_names = set()
 
@@ -55,6 +56,8 @@ DENSE_MINIMUM_DENSITY = 0.1
 
 
 def _stage_rows(method, driver):
+	if method == _codegen.JB_RK23:
+		return 4
 	return 7 if method == _codegen.JB_DP5 else (16 if driver == _codegen.JB_DRV_IVP_DENSE else 13)
 
 
@@ -79,7 +82,7 @@ def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None
 	dense = 1 if driver == _codegen.JB_DRV_IVP_DENSE else 0
 	row_bytes = (n + 2) // 2 * 2 * 8
 	available = SHARED_MEMORY_PER_BLOCK - table_bytes - 8 * n - 64
-	last_stage = 6 if method == _codegen.JB_DP5 else 12      # K[S]: its row doubles as the staging row while k <= S
+	last_stage = {_codegen.JB_DP5: 6, _codegen.JB_DOP853: 12, _codegen.JB_RK23: 3}[method]      # K[S]: its row doubles as the staging row while k <= S
 
 	def teams(k, w):
 		"""trajectories per SM with k cached rows and w warps per trajectory"""
@@ -510,7 +513,7 @@ class jitcode:
 		As in the reference (_jitcode.py:560-626).
 
 		name : "dopri5" | "dop853" (Hairer's codes as scipy.integrate.ode runs them: every `integrate` call is a
-			fresh start that lands exactly on the target time) or "RK45" | "DOP853" (SciPy's solve_ivp stepper,
+			fresh start that lands exactly on the target time) or "RK45" | "DOP853" | "RK23" (SciPy's solve_ivp stepper,
 			persistent between calls; with `interpolate` the sample is the dense output of the step that passed
 			the target time, without it the last step is clipped to the target time).
 		nsteps : limit of step attempts per `integrate` call for the `ode` names.
@@ -520,7 +523,7 @@ class jitcode:
 			(engine-specific; see _storage_for, _choose_storage and _warp_configuration).
 		"""
 		if name in NOT_REBUILT:
-			raise NotImplementedError(f"The B200 engine only implements the explicit Dormand–Prince pairs (dopri5, dop853, RK45, DOP853), not {name!r}.")
+			raise NotImplementedError(f"The B200 engine only implements explicit Runge–Kutta pairs (dopri5, dop853, RK45, DOP853, RK23), not {name!r}.")
 		if name not in INTEGRATORS:
 			raise RuntimeError("There is no integrator with that name.")
 		method, backend = INTEGRATORS[name]

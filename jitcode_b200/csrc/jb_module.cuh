@@ -2,7 +2,7 @@
 //
 // A generated module defines, before including this file:
 //   struct jb_generated::Sys   N, NP, NB, NL, NT, Par, rhs(t, y, dy, par), tangent_index(k)
-//   JB_MODULE_METHOD           JB_DP5 | JB_DOP853
+//   JB_MODULE_METHOD           JB_DP5 | JB_DOP853 | JB_RK23
 //   JB_MODULE_DRIVER           JB_DRV_ODE | JB_DRV_IVP_DENSE | JB_DRV_IVP_LAND
 //   JB_MODULE_STORAGE          JB_STORE_REGISTERS | JB_STORE_GLOBAL | JB_STORE_WARP
 //   JB_MODULE_THREADS          threads per block of the integrate kernel
@@ -23,7 +23,7 @@
 namespace jb {
 
 using Sys = jb_generated::Sys;
-using Tab = std::conditional<JB_MODULE_METHOD == JB_DP5, DP5, DOP853>::type;
+using Tab = std::conditional<JB_MODULE_METHOD == JB_DP5, DP5, std::conditional<JB_MODULE_METHOD == JB_RK23, RK23, DOP853>::type>::type;
 constexpr int MODULE_MODE = JB_MODULE_STORAGE;
 constexpr bool MODULE_REG = MODULE_MODE == JB_STORE_REGISTERS;
 constexpr bool MODULE_WARP = MODULE_MODE == JB_STORE_WARP;

@@ -146,6 +146,10 @@ template <> struct Coef<DOP853> {
 	static __host__ __device__ constexpr double a(int s, int j) { return dop853::A[s][j]; }
 	static __host__ __device__ constexpr double c(int s) { return dop853::C[s]; }
 };
+template <> struct Coef<RK23> {
+	static __host__ __device__ constexpr double a(int s, int j) { return RK23::A[s][j]; }
+	static __host__ __device__ constexpr double c(int s) { return RK23::C[s]; }
+};
 
 struct Params {             // kernel argument block (by value)
 	int64_t B, ld;
@@ -451,7 +455,7 @@ struct Stepper : Store {
 			const double sum = this->sum([&](int i, auto r) {
 				double e = 0.0;
 				static_for<0, Tab::KROWS>([&](auto j) {
-					constexpr double w = DP5::E[j];
+					constexpr double w = Tab::E[j];
 					if constexpr (w != 0.0) e = fma(w, this->template k<j>(i, r), e);
 				});
 				const double sk = fma(rtol, fmax(fabs(this->y(i, r)), fabs(this->z(i, r))), atol(i));
@@ -875,12 +879,12 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 		if constexpr (DENSE) {
 			if (!interpolant) {
 				// ---- materialise the interpolant of the last step (rk.py:178-180, 693-712)
-				if constexpr (std::is_same<Tab, DP5>::value) {
+				if constexpr (!std::is_same<Tab, DOP853>::value) {
 					st.for_each([&](int i, auto r) {
-						static_for<0, 4>([&](auto p) {
+						static_for<0, Tab::NDENSE>([&](auto p) {
 							double q = 0.0;
-							static_for<0, 7>([&](auto j) {
-								constexpr double w = DP5::P[j][p];
+							static_for<0, Tab::KROWS>([&](auto j) {
+								constexpr double w = Tab::P[j][p];
 								if constexpr (w != 0.0) q = fma(w, st.template k<j>(i, r), q);
 							});
 							Qc(p).set(i, q);
@@ -926,11 +930,9 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			const bool restart = a.post != JB_POST_NONE;
 			st.for_each([&](int i, auto pass) {
 				double r;
-				if constexpr (std::is_same<Tab, DP5>::value) {
-					r = Qc(3)(i);
-					r = fma(r, x, Qc(2)(i));
-					r = fma(r, x, Qc(1)(i));
-					r = fma(r, x, Qc(0)(i));
+				if constexpr (!std::is_same<Tab, DOP853>::value) {
+					r = Qc(Tab::NDENSE - 1)(i);
+					static_for<1, Tab::NDENSE>([&](auto p) { r = fma(r, x, Qc(Tab::NDENSE - 1 - p)(i)); });
 					r = fma(hh * x, r, Oc(i));
 				} else {
 					r = 0.0;

@@ -42,6 +42,31 @@ struct DP5 {
 	};
 };
 
+// Bogacki–Shampine 3(2) ("RK23" of scipy.integrate.solve_ivp, scipy/integrate/_ivp/rk.py:183-276); published coefficients
+struct RK23 {
+	static constexpr int NSTAGE = 3;
+	static constexpr int KROWS = 4;
+	static constexpr int KROWS_DENSE = 4;
+	static constexpr int ERR_ORDER = 2;     // exponent -1/3
+	static constexpr int HAIRER_ORDER = 3;  // (no Hairer code of this order; only the solve_ivp drivers use the pair)
+	static constexpr int NDENSE = 3;        // cubic dense output
+	static constexpr bool ERR_NEEDS_FSAL = true;
+	JB_TABLE double C[4] = { 0.0, 1.0/2, 3.0/4, 1.0 };
+	JB_TABLE double A[4][4] = {
+		{ 0, 0, 0, 0 },
+		{ 1.0/2, 0, 0, 0 },
+		{ 0, 3.0/4, 0, 0 },
+		{ 2.0/9, 1.0/3, 4.0/9, 0 },
+	};
+	JB_TABLE double E[4] = { 5.0/72, -1.0/12, -1.0/9, 1.0/8 };
+	JB_TABLE double P[4][3] = {
+		{ 1.0, -4.0/3, 5.0/9 },
+		{ 0, 1.0, -2.0/3 },
+		{ 0, 4.0/3, -8.0/9 },
+		{ 0, -1.0, 1.0 },
+	};
+};
+
 struct DOP853 {
 	static constexpr int NSTAGE = 12;
 	static constexpr int KROWS = 13;

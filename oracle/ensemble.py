@@ -18,7 +18,7 @@ import numpy as np
 
 from . import wrappers
 
-RHS_PER_ATTEMPT = {"dopri5": 6, "RK45": 6, "dop853": 12, "DOP853": 12}
+RHS_PER_ATTEMPT = {"dopri5": 6, "RK45": 6, "dop853": 12, "DOP853": 12, "RK23": 3}
 
 
 class _CountingRhs:

@@ -40,6 +40,8 @@ VARIANTS = [  # label, integrator name, interpolate
 	("RK45_land", "RK45", False),
 	("DOP853", "DOP853", True),
 	("DOP853_land", "DOP853", False),
+	("RK23", "RK23", True),
+	("RK23_land", "RK23", False),
 ]
 
 def reference_backend(name, interpolate, f, **params):

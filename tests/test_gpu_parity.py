@@ -25,6 +25,7 @@ TOL = {"rtol": RTOL, "atol": ATOL}
 VARIANTS = [  # label in the golden files, integrator name, interpolate
 	("dopri5", "dopri5", True), ("dop853", "dop853", True), ("RK45", "RK45", True),
 	("RK45_land", "RK45", False), ("DOP853", "DOP853", True), ("DOP853_land", "DOP853", False),
+	("RK23", "RK23", True), ("RK23_land", "RK23", False),
 ]
 
 
@@ -73,7 +74,8 @@ def test_y1_golden(golden, label, name, interpolate):
 	ODE.set_initial_value(W.FHN_Y0, 0.0)
 	y1 = ODE.integrate(1.0)
 	assert y1.shape == (4,)
-	assert_allclose(y1, W.FHN_Y1, rtol=1e-4)
+	# reference tests/test_jitcode.py: rtol 1e-4 (:93), 1e-3 in the sweep over all integrators (:130), which RK23 needs
+	assert_allclose(y1, W.FHN_Y1, rtol=1e-3 if name == "RK23" else 1e-4)
 	assert_allclose(y1, g[f"y1_{label}"], rtol=1e-7)
 	ODE.set_integrator(name, interpolate=interpolate, **TOL)
 	ODE.set_initial_value(W.FHN_Y0, 0.0)
@@ -138,7 +140,7 @@ def test_roessler_network_golden(golden, storage):
 				assert_allclose(result, g[name][i], rtol=1e-6, atol=1e-8)
 
 
-@pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("RK45", True), ("RK45", False), ("dop853", True), ("DOP853", True)])
+@pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("RK45", True), ("RK45", False), ("dop853", True), ("DOP853", True), ("RK23", True)])
 def test_warp_storage_matches_global_storage(name, interpolate):
 	"""the two large-system kernels (thread per trajectory in HBM tiles / warp per trajectory in shared memory)
 	run the same controller: on a short, non-chaotic horizon they agree to rounding, with equal step counts."""
@@ -271,7 +273,7 @@ def test_lotka_volterra_invariant_large_ensemble():
 
 # ------------------------------------------------------------------ the wrappers' contract (reference tests/test_integrator_tools.py:33-69)
 
-@pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("dop853", True), ("RK45", True), ("RK45", False), ("DOP853", True), ("DOP853", False)])
+@pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("dop853", True), ("RK45", True), ("RK45", False), ("DOP853", True), ("DOP853", False), ("RK23", True), ("RK23", False)])
 def test_wrapper_contract(name, interpolate):
 	rng = np.random.default_rng(42)
 	ODE = make(W.fhn())
@@ -280,8 +282,8 @@ def test_wrapper_contract(name, interpolate):
 	ODE.set_initial_value(initial, 0.0)
 	assert_allclose(ODE.integrate(0), initial, rtol=1e-12)      # zero-length integration
 	ODE.set_initial_value(W.FHN_Y0, 0.0)                        # re-initialisation
-	assert_allclose(ODE.integrate(1.0), W.FHN_Y1, rtol=1e-4)
-	if not (name in ("RK45", "DOP853") and interpolate):
+	assert_allclose(ODE.integrate(1.0), W.FHN_Y1, rtol=1e-3 if name == "RK23" else 1e-4)
+	if not (name in ("RK45", "DOP853", "RK23") and interpolate):
 		with pytest.raises(ValueError):
 			ODE.integrate(0.5)                                  # backwards
 

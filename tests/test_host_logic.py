@@ -287,7 +287,7 @@ def test_no_integrator():
 
 def test_implicit_methods_are_refused():
 	ODE = jitcode(fhn_list(), verbose=False)
-	for name in ("LSODA", "vode", "BDF", "Radau"):
+	for name in ("LSODA", "vode", "lsoda", "BDF", "Radau"):
 		with pytest.raises(NotImplementedError):
 			ODE.set_integrator(name)
 

@@ -20,6 +20,7 @@ TOL = {"rtol": 1e-6, "atol": 1e-12}
 VARIANTS = [
 	("dopri5", "dopri5", True), ("dop853", "dop853", True), ("RK45", "RK45", True),
 	("RK45_land", "RK45", False), ("DOP853", "DOP853", True), ("DOP853_land", "DOP853", False),
+	("RK23", "RK23", True), ("RK23_land", "RK23", False),
 ]
 
 
@@ -53,7 +54,8 @@ def test_y1_golden(fhn, golden, label, name, interpolate):
 	backend = wrappers.make_backend(name, fhn.f, interpolate=interpolate)
 	backend.set_initial_value(W.FHN_Y0, 0.0)
 	y1 = backend.integrate(1.0)
-	assert_allclose(y1, W.FHN_Y1, rtol=1e-4)
+	# reference tests/test_jitcode.py: rtol 1e-4 (:93), 1e-3 in the sweep over all integrators (:130), which RK23 needs
+	assert_allclose(y1, W.FHN_Y1, rtol=1e-3 if name == "RK23" else 1e-4)
 	assert_allclose(y1, golden("fhn")[f"y1_{label}"], rtol=1e-9)
 
 
