@@ -324,7 +324,7 @@ def run_ours(args):
 		bytes_per_launch = 280.0 * n * own_attempts           # 35·n·8 B per trajectory-step
 		kernel_s = statistics.mean(kernel_ms) * 1e-3
 		achieved = bytes_per_launch / kernel_s / 1e9
-		storage_name = {0: "registers", 1: "global", 2: "warp", 3: "dense"}.get(module.info.storage)
+		storage_name = {0: "registers", 1: "global", 2: "warp", 3: "shared", 4: "dense"}.get(module.info.storage)
 		traffic_file = ROOT / "profiles" / "traffic.json"
 		traffic = None
 		if traffic_file.exists():

@@ -18,11 +18,11 @@ from sympy.printing.c import C99CodePrinter
 
 JB_DP5, JB_DOP853, JB_RK23 = 0, 1, 2
 JB_DRV_ODE, JB_DRV_IVP_DENSE, JB_DRV_IVP_LAND = 0, 1, 2
-JB_STORE_REGISTERS, JB_STORE_GLOBAL, JB_STORE_WARP = 0, 1, 2
+JB_STORE_REGISTERS, JB_STORE_GLOBAL, JB_STORE_WARP, JB_STORE_SHARED = 0, 1, 2, 3
 
 METHOD_NAMES = {JB_DP5: "JB_DP5", JB_DOP853: "JB_DOP853", JB_RK23: "JB_RK23"}
 DRIVER_NAMES = {JB_DRV_ODE: "JB_DRV_ODE", JB_DRV_IVP_DENSE: "JB_DRV_IVP_DENSE", JB_DRV_IVP_LAND: "JB_DRV_IVP_LAND"}
-STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL", JB_STORE_WARP: "JB_STORE_WARP"}
+STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL", JB_STORE_WARP: "JB_STORE_WARP", JB_STORE_SHARED: "JB_STORE_SHARED"}
 
 
 class CudaPrinter(C99CodePrinter):
@@ -197,6 +197,7 @@ struct Sys {{
 	static constexpr int TF_COUNT = {len(tf)}, TU_COUNT = {len(tu)};
 	static constexpr int NROW = {n_row};   // shared-memory row length (warp storage): position N holds 0
 	static constexpr int TEAM_WARPS = {int(team_warps)};   // warps that share one trajectory (warp storage)
+	static constexpr int THREADS = {int(threads)};   // threads per block (= row stride of shared storage)
 	typedef {tu_type} TU;
 	static __device__ __forceinline__ const TU *components(const void *tables)
 	{{

@@ -109,7 +109,7 @@ def _check(lib, code, what):
 class DenseInfo:
 	"""what CudaEnsembleIntegrator users read from module.info"""
 	def __init__(self, n):
-		self.n, self.n_params, self.n_basic, self.n_lyap, self.storage = n, 0, n, 0, 3
+		self.n, self.n_params, self.n_basic, self.n_lyap, self.storage = n, 0, n, 0, 4
 		self.threads_per_block, self.shared_bytes = 256, 0
 
 

@@ -47,7 +47,8 @@ _used_module_names = set()
 
 
 SHARED_MEMORY_PER_BLOCK = 227 * 1024      # sm_100a: opt-in maximum of dynamic shared memory per block
-STORAGE_BY_NAME = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL, "warp": _codegen.JB_STORE_WARP, "dense": "dense"}
+STORAGE_BY_NAME = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL, "warp": _codegen.JB_STORE_WARP,
+		"shared": _codegen.JB_STORE_SHARED, "dense": "dense"}
 # The dense engine costs 4·n² flops per right-hand side and trajectory, the written-out form ≈ 40 per sine term:
 # measured on the reference's own example (examples/kuramoto_network.py: n = 100, 20 % density) the GEMM form is
 # 4.5× faster than the generated code, so it is chosen from 10 % density on.
@@ -61,11 +62,20 @@ def _stage_rows(method, driver):
 	return 7 if method == _codegen.JB_DP5 else (16 if driver == _codegen.JB_DRV_IVP_DENSE else 13)
 
 
+def _shared_threads(n, method, driver):
+	"""threads per block of shared storage: every thread keeps its trajectory's state and stages in shared memory"""
+	rows = 2 + _stage_rows(method, driver) + (1 if driver == _codegen.JB_DRV_IVP_DENSE else 0)
+	return min(256, SHARED_MEMORY_PER_BLOCK // (rows * n * 8) // 32 * 32)
+
+
 def _storage_for(n, method, driver):
-	"""registers while state + stages fit a thread's register file, else the tiled global workspace
-	(warp storage is chosen on top of this when the system vectorises well, see jitcode._module)."""
+	"""registers while state + stages fit a thread's register file; the block's shared memory while at least four
+	warps of trajectories fit it (mid-size systems: the stages stay on chip, 30 instead of 250 cycles away); else the
+	tiled global workspace (warp storage is chosen on top of this when the system vectorises well, see jitcode._module)."""
 	rows = _stage_rows(method, driver) + 3
-	return _codegen.JB_STORE_REGISTERS if rows * n <= 88 else _codegen.JB_STORE_GLOBAL
+	if rows * n <= 88:
+		return _codegen.JB_STORE_REGISTERS
+	return _codegen.JB_STORE_SHARED if _shared_threads(n, method, driver) >= 128 else _codegen.JB_STORE_GLOBAL
 
 
 def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None, team_warps=None):
@@ -316,7 +326,7 @@ class jitcode:
 
 	def _choose_storage(self, method, driver):
 		storage = _storage_for(self.n, method, driver)
-		if storage == _codegen.JB_STORE_GLOBAL and self.n >= 64:
+		if storage != _codegen.JB_STORE_REGISTERS and self.n >= 64:
 			plan = self._warp_plan()
 			if plan is not None and plan[0].efficiency >= 0.5:
 				if _warp_configuration(self.n, method, driver, plan[2].nbytes)[1] >= 128:
@@ -349,7 +359,9 @@ class jitcode:
 					self.generate_f_cuda()
 				statements = self._statements
 				if threads is None:
-					threads = 128 if storage == _codegen.JB_STORE_REGISTERS else 64
+					threads = {_codegen.JB_STORE_REGISTERS: 128, _codegen.JB_STORE_SHARED: _shared_threads(self.n, method, driver)}.get(storage, 64)
+				if storage == _codegen.JB_STORE_SHARED and not 32 <= threads <= _shared_threads(self.n, method, driver):
+					raise ValueError("Shared storage: the stages of that many trajectories do not fit one block's shared memory.")
 				if min_blocks is None and storage == _codegen.JB_STORE_GLOBAL:
 					min_blocks = 8      # 16 warps/SM at ≤ 128 registers: measured +60 % over 8 warps at 255 (latency-bound streaming)
 			source = _codegen.module_source(

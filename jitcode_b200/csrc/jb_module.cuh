@@ -27,6 +27,10 @@ using Tab = std::conditional<JB_MODULE_METHOD == JB_DP5, DP5, std::conditional<J
 constexpr int MODULE_MODE = JB_MODULE_STORAGE;
 constexpr bool MODULE_REG = MODULE_MODE == JB_STORE_REGISTERS;
 constexpr bool MODULE_WARP = MODULE_MODE == JB_STORE_WARP;
+constexpr bool MODULE_SHARED = MODULE_MODE == JB_STORE_SHARED;
+// thread-per-trajectory with the stages in shared memory: (Y, Z, K rows, y_old) × N × threads doubles per block
+constexpr size_t THREAD_SHARED_BYTES = MODULE_SHARED
+		? sizeof(double) * (size_t) (2 + Layout<Tab, JB_MODULE_DRIVER>::KR + (Layout<Tab, JB_MODULE_DRIVER>::DENSE ? 1 : 0)) * Sys::N * JB_MODULE_THREADS : 0;
 using ModuleLayout = Layout<Tab, JB_MODULE_DRIVER>;
 
 // ---- warp storage: shared memory of a block = [tables of the right-hand side][stage vectors of warp 0][of warp 1]…
@@ -75,6 +79,11 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
 			T::sync();
 		}
+	} else if constexpr (MODE == JB_STORE_SHARED) {
+		extern __shared__ __align__(16) double jb_smem[];
+		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+		if (b >= a.B) return;
+		run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b, jb_smem + threadIdx.x);
 	} else {
 		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 		if (b >= a.B) return;
@@ -235,7 +244,7 @@ int jb_get_info(jb_module_info *info)
 	info->state_scalars = jb::ModuleLayout::STATE_SCALARS;
 	info->work_vectors = jb::MODULE_MODE == JB_STORE_GLOBAL ? jb::ModuleLayout::WORK_VECTORS : 0;
 	info->threads_per_block = JB_MODULE_THREADS;
-	info->shared_bytes = (int32_t) jb::Shared::BYTES;
+	info->shared_bytes = (int32_t) (jb::MODULE_SHARED ? jb::THREAD_SHARED_BYTES : jb::Shared::BYTES);
 	return 0;
 }
 
@@ -307,7 +316,12 @@ int jb_integrate(const jb_integrate_args *x)
 		return jb::launched("jb_integrate");
 	}
 	const unsigned blocks = (unsigned) ((x->B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);
-	jb::jb_integrate_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, 0, (cudaStream_t) x->stream>>>(a);
+	if (jb::MODULE_SHARED) {
+		const cudaError_t err = cudaFuncSetAttribute((const void *) jb::jb_integrate_kernel<jb::MODULE_MODE>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) jb::THREAD_SHARED_BYTES);
+		if (err != cudaSuccess) return jb::fail((int) err, "reserving shared memory");
+	}
+	jb::jb_integrate_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, jb::THREAD_SHARED_BYTES, (cudaStream_t) x->stream>>>(a);
 	return jb::launched("jb_integrate");
 }
 

@@ -47,11 +47,13 @@ struct RVec {               // thread-private, scalarised into registers
 	__device__ __forceinline__ void set(int i, double x) { v[i] = x; }
 };
 
-struct GVec {               // one trajectory's column of a tile: element i at p[i*TILE]
+template <int STRIDE>
+struct StrideVec {          // element i at p[i*STRIDE]: consecutive threads touch consecutive words
 	double *p;
-	__device__ __forceinline__ double operator()(int i) const { return p[i * TILE]; }
-	__device__ __forceinline__ void set(int i, double x) const { p[i * TILE] = x; }
+	__device__ __forceinline__ double operator()(int i) const { return p[i * STRIDE]; }
+	__device__ __forceinline__ void set(int i, double x) const { p[i * STRIDE] = x; }
 };
+using GVec = StrideVec<TILE>;       // one trajectory's column of a tile in global memory
 
 struct SVec {               // contiguous vector: shared memory (warp storage) or one row of a (B, n) global array
 	double *p;
@@ -116,7 +118,8 @@ __device__ __forceinline__ void take(RVec<N> &dst, RVec<N> &src)
 #pragma unroll
 	for (int i = 0; i < N; ++i) dst.v[i] = src.v[i];
 }
-__device__ __forceinline__ void take(GVec &dst, GVec &src)
+template <int STRIDE>
+__device__ __forceinline__ void take(StrideVec<STRIDE> &dst, StrideVec<STRIDE> &src)
 {
 	double *const p = dst.p;
 	dst.p = src.p;
@@ -186,13 +189,13 @@ template <class Tab, int DRIVER> struct Layout {
 // ---------------------------------------------------------------------------------------------
 // calling the generated right-hand side
 
-// global: one out-of-line copy of the (large) right-hand side
-template <class Sys>
+// global / shared: one out-of-line copy of the (large) right-hand side
+template <class Sys, int STRIDE = TILE>
 __device__ __noinline__ void rhs_outlined(double t, const double *__restrict__ in, double *__restrict__ out,
 		const typename Sys::Par par)
 {
-	const GVec vi{const_cast<double *>(in)};
-	GVec vo{out};
+	const StrideVec<STRIDE> vi{const_cast<double *>(in)};
+	StrideVec<STRIDE> vo{out};
 	Sys::rhs(t, vi, vo, par);
 }
 // warp storage: one out-of-line copy of the vectorised right-hand side; threads read what other threads of their
@@ -221,14 +224,18 @@ __device__ __noinline__ void rhs_warp_outlined(double t, const double *__restric
 // compile-time constant where rows are cached in registers, otherwise a dummy).
 
 template <class Sys, class Tab, int DRIVER, int MODE>
-struct ThreadStore {        // one thread per trajectory: registers (MODE 0) or the caller's tiled workspace (MODE 1)
+struct ThreadStore {        // one thread per trajectory: registers (MODE 0), the caller's tiled workspace (MODE 1)
+	                            // or the block's shared memory (MODE 3: rows of one word per thread)
 	static constexpr int N = Sys::N;
 	using L = Layout<Tab, DRIVER>;
 	static constexpr bool REG = MODE == JB_STORE_REGISTERS;
+	static constexpr bool SHARED = MODE == JB_STORE_SHARED;
 	static constexpr bool WARP = false;
 	static constexpr int KR = L::KR;
 	static constexpr int UNR = REG ? (N > 0 ? N : 1) : 4;   // unroll factor of component loops
-	using Vec = typename std::conditional<REG, RVec<N>, GVec>::type;
+	static constexpr int STRIDE = SHARED ? Sys::THREADS : TILE;
+	static constexpr int ROWS = 2 + KR + (L::DENSE ? 1 : 0);    // shared storage: Y, Z, K rows, y_old
+	using Vec = typename std::conditional<REG, RVec<N>, StrideVec<STRIDE>>::type;
 	using IVec = GVec;      // persistent solver vectors in the caller's memory
 	using UVec = GVec;      // the caller's state and samples
 
@@ -266,7 +273,7 @@ struct ThreadStore {        // one thread per trajectory: registers (MODE 0) or 
 	template <int J> __device__ __forceinline__ void call(double t, const Vec &in)
 	{
 		if constexpr (REG) Sys::rhs(t, in, K[J], par);
-		else rhs_outlined<Sys>(t, in.p, K[J].p, par);
+		else rhs_outlined<Sys, STRIDE>(t, in.p, K[J].p, par);
 	}
 	template <int J> __device__ __forceinline__ void rhs_y(double t) { call<J>(t, Y); }
 	template <int J> __device__ __forceinline__ void rhs_z(double t) { call<J>(t, Z); }
@@ -705,6 +712,15 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	} else if constexpr (WARP) {
 		st.bind(smem);
 		st.for_each([&](int i, auto r) { st.set_y(i, r, Yc(i)); });
+	} else if constexpr (MODE == JB_STORE_SHARED) {
+		// rows of N × (threads per block) doubles in the block's shared memory; this thread's column starts at `smem`
+		constexpr int ROW = N * Sys::THREADS;
+		st.Y.p = smem;
+		st.Z.p = smem + ROW;
+#pragma unroll
+		for (int j = 0; j < ST::KR; ++j) st.K[j].p = smem + (2 + j) * ROW;
+		if constexpr (DENSE) st.YO.p = smem + (2 + ST::KR) * ROW;
+		st.for_each([&](int i, auto r) { st.set_y(i, r, Yc(i)); });
 	} else {
 		st.Y.p = Yc.p;
 		st.Z.p = a.work + off;
@@ -1010,8 +1026,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 #pragma unroll
 		for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
 	} else {
-		bool copy_back = WARP;
-		if constexpr (!WARP) copy_back = st.Y.p != Yc.p;
+		bool copy_back = WARP || MODE == JB_STORE_SHARED;
+		if constexpr (MODE == JB_STORE_GLOBAL) copy_back = st.Y.p != Yc.p;
 		if (copy_back) st.for_each([&](int i, auto r) { Yc.set(i, st.y(i, r)); });
 	}
 	if constexpr (IVP) {

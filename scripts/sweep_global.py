@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 import workloads as W
 from jitcode_b200 import jitcode, jitcode_lyap
 which = sys.argv[1]
-for threads, cap in [(64, 1), (64, 4), (64, 6), (64, 8), (64, 12), (64, 16), (128, 4), (128, 6), (32, 16), (32, 24)]:
+for storage, threads, cap in [("global", 64, 8), ("shared", 160, 1), ("shared", 128, 1), ("shared", 96, 1), ("shared", 64, 1), ("shared", 64, 2), ("shared", 32, 4)]:
 	for _ in (0,):
 		args = []
 		if which == "ro":
@@ -22,7 +22,7 @@ for threads, cap in [(64, 1), (64, 4), (64, 6), (64, 8), (64, 12), (64, 16), (12
 			B = 100_000
 			ODE = jitcode_lyap(W.fhn()["f_sym"], n_lyap=4, verbose=False, seed=1)
 			ODE.compile_cuda(extra_compile_args=args)
-			ODE.set_integrator("dopri5", threads=threads, min_blocks=cap)
+			ODE.set_integrator("dopri5", storage=storage, threads=threads, min_blocks=cap)
 			Y0 = torch.as_tensor(W.fhn_lyap_ensemble(B)).cuda()
 			init = lambda: ODE.set_initial_value(Y0, 0.0)
 			run = lambda: ODE.integrate_many(np.arange(1, 21) * 10.0)
@@ -33,4 +33,4 @@ for threads, cap in [(64, 1), (64, 4), (64, 6), (64, 8), (64, 12), (64, 16), (12
 			e0.record(); run(); e1.record(); torch.cuda.synchronize()
 			best = min(best, e0.elapsed_time(e1))
 		acc, rej = ODE.step_counts()
-		print(f"{which} cap={cap} threads={threads} {best:9.2f} ms {(acc+rej)/best*1e3:.3e} steps/s", flush=True)
+		print(f"{which} {storage} cap={cap} threads={threads} {best:9.2f} ms {(acc+rej)/best*1e3:.3e} steps/s", flush=True)

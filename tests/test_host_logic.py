@@ -160,6 +160,8 @@ def test_warp_module_builds():
 	assert module.info.threads_per_block % 32 == 0 and 0 < module.info.shared_bytes <= 227 * 1024
 	thread_module = ODE.compile_cuda(storage="global")
 	assert thread_module.info.storage == _codegen.JB_STORE_GLOBAL and thread_module.info.work_vectors == 8
+	lyap = jitcode_lyap(fhn_list(), n_lyap=4, verbose=False).compile_cuda()
+	assert lyap.info.storage == _codegen.JB_STORE_SHARED and lyap.info.work_vectors == 0 and lyap.info.shared_bytes == 9 * 20 * 160 * 8
 
 
 def test_module_builds_loads_and_exports_every_symbol():
@@ -243,7 +245,8 @@ def test_storage_choice():
 	from jitcode_b200._jitcode import _storage_for
 	assert _storage_for(2, _codegen.JB_DP5, _codegen.JB_DRV_ODE) == _codegen.JB_STORE_REGISTERS
 	assert _storage_for(8, _codegen.JB_DP5, _codegen.JB_DRV_IVP_DENSE) == _codegen.JB_STORE_REGISTERS
-	assert _storage_for(20, _codegen.JB_DP5, _codegen.JB_DRV_ODE) == _codegen.JB_STORE_GLOBAL
+	assert _storage_for(20, _codegen.JB_DP5, _codegen.JB_DRV_ODE) == _codegen.JB_STORE_SHARED      # 160 trajectories' stages per block
+	assert _storage_for(48, _codegen.JB_DP5, _codegen.JB_DRV_ODE) == _codegen.JB_STORE_GLOBAL
 	assert _storage_for(4, _codegen.JB_DOP853, _codegen.JB_DRV_IVP_DENSE) == _codegen.JB_STORE_REGISTERS
 	assert _storage_for(300, _codegen.JB_DP5, _codegen.JB_DRV_ODE) != _codegen.JB_STORE_REGISTERS
 
