@@ -118,7 +118,7 @@ typedef struct jb_integrate_args {
 	double  *work;            /* [work_vectors][n][ld]  scratch (global storage) */
 	double  *Yres;            /* [n][ld] state at the last sample time (required for JB_DRV_IVP_DENSE, else optional) */
 	double  *Yrec;            /* [n_times][n][ld] every sample, or NULL */
-	double  *lyap_rec;        /* [n_times][n_lyap or 1][ld] local exponents per sample, or NULL */
+	double  *lyap_rec;        /* [n_times * (n_lyap or 1)][ld] local exponents: one (tiled / row) vector per trajectory with entry (sample, exponent) at row sample * n_out + exponent, or NULL */
 	double  *lyap_acc;        /* [2][n_lyap or 1][ld] += sum and sum of squares of the local exponents of this launch, or NULL */
 	const double *proj;       /* [n_proj][n_basic] orthonormalised projection vectors (restricted), or NULL */
 	int32_t *status;          /* [B] enum jb_status, sticky: a failed trajectory is not advanced further */

@@ -363,11 +363,9 @@ class CudaEnsembleIntegrator:
 			out = self._current_rows()[None]
 		self._rows = out[-1]
 		if self.n_out:
-			lv = self.n_out * self.ld
-			lyaps = torch.empty((n_times, self.B, self.n_out), dtype=torch.float64, device=self.device)
-			for i in range(n_times):
-				self.module.unpack(lyap_rec[i*lv:(i+1)*lv].data_ptr(), lyaps[i].data_ptr(), self.B, self.n_out, self.ld, self.stream)
-			self.last_lyaps = lyaps
+			# one vector of n_times·n_out entries per trajectory → (B, n_times, n_out) with a single un-tiling
+			flat = self._unpack(lyap_rec, n_times * self.n_out)
+			self.last_lyaps = flat.view(self.B, n_times, self.n_out).permute(1, 0, 2)
 		self._check_failures()
 		if self._single:
 			out = out[:, 0]

@@ -617,6 +617,20 @@ def random_directions(B, n, generator=None, device="cpu"):
 	return vectors / vectors.norm(dim=1, keepdim=True)
 
 
+class _Generators:
+	"""one seeded torch generator per device: tangent vectors of a CUDA-resident ensemble are drawn on the GPU"""
+	def __init__(self, seed):
+		self.seed, self.generators = seed, {}
+
+	def on(self, device):
+		if self.seed is None:
+			return None
+		device = torch.device(device)
+		if device not in self.generators:
+			self.generators[device] = torch.Generator(device=device).manual_seed(self.seed)
+		return self.generators[device]
+
+
 class jitcode_lyap(jitcode):
 	"""
 	As `jitcode`, plus (_jitcode.py:671-779):
@@ -644,7 +658,7 @@ class jitcode_lyap(jitcode):
 		super().__init__(full, helpers=helpers, n=self.n_basic*(self._n_lyap+1), **kwargs)
 		self._n_basic_module = self.n_basic
 		self._n_lyap_module = self._n_lyap
-		self._generator = None if seed is None else torch.Generator().manual_seed(seed)
+		self._generators = _Generators(seed)
 
 	def _with_tangent_vectors(self, state):
 		if isinstance(state, dict):
@@ -656,8 +670,9 @@ class jitcode_lyap(jitcode):
 		if rows2.shape[1] != self.n_basic:
 			raise ValueError("The dimension of the initial value does not match the dimension of your differential equations.")
 		B = rows2.shape[0]
-		tangents = torch.cat([random_directions(B, self.n_basic, self._generator) for _ in range(self._n_lyap)], dim=1)
-		full = torch.cat([rows2.to(torch.float64), tangents.to(rows2.device)], dim=1)
+		generator = self._generators.on(rows2.device)
+		tangents = torch.cat([random_directions(B, self.n_basic, generator, rows2.device) for _ in range(self._n_lyap)], dim=1)
+		full = torch.cat([rows2.to(torch.float64), tangents], dim=1)
 		if single:
 			full = full[0]
 		return full if is_tensor else full.numpy()
@@ -772,7 +787,7 @@ class jitcode_transversal_lyap(jitcode, GroupHandler):
 		self._n_basic_module = n
 		self._n_lyap_module = 1
 		self._tangent_indices_module = list(self.tangent_indices)
-		self._generator = None if seed is None else torch.Generator().manual_seed(seed)
+		self._generators = _Generators(seed)
 
 	def set_initial_value(self, y, time=0.0):
 		if isinstance(y, dict):
@@ -786,7 +801,7 @@ class jitcode_transversal_lyap(jitcode, GroupHandler):
 		B = rows2.shape[0]
 		full = torch.empty((B, self.n), dtype=torch.float64, device=rows2.device)
 		full[:, self.main_indices] = rows2
-		full[:, self.tangent_indices] = random_directions(B, len(self.tangent_indices), self._generator).to(rows2.device)
+		full[:, self.tangent_indices] = random_directions(B, len(self.tangent_indices), self._generators.on(rows2.device), rows2.device)
 		if single:
 			full = full[0]
 		super().set_initial_value(full if is_tensor else full.numpy(), time)

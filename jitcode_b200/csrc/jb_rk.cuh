@@ -996,8 +996,9 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 				if (k >= n_out) break;
 				const double lyap = log(norms[k]) / dt_lyap;
 				if (a.lyap_rec && leader) {
-					if constexpr (WARP) a.lyap_rec[((int64_t) it * ld + b) * n_out + k] = lyap;
-					else a.lyap_rec[(int64_t) it * n_out * ld + tile_offset(b, n_out) + k * TILE] = lyap;
+					// one vector of n_times · n_out entries per trajectory, entry (it, k) at row it·n_out + k
+					if constexpr (WARP) a.lyap_rec[((int64_t) b * a.n_times + it) * n_out + k] = lyap;
+					else a.lyap_rec[tile_offset(b, a.n_times * n_out) + (int64_t) (it * n_out + k) * TILE] = lyap;
 				}
 				if (it >= a.lyap_discard) {
 					lyap_sum[k] += lyap;
