@@ -288,12 +288,12 @@ class jitcode:
 
 	def compile_cuda(self, extra_compile_args=None, extra_link_args=None, verbose=False, modulename=None, omp=None,
 			method=_codegen.JB_DP5, driver=_codegen.JB_DRV_ODE, storage=None, threads=None, kregs=None, min_blocks=None, team_warps=None):
-		if isinstance(storage, str):
-			storage = STORAGE_BY_NAME[storage]
 		"""
 		Compiles (or fetches from the cache) and loads the module for one integrator configuration
 		(counterpart of compile_C, _jitcode.py:367-417).  `set_integrator` calls this itself.
 		"""
+		if isinstance(storage, str):
+			storage = STORAGE_BY_NAME[storage]
 		if modulename is not None:
 			if modulename in _used_module_names:
 				raise NameError("Module name has already been used in this instance of Python.")
@@ -307,6 +307,8 @@ class jitcode:
 
 	compile_C = compile_cuda
 
+	blocked_rings = True      # warp storage: ring neighbourhoods served from register windows (_vectorise.ring_blockings)
+
 	def _warp_plan(self, team_warps=1):
 		"""the vectorised form of the right-hand side, printed for teams of `team_warps` warps per trajectory
 		(None if the system cannot be vectorised)."""
@@ -318,7 +320,7 @@ class jitcode:
 				try:
 					if not hasattr(self, "_plan_tree"):
 						self._plan_tree = _vectorise.make_plan(self._f_list, self.helpers, self.control_pars)
-					lines, tables, component_of = _vectorise.warp_statements(self._plan_tree, team_warps)
+					lines, tables, component_of = _vectorise.warp_statements(self._plan_tree, team_warps, self.blocked_rings)
 					self._plans[team_warps] = (self._plan_tree, lines, tables, component_of)
 				except NotImplementedError:
 					pass

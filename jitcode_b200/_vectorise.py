@@ -214,6 +214,28 @@ class Group:
 	def size(self):
 		return len(self.outs)
 
+	def reordered(self, order):
+		"""the same group with its statements in another order (place m holds what was statement order[m])."""
+		other = object.__new__(Group)
+		other.key, other.body, other.prefix = self.key, self.body, self.prefix
+		other.n_const, other.n_index = self.n_const, self.n_index
+		other.outs = [self.outs[m] for m in order]
+		other.consts = [[slot[m] for m in order] for slot in self.consts]
+		other.indices = [[slot[m] for m in order] for slot in self.indices]
+		other.loops = []
+		for loop in self.loops:
+			moved = object.__new__(Loop)
+			moved.symbol, moved.body, moved.prefix = loop.symbol, loop.body, loop.prefix
+			moved.n_const, moved.n_index = loop.n_const, loop.n_index
+			terms = [k for m in order for k in range(loop.start[m], loop.start[m+1])]
+			moved.start = [0]
+			for m in order:
+				moved.start.append(moved.start[-1] + loop.start[m+1] - loop.start[m])
+			moved.consts = [[slot[k] for k in terms] for slot in loop.consts]
+			moved.indices = [[slot[k] for k in terms] for slot in loop.indices]
+			other.loops.append(moved)
+		return other
+
 
 class Plan:
 	"""everything the code printer and the NumPy interpreter need."""
@@ -353,18 +375,77 @@ def _uniform(values):
 	return len(values) > 0 and all(v == values[0] for v in values)
 
 
-def component_positions(plan):
+def component_positions(plan, groups=None):
 	"""Where component i lives inside the kernel's vectors: the outputs of every group are made contiguous
 	(group after group, statement after statement), so that a group's lanes write — and, for neighbour
 	couplings, mostly read — consecutive shared-memory words.  The permutation costs nothing: every index
 	the right-hand side uses comes from the tables printed here; only loading and storing the caller's
 	state goes through it (Sys::component_of)."""
 	position = {}
-	for group in plan.groups:
+	for group in (plan.groups if groups is None else groups):
 		for out in group.outs:
 			position[out] = len(position)
 	assert sorted(position) == list(range(plan.n)), "every component needs exactly one equation"
 	return position
+
+
+# Blocked rings.  With statements dealt to the lanes round-robin (lane ℓ runs statements ℓ, ℓ+32, …), a lane that
+# sums its ring neighbours m±1 … m±D reads 2D words per statement and never reads a word twice.  If instead every
+# lane runs a BLOCK of consecutive ring elements (lane ℓ: elements ℓ·Q … ℓ·Q+Q−1, one per pass), the neighbourhoods
+# of its Q statements overlap: it reads the 2D+Q words of the block's surroundings once, keeps them in registers and
+# serves all its passes from there — the shared-memory traffic of the gather falls by 2D·Q/(2D+Q).  The words are
+# stored pass-major (place q·L + ℓ for element ℓ·Q + q, L lanes in use), so that at every step of the window the
+# lanes of a warp still read consecutive words.
+
+def _ring_split(size, team):
+	"""(lanes, passes) with lanes·passes = size, lanes ≤ team and at most a quarter more passes than the round-robin
+	order needs; None if the ring cannot be cut that way."""
+	least = -(-size // team)
+	for passes in range(max(2, least), least + max(1, least // 4) + 1):
+		if size % passes == 0 and size // passes <= team:
+			return size // passes, passes
+	return None
+
+
+def _blocked_order(size, lanes, passes):
+	"""place q·lanes + ℓ holds ring element ℓ·passes + q."""
+	return [(place % lanes) * passes + place // lanes for place in range(size)]
+
+
+def _bare_gather(loop):
+	return loop.n_index == 1 and all(_uniform(values) for values in loop.consts) and _paddable(loop)
+
+
+def ring_blockings(plan, team):
+	"""{group size: (lanes, passes)} for the sizes of groups that sum over ring neighbours of their own kind and gain
+	from the blocked order; every group of such a size is printed in that order."""
+	owner = {out: (g, m) for g, group in enumerate(plan.groups) for m, out in enumerate(group.outs)}
+	found = {}
+	for group in plan.groups:
+		split = _ring_split(group.size, team)
+		if split is None or group.size in found or min(group.outs) < 0:
+			continue
+		lanes, passes = split
+		for loop in group.loops:
+			if not _bare_gather(loop):
+				continue
+			targets = {owner[c][0] for c in loop.indices[0]}
+			if len(targets) != 1 or plan.groups[next(iter(targets))].size != group.size:
+				continue
+			size, popularity = group.size, {}
+			for m in range(size):
+				for k in range(loop.start[m], loop.start[m+1]):
+					d = (owner[loop.indices[0][k]][1] - m) % size
+					popularity[d] = popularity.get(d, 0) + 1
+			common = sorted(d for d, count in popularity.items() if count >= 0.6 * size)[:32]
+			if len(common) < 4:
+				continue
+			signed = [d if d <= size // 2 else d - size for d in common]
+			window = {divmod(q + d, passes) for q in range(passes) for d in signed}
+			carries = [carry for carry, _ in window]
+			if max(carries) - min(carries) < lanes and 4 * len(window) <= 3 * len(common) * (-(-size // team)):
+				found[size] = split
+	return found
 
 
 def _paddable(loop):
@@ -390,8 +471,11 @@ def _ell(values, start, size, width, pad):
 	return out
 
 
-def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team):
-	"""one variable-length sum of a group, in ELL form: all lanes run the same (unrolled) number of terms."""
+def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, blocked=None, prologue=None, base_of=None):
+	"""one variable-length sum of a group, in ELL form: all lanes run the same (unrolled) number of terms.
+	team: lanes that share the group's statements (lane ℓ runs statements ℓ, ℓ+team, …); blocked: passes per lane if
+	the group is printed in the blocked ring order (then team = lanes in use, see _ring_split); prologue: lines that
+	go in front of the loop over the passes."""
 	size = group.size
 	lengths = [loop.start[m+1] - loop.start[m] for m in range(size)]
 	width = max(lengths)
@@ -422,12 +506,23 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team):
 		# statement says which diagonals it really has.  Everything else stays in the padded pair table.
 		diagonals, lo, ring = [], 0, 0
 		gathered = [p for terms in per_statement for p in terms]
+		distance = None
 		if gathered and min(group.outs) >= 0:
-			lo, ring = min(gathered), max(gathered) - min(gathered) + 1
+			if blocked:
+				# ring coordinates instead of places: place q·team + ℓ of the gathered group holds element ℓ·blocked + q
+				spans = {base_of(p) for p in gathered}
+				if len(spans) == 1 and next(iter(spans))[1] == size:
+					lo, ring = next(iter(spans))[0], size
+					element = lambda place: (place % team) * blocked + place // team
+					distance = lambda m, p: (element(p - lo) - element(m)) % ring
+			else:
+				lo, ring = min(gathered), max(gathered) - min(gathered) + 1
+				distance = lambda m, p: (p - lo - m) % ring
+		if distance:
 			popularity = {}
 			for m, terms in enumerate(per_statement):
 				for p in terms:
-					d = (p - lo - m) % ring
+					d = distance(m, p)
 					popularity[d] = popularity.get(d, 0) + 1
 			diagonals = sorted(d for d, count in popularity.items() if count >= 0.6 * size)[:32]
 			if len(diagonals) < 4 or ring > 32767:
@@ -439,7 +534,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team):
 			for m, terms in enumerate(per_statement):
 				mask, rest, seen = 0, [], set()
 				for p in terms:
-					d = (p - lo - m) % ring
+					d = distance(m, p)
 					if d in where and d not in seen:
 						mask |= 1 << where[d]
 						seen.add(d)
@@ -478,8 +573,39 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team):
 				# the mask is split into two 16-bit table entries
 				low = tables.add_u([mask & 0xffff for mask in masks])
 				high = tables.add_u([mask >> 16 for mask in masks])
-				lines.append(f"\t\tconst unsigned present = JB_TU[{low} + m] | ((unsigned) JB_TU[{high} + m] << 16);")
-			for k, d in enumerate(diagonals):
+				if not blocked:
+					lines.append(f"\t\tconst unsigned present = JB_TU[{low} + m] | ((unsigned) JB_TU[{high} + m] << 16);")
+			if blocked:
+				# the window: every word any pass of this lane needs is read ONCE, in front of the passes, and added to the
+				# sums of all the passes that have it as a neighbour (registers: two partial sums per pass, no window array)
+				signed = [d if d <= ring // 2 else d - ring for d in diagonals]
+				tag = lambda number: f"{'m' if number < 0 else 'p'}{abs(number)}"
+				for c, values in enumerate(consts):
+					prologue.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
+				users = {}
+				for q in range(blocked):
+					for k, d in enumerate(signed):
+						users.setdefault(divmod(q + d, blocked), []).append((q, k))
+				for carry in sorted({carry for carry, _ in users}):
+					shifted = f"lane {'-' if carry < 0 else '+'} {abs(carry)}"
+					wrapped = f"{shifted} < 0 ? {shifted} + {team} : {shifted}" if carry < 0 else f"{shifted} >= {team} ? {shifted} - {team} : {shifted}"
+					prologue.append(f"\tconst int {name}_l{tag(carry)} = {wrapped if carry else 'lane'};")
+				for q in range(blocked):
+					prologue.append(f"\tdouble {name}_s{q}a = 0.0, {name}_s{q}b = 0.0;")
+					if not all_present:
+						prologue.append(f"\tconst unsigned {name}_present{q} = JB_TU[{low} + lane + {q * team}] | ((unsigned) JB_TU[{high} + lane + {q * team}] << 16);")
+				for count, ((carry, source), wanted) in enumerate(sorted(users.items())):
+					prologue.append("\t{")
+					prologue.append(f"\t\tconst double {name}_w = y({lo + source*team} + {name}_l{tag(carry)});")
+					for q, k in wanted:
+						guard = "" if all_present else f"if ({name}_present{q} & {1 << k}u) "
+						prologue.append(f"\t\t{guard}{name}_s{q}{'ab'[count % 2]} += {term.replace(reads, name + '_w')};")
+					prologue.append("\t}")
+				lines.append("\t\tswitch (pass) {      // a constant once the passes are unrolled")
+				for q in range(blocked):
+					lines.append(f"\t\tcase {q}: {name}_a = {name}_s{q}a; {name}_b = {name}_s{q}b; break;")
+				lines.append("\t\t}")
+			for k, d in enumerate([] if blocked else diagonals):
 				# first case: no thread of this pass wraps around the ring; second: all of them do (pass is a constant after unrolling)
 				index = (f"(({team} * pass + {team - 1} + {d} < {ring}) ? m + {d} : (({team} * pass + {d} >= {ring}) ? m + {d} - {ring} : "
 						f"(m + {d} >= {ring} ? m + {d} - {ring} : m + {d})))")
@@ -531,7 +657,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team):
 	lines.append("\t}")
 
 
-def warp_statements(plan, team_warps=1):
+def warp_statements(plan, team_warps=1, blocked_rings=True):
 	"""returns (lines of the body of Sys::rhs_warp, Tables, component_of) where component_of[q] is the
 	component stored at position q of the kernel's vectors; position n is a slot that always holds 0.
 	team_warps: how many warps share one trajectory (`lane` in the printed code is the rank within that team)."""
@@ -539,8 +665,12 @@ def warp_statements(plan, team_warps=1):
 	printer = CudaPrinter()
 	tables = Tables()
 	lines = []
-	position = component_positions(plan)
+	blockings = ring_blockings(plan, team) if blocked_rings else {}
+	groups = [group.reordered(_blocked_order(group.size, *blockings[group.size])) if group.size in blockings else group for group in plan.groups]
+	position = component_positions(plan, groups)
 	zero_slot = plan.n
+	spans = [(position[group.outs[0]], group.size) for group in groups]
+	base_of = lambda p: next(span for span in spans if span[0] <= p < span[0] + span[1])
 
 	def located(expr):
 		"""y(i) with a literal index → y(position of i)."""
@@ -595,24 +725,34 @@ def warp_statements(plan, team_warps=1):
 		flush()
 	assert not pending, "unresolvable temporaries"
 
-	for g, group in enumerate(plan.groups):
+	for g, group in enumerate(groups):
 		base = position[group.outs[0]]
-		lines.append(f"// group {g}: {group.size} statement(s), components at positions {base} … {base + group.size - 1}")
-		n_pass = (group.size + team - 1) // team
+		lanes, blocked = blockings.get(group.size, (team, None))
+		lines.append(f"// group {g}: {group.size} statement(s), components at positions {base} … {base + group.size - 1}"
+				+ (f"; blocked ring order, {lanes} lanes × {blocked} consecutive elements" if blocked else ""))
+		n_pass = (group.size + lanes - 1) // lanes
+		header, prologue = [], []
+		if blocked:
+			header.append(f"if (lane < {lanes}) {{")
 		if group.loops and n_pass <= 16:
 			# passes unrolled: every pass knows its own trip counts at compile time
-			lines.append("#pragma unroll")
-			lines.append(f"for (int pass = 0; pass < {n_pass}; ++pass) {{")
-			lines.append(f"\tconst int m = lane + {team} * pass;")
-			lines.append(f"\tif (m >= {group.size}) break;")
+			header.append("#pragma unroll")
+			header.append(f"for (int pass = 0; pass < {n_pass}; ++pass) {{")
+			header.append(f"\tconst int m = lane + {lanes} * pass;")
+			if not blocked:
+				header.append(f"\tif (m >= {group.size}) break;")
 		else:
-			lines.append(f"for (int m = lane; m < {group.size}; m += {team}) {{")
-			lines.append(f"\tconst int pass = m / {team}; (void) pass;")
+			header.append(f"for (int m = lane, pass = 0; m < {group.size}; m += {lanes}, ++pass) {{")
+			header.append("\t(void) pass;")
+		body, lines = lines, []
 		for loop in group.loops:
-			_print_loop(printer, loop, group, position, tables, lines, zero_slot, team)
+			_print_loop(printer, loop, group, position, tables, lines, zero_slot, lanes, blocked, prologue, base_of)
 		slot_preamble(group.prefix, group.consts, group.indices, "m", "\t")
 		lines.append(f"\tdy.set({base} + m, {printer.doprint(group.body)});")
 		lines.append("}")
+		if blocked:
+			lines.append("}")
+		lines = body + (header[:1] + prologue + header[1:] if blocked else header) + lines
 	helper_declarations = [f"double {symbol.name};" for symbol, _ in plan.helpers]
 	component_of = [None] * plan.n
 	for component, where in position.items():

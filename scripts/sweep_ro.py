@@ -9,21 +9,25 @@ T = 10.0
 N = next((int(a[2:]) for a in sys.argv[2:] if a.startswith("N=")), 100)
 system = W.roessler_network(N)
 Y0, pars = W.roessler_ensemble(B, N=N)
-Yd, Pd = torch.as_tensor(Y0).cuda(), torch.as_tensor(pars).cuda()
-N = 100
+Yd, Pd = (torch.as_tensor(Y0).cuda(), torch.as_tensor(pars).cuda()) if torch.cuda.is_available() else (None, None)
 configs = [("global", None, None)] + [("warp", k, th) for k, th in [(0, None), (2, None), (4, None), (5, None), (6, None), (7, None), (7, 192), (7, 128), (6, 256), (5, 256), (4, 256), (0, 256)]]
 if len(sys.argv) > 2:
 	# kregs:threads[:team_warps]  (0 = default); "N=…" changes the network size
 	configs = []
 	for a in sys.argv[2:]:
-		if a.startswith("N="):
-			N = int(a[2:]); continue
+		if a.startswith("N=") or a.startswith("blocked="):
+			continue
 		parts = [int(x) for x in a.split(":")]
 		configs.append(("warp", parts[0] if parts[0] >= 0 else None, parts[1] or None, (parts[2] or None) if len(parts) > 2 else None))
 configs = [c if len(c) == 4 else (*c, None) for c in configs]
 ref = None
+blocked = next((bool(int(a[8:])) for a in sys.argv[2:] if a.startswith("blocked=")), True)
+compile_only = not torch.cuda.is_available()
 for storage, kregs, threads, team in configs:
 	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=system["n"], control_pars=system["control_pars"], verbose=False)
+	ODE.blocked_rings = blocked
+	if compile_only:
+		ODE.compile_cuda(storage=storage, kregs=kregs, threads=threads, team_warps=team); continue
 	try:
 		ODE.set_integrator("dopri5", rtol=1e-6, atol=1e-12, storage=storage, kregs=kregs, threads=threads, team_warps=team)
 	except Exception as error:
@@ -42,4 +46,4 @@ for storage, kregs, threads, team in configs:
 	acc, rej = ODE.step_counts()
 	if ref is None: ref = out
 	info = ODE.integrator.module.info
-	print(f"{storage:6s} team={team} kregs={kregs} threads={info.threads_per_block:4d} smem={info.shared_bytes:6d} {best:8.2f} ms {(acc+rej)/best*1e3:.3e} steps/s  maxdiff {float((out-ref).abs().max()):.2e}", flush=True)
+	print(f"blocked={int(blocked)} {storage:6s} team={team} kregs={kregs} threads={info.threads_per_block:4d} smem={info.shared_bytes:6d} {best:8.2f} ms {(acc+rej)/best*1e3:.3e} steps/s  maxdiff {float((out-ref).abs().max()):.2e}", flush=True)

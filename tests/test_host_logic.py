@@ -52,6 +52,15 @@ def evaluate(f, helpers, state, time=0.0):
 	return np.array([float(sympy.sympify(entry).subs(values).subs(subs)) for entry in f])
 
 
+def evaluate_large(f, helpers, state, time=0.0):
+	"""the same for large systems: exact replacement of the atoms instead of the general substitution."""
+	values = {y(i): sympy.Float(v) for i, v in enumerate(state)}
+	values[t] = sympy.Float(time)
+	for symbol, definition in _symbolic.sort_helpers(helpers):
+		values[symbol] = sympy.Float(float(definition.xreplace(values)))
+	return np.array([float(sympy.sympify(entry).xreplace(values)) for entry in f])
+
+
 @pytest.mark.parametrize("style", [fhn_list, lambda: fhn_generator, fhn_dict])
 def test_input_styles(style):
 	f, n = _symbolic.handle_input(style())
@@ -150,6 +159,33 @@ def test_vectoriser_plan_matches_direct_evaluation(name):
 	if name == "roessler":
 		assert [group.size for group in plan.groups] == [24, 24, 24] and plan.efficiency == 0.75
 		assert len(plan.helpers) == 1 and plan.helpers[0][1].loops[0].start == [0, 24]
+
+
+@pytest.mark.parametrize("name,team_warps", [("roessler100", 1), ("roessler100", 2), ("roessler50", 1), ("roessler24", 1), ("kuramoto40", 1), ("roessler200", 1), ("roessler40lyap", 1)])
+def test_printed_vectorised_code_on_host_lanes(name, team_warps, tmp_path):
+	"""the code printed for the GPU (blocked ring order with register windows, diagonals, pair tables, permuted
+	components), compiled for the host and run lane by lane, equals direct evaluation of the symbolic input."""
+	from jitcode_b200 import _vectorise
+	from host_lanes import evaluate_printed
+	if name.startswith("roessler"):
+		system, pars = W.roessler_network(int(name[8:].replace("lyap", ""))), [0.013]
+	else:
+		system, pars = W.kuramoto(int(name[8:])), []
+	f, n = _symbolic.handle_input(system["f_sym"], system["n"])
+	helpers = _symbolic.sort_helpers(system["helpers"])
+	if name.endswith("lyap"):       # tangent equations: neighbour sums with a coefficient
+		f, n = _symbolic.lyapunov_system(f, helpers, n, 1), 2 * n
+	plan = _vectorise.make_plan(f, helpers, system["control_pars"])
+	blockings = _vectorise.ring_blockings(plan, 32 * team_warps)
+	assert blockings == {("roessler40lyap", 1): {40: (20, 2)}, ("roessler100", 1): {100: (25, 4)}, ("roessler100", 2): {100: (50, 2)}, ("roessler50", 1): {50: (25, 2)}, ("roessler200", 1): {200: (25, 8)}}.get((name, team_warps), {})
+	state = np.random.default_rng(5).random(n)
+	subs = dict(zip(system["control_pars"], pars))
+	expected = evaluate_large([entry.xreplace(subs) for entry in f], [(s, d.xreplace(subs)) for s, d in helpers], state, time=0.7)
+	for blocked in (True, False):
+		lines, tables, component_of = _vectorise.warp_statements(plan, team_warps, blocked_rings=blocked)
+		assert ("switch (pass)" in "\n".join(lines)) == (blocked and bool(blockings))
+		got = evaluate_printed(lines, tables, component_of, len(pars), 0.7, state, pars, 32 * team_warps, 1 + len(helpers), tmp_path)
+		np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-14)
 
 
 def test_warp_module_builds():
