@@ -33,6 +33,7 @@ from sympy.core.function import AppliedUndef
 from ._codegen import CudaPrinter, _repeated_function_calls
 
 LOOP_MIN = 3        # a run of at least this many equally shaped terms in a sum becomes a loop
+FUSE_MAX = 4        # groups of equal size printed into one loop
 
 
 # ------------------------------------------------------------------ canonical trees
@@ -355,6 +356,17 @@ class Tables:
 		self.f64.extend(float(v) for v in values)
 		return offset
 
+	def shared_f64(self, values):
+		"""(sign, offset) of a table that holds these numbers or their negatives (ω_i of one equation, −ω_i of another):
+		equal addresses let the compiler load them once."""
+		values = [float(v) for v in values]
+		for sign in ("", "-"):
+			wanted = values if not sign else [-v for v in values]
+			for offset in range(0, len(self.f64) - len(values) + 1):
+				if self.f64[offset] == wanted[0] and self.f64[offset:offset + len(values)] == wanted:
+					return sign, offset
+		return "", self.add_f64(values)
+
 	def add_u(self, values, align=1):
 		while len(self.u) % align:
 			self.u.append(0)
@@ -657,7 +669,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 	lines.append("\t}")
 
 
-def warp_statements(plan, team_warps=1, blocked_rings=True):
+def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 	"""returns (lines of the body of Sys::rhs_warp, Tables, component_of) where component_of[q] is the
 	component stored at position q of the kernel's vectors; position n is a slot that always holds 0.
 	team_warps: how many warps share one trajectory (`lane` in the printed code is the rank within that team)."""
@@ -697,13 +709,14 @@ def warp_statements(plan, team_warps=1, blocked_rings=True):
 			if _uniform(values):
 				lines.append(f"{indent}const double {prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
 			else:
-				lines.append(f"{indent}const double {prefix}c{c} = JB_TF[{tables.add_f64(values)} + {where}];")
+				sign, offset = tables.shared_f64(values)
+				lines.append(f"{indent}const double {prefix}c{c} = {sign}JB_TF[{offset} + {where}];")
 		for j, values in enumerate(indices):
 			values = [position[v] for v in values]
 			if _uniform(values):
 				lines.append(f"{indent}const int {prefix}i{j} = {values[0]};")
-			elif where == "m" and _uniform([v - m for m, v in enumerate(values)]):
-				lines.append(f"{indent}const int {prefix}i{j} = {values[0]} + m;")      # consecutive positions: no table
+			elif where != "0" and _uniform([v - m for m, v in enumerate(values)]):
+				lines.append(f"{indent}const int {prefix}i{j} = {values[0]} + {where};")      # consecutive positions: no table
 			else:
 				lines.append(f"{indent}const int {prefix}i{j} = JB_TU[{tables.add_u(values)} + {where}];")
 
@@ -712,6 +725,12 @@ def warp_statements(plan, team_warps=1, blocked_rings=True):
 		lines.append("{")
 		for loop in group.loops:
 			count = loop.start[1]
+			if _bare_gather(loop):
+				# a plain sum may run in any order: by position, so that lanes read consecutive words (and need no table)
+				by_position = sorted(range(count), key=lambda k: position[loop.indices[0][k]])
+				loop = group.reordered([0]).loops[group.loops.index(loop)]
+				loop.indices = [[slot[k] for k in by_position] for slot in loop.indices]
+				loop.consts = [[slot[k] for k in by_position] for slot in loop.consts]
 			lines.append(f"\tdouble {loop.symbol.name}_acc = 0.0;")
 			lines.append(f"\tfor (int k = lane; k < {count}; k += {team}) {{")
 			slot_preamble(loop.prefix, loop.consts, loop.indices, "k", "\t\t")
@@ -725,30 +744,40 @@ def warp_statements(plan, team_warps=1, blocked_rings=True):
 		flush()
 	assert not pending, "unresolvable temporaries"
 
+	# groups of one size run in ONE loop over the lanes' statements (at most FUSE_MAX of them): what several of them
+	# read — the oscillator's own x, y, z in each of its three equations — is then loaded once
+	batches = OrderedDict()
 	for g, group in enumerate(groups):
-		base = position[group.outs[0]]
-		lanes, blocked = blockings.get(group.size, (team, None))
-		lines.append(f"// group {g}: {group.size} statement(s), components at positions {base} … {base + group.size - 1}"
-				+ (f"; blocked ring order, {lanes} lanes × {blocked} consecutive elements" if blocked else ""))
-		n_pass = (group.size + lanes - 1) // lanes
-		header, prologue = [], []
+		shape, part = (group.size, blockings.get(group.size, (team, None))), 0
+		while len(batches.get((shape, part), ())) >= (FUSE_MAX if fuse_groups else 1):
+			part += 1
+		batches.setdefault((shape, part), []).append((g, group))
+	for ((size, (lanes, blocked)), _), members in batches.items():
+		n_pass = (size + lanes - 1) // lanes
+		header, prologue, stores = [], [], []
 		if blocked:
 			header.append(f"if (lane < {lanes}) {{")
-		if group.loops and n_pass <= 16:
+		if any(group.loops for _, group in members) and n_pass <= 16:
 			# passes unrolled: every pass knows its own trip counts at compile time
 			header.append("#pragma unroll")
 			header.append(f"for (int pass = 0; pass < {n_pass}; ++pass) {{")
 			header.append(f"\tconst int m = lane + {lanes} * pass;")
 			if not blocked:
-				header.append(f"\tif (m >= {group.size}) break;")
+				header.append(f"\tif (m >= {size}) break;")
 		else:
-			header.append(f"for (int m = lane, pass = 0; m < {group.size}; m += {lanes}, ++pass) {{")
+			header.append(f"for (int m = lane, pass = 0; m < {size}; m += {lanes}, ++pass) {{")
 			header.append("\t(void) pass;")
 		body, lines = lines, []
-		for loop in group.loops:
-			_print_loop(printer, loop, group, position, tables, lines, zero_slot, lanes, blocked, prologue, base_of)
-		slot_preamble(group.prefix, group.consts, group.indices, "m", "\t")
-		lines.append(f"\tdy.set({base} + m, {printer.doprint(group.body)});")
+		for g, group in members:
+			base = position[group.outs[0]]
+			body.append(f"// group {g}: {group.size} statement(s), components at positions {base} … {base + group.size - 1}"
+					+ (f"; blocked ring order, {lanes} lanes × {blocked} consecutive elements" if blocked else ""))
+			for loop in group.loops:
+				_print_loop(printer, loop, group, position, tables, lines, zero_slot, lanes, blocked, prologue, base_of)
+			slot_preamble(group.prefix, group.consts, group.indices, "m", "\t")
+			lines.append(f"\tconst double {group.prefix}value = {printer.doprint(group.body)};")
+			stores.append(f"\tdy.set({base} + m, {group.prefix}value);")
+		lines.extend(stores)
 		lines.append("}")
 		if blocked:
 			lines.append("}")

@@ -15,17 +15,18 @@ if len(sys.argv) > 2:
 	# kregs:threads[:team_warps]  (0 = default); "N=…" changes the network size
 	configs = []
 	for a in sys.argv[2:]:
-		if a.startswith("N=") or a.startswith("blocked="):
+		if a.startswith("N=") or a.startswith("blocked=") or a.startswith("fuse="):
 			continue
 		parts = [int(x) for x in a.split(":")]
 		configs.append(("warp", parts[0] if parts[0] >= 0 else None, parts[1] or None, (parts[2] or None) if len(parts) > 2 else None))
 configs = [c if len(c) == 4 else (*c, None) for c in configs]
 ref = None
 blocked = next((bool(int(a[8:])) for a in sys.argv[2:] if a.startswith("blocked=")), True)
+fuse = next((bool(int(a[5:])) for a in sys.argv[2:] if a.startswith("fuse=")), True)
 compile_only = not torch.cuda.is_available()
 for storage, kregs, threads, team in configs:
 	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=system["n"], control_pars=system["control_pars"], verbose=False)
-	ODE.blocked_rings = blocked
+	ODE.blocked_rings, ODE.fuse_groups = blocked, fuse
 	if compile_only:
 		ODE.compile_cuda(storage=storage, kregs=kregs, threads=threads, team_warps=team); continue
 	try:
@@ -46,4 +47,4 @@ for storage, kregs, threads, team in configs:
 	acc, rej = ODE.step_counts()
 	if ref is None: ref = out
 	info = ODE.integrator.module.info
-	print(f"blocked={int(blocked)} {storage:6s} team={team} kregs={kregs} threads={info.threads_per_block:4d} smem={info.shared_bytes:6d} {best:8.2f} ms {(acc+rej)/best*1e3:.3e} steps/s  maxdiff {float((out-ref).abs().max()):.2e}", flush=True)
+	print(f"blocked={int(blocked)} fuse={int(fuse)} {storage:6s} team={team} kregs={kregs} threads={info.threads_per_block:4d} smem={info.shared_bytes:6d} {best:8.2f} ms {(acc+rej)/best*1e3:.3e} steps/s  maxdiff {float((out-ref).abs().max()):.2e}", flush=True)
