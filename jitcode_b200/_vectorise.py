@@ -34,6 +34,7 @@ from ._codegen import CudaPrinter, _repeated_function_calls
 
 LOOP_MIN = 3        # a run of at least this many equally shaped terms in a sum becomes a loop
 FUSE_MAX = 4        # groups of equal size printed into one loop
+SPREAD_OVER_BANKS = True
 
 
 # ------------------------------------------------------------------ canonical trees
@@ -483,6 +484,26 @@ def _ell(values, start, size, width, pad):
 	return out
 
 
+def _spread_over_banks(entries, width):
+	"""The terms of a sum may run in any order, and padding may sit anywhere: every statement's gathers are dealt
+	to the `width` slots of its pass so that the lanes which execute a slot together (half a warp per 64-bit
+	shared-memory wavefront) hit as few equal banks with different words as possible.  entries[lane]: positions."""
+	load = {}       # (slot, half-warp, bank) → words already read there
+	placed = []
+	for lane, wanted in enumerate(entries):
+		row, free = [None] * width, list(range(width))
+		for where in wanted:
+			def cost(k):
+				others = load.get((k, (lane % 32) // 16, where % 16), ())
+				return 0 if where in others else len(others)
+			best = min(free, key=lambda k: (cost(k), k))
+			free.remove(best)
+			row[best] = where
+			load.setdefault((best, (lane % 32) // 16, where % 16), set()).add(where)
+		placed.append(row)
+	return placed
+
+
 def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, blocked=None, prologue=None, base_of=None):
 	"""one variable-length sum of a group, in ELL form: all lanes run the same (unrolled) number of terms.
 	team: lanes that share the group's statements (lane ℓ runs statements ℓ, ℓ+team, …); blocked: passes per lane if
@@ -564,12 +585,12 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 			pass_width += pass_width % 2
 			bases.append(len(words) // 2)      # in 32-bit words
 			widths.append(pass_width // 2)
+			placed = _spread_over_banks([per_statement[m] for m in members], pass_width) if SPREAD_OVER_BANKS else [list(per_statement[m]) + [None] * (pass_width - lengths[m]) for m in members]
 			for kp in range(pass_width // 2):
 				for lane in range(team):
-					m = team*p + lane
 					for k in (2*kp, 2*kp + 1):
-						inside = m < size and k < lengths[m]
-						words.append(8 * (per_statement[m][k] if inside else zero_slot))
+						where = placed[lane][k] if lane < len(placed) else None
+						words.append(8 * (zero_slot if where is None else where))
 		offset = tables.add_u(words, align=2) if words else 0
 		for c, values in enumerate(consts):
 			lines.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
@@ -603,19 +624,21 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 					wrapped = f"{shifted} < 0 ? {shifted} + {team} : {shifted}" if carry < 0 else f"{shifted} >= {team} ? {shifted} - {team} : {shifted}"
 					prologue.append(f"\tconst int {name}_l{tag(carry)} = {wrapped if carry else 'lane'};")
 				for q in range(blocked):
-					prologue.append(f"\tdouble {name}_s{q}a = 0.0, {name}_s{q}b = 0.0;")
+					prologue.append(f"\tdouble {name}_s{q}a = 0.0, {name}_s{q}b = 0.0, {name}_s{q}c = 0.0, {name}_s{q}d = 0.0;")
 					if not all_present:
 						prologue.append(f"\tconst unsigned {name}_present{q} = JB_TU[{low} + lane + {q * team}] | ((unsigned) JB_TU[{high} + lane + {q * team}] << 16);")
 				for count, ((carry, source), wanted) in enumerate(sorted(users.items())):
 					prologue.append("\t{")
 					prologue.append(f"\t\tconst double {name}_w = y({lo + source*team} + {name}_l{tag(carry)});")
 					for q, k in wanted:
-						guard = "" if all_present else f"if ({name}_present{q} & {1 << k}u) "
-						prologue.append(f"\t\t{guard}{name}_s{q}{'ab'[count % 2]} += {term.replace(reads, name + '_w')};")
+						# a select on the VALUE keeps the selects off the dependent chain of additions
+						value = term.replace(reads, name + "_w")
+						value = value if all_present else f"(({name}_present{q} & {1 << k}u) ? {value} : 0.0)"
+						prologue.append(f"\t\t{name}_s{q}{'abcd'[count % 4]} += {value};")
 					prologue.append("\t}")
 				lines.append("\t\tswitch (pass) {      // a constant once the passes are unrolled")
 				for q in range(blocked):
-					lines.append(f"\t\tcase {q}: {name}_a = {name}_s{q}a; {name}_b = {name}_s{q}b; break;")
+					lines.append(f"\t\tcase {q}: {name}_a = {name}_s{q}a + {name}_s{q}c; {name}_b = {name}_s{q}b + {name}_s{q}d; break;")
 				lines.append("\t\t}")
 			for k, d in enumerate([] if blocked else diagonals):
 				# first case: no thread of this pass wraps around the ring; second: all of them do (pass is a constant after unrolling)
