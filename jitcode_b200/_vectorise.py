@@ -35,6 +35,7 @@ from ._codegen import CudaPrinter, _repeated_function_calls
 LOOP_MIN = 3        # a run of at least this many equally shaped terms in a sum becomes a loop
 FUSE_MAX = 4        # groups of equal size printed into one loop
 SPREAD_OVER_BANKS = True
+SUBTRACT_MISSING = True
 
 
 # ------------------------------------------------------------------ canonical trees
@@ -576,22 +577,51 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 				masks.append(mask)
 				remainder.append(rest)
 			per_statement = remainder
-		lengths = [len(terms) for terms in per_statement]
+		# Nearly complete rings (blocked order): testing a mask bit for every neighbour of every statement costs four
+		# instructions per term.  Where few neighbours are absent, every statement instead sums ALL the ring
+		# neighbours (no masks; what all passes of a lane have in common is added once) and the absent ones are read
+		# through a second pair table and subtracted.
+		missing = None
+		if diagonals and blocked and SUBTRACT_MISSING:
+			full = (1 << len(diagonals)) - 1
+			absent = sum(bin(full ^ mask).count("1") for mask in masks)
+			if 0 < absent <= 0.25 * len(diagonals) * size:
+				place = lambda e: (e % blocked) * team + e // blocked
+				missing = [[lo + place((element(m) + d) % ring) for k, d in enumerate(diagonals) if not mask >> k & 1] for m, mask in enumerate(masks)]
+				masks = [full] * size
 
-		words, bases, widths = [], [], []
-		for p in range(n_pass):
-			members = range(team*p, min(size, team*p + team))
-			pass_width = max(lengths[m] for m in members)
-			pass_width += pass_width % 2
-			bases.append(len(words) // 2)      # in 32-bit words
-			widths.append(pass_width // 2)
-			placed = _spread_over_banks([per_statement[m] for m in members], pass_width) if SPREAD_OVER_BANKS else [list(per_statement[m]) + [None] * (pass_width - lengths[m]) for m in members]
-			for kp in range(pass_width // 2):
-				for lane in range(team):
-					for k in (2*kp, 2*kp + 1):
-						where = placed[lane][k] if lane < len(placed) else None
-						words.append(8 * (zero_slot if where is None else where))
-		offset = tables.add_u(words, align=2) if words else 0
+		def pair_table(lists):
+			"""padded table of 16-bit byte offsets, two per 32-bit word, pass after pass → (offset, bases, pairs per pass)"""
+			words, bases, widths = [], [], []
+			for p in range(n_pass):
+				members = range(team*p, min(size, team*p + team))
+				pass_width = max(len(lists[m]) for m in members)
+				pass_width += pass_width % 2
+				bases.append(len(words) // 2)      # in 32-bit words
+				widths.append(pass_width // 2)
+				placed = _spread_over_banks([lists[m] for m in members], pass_width) if SPREAD_OVER_BANKS else [list(lists[m]) + [None] * (pass_width - len(lists[m])) for m in members]
+				for kp in range(pass_width // 2):
+					for lane in range(team):
+						for k in (2*kp, 2*kp + 1):
+							where = placed[lane][k] if lane < len(placed) else None
+							words.append(8 * (zero_slot if where is None else where))
+			return (tables.add_u(words, align=2), bases, widths) if words else None
+
+		def print_pairs(table, first, second, sign):
+			offset, bases, widths = table
+			lines.append("\t{")
+			lines.append(f"\t\tconstexpr int pass_base[{n_pass}] = {{ {', '.join(map(str, bases))} }}, pass_pairs[{n_pass}] = {{ {', '.join(map(str, widths))} }};")
+			lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
+			lines.append("#pragma unroll")
+			lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
+			lines.append(f"\t\t\tconst unsigned pair = pairs[k * {team}];")
+			lines.append(f"\t\t\t{first} {sign}= {term.replace(reads, 'y.at(pair & 0xffffu)')};")
+			lines.append(f"\t\t\t{second} {sign}= {term.replace(reads, 'y.at(pair >> 16)')};")
+			lines.append("\t\t}")
+			lines.append("\t}")
+
+		extra_table = pair_table(per_statement)
+		missing_table = pair_table(missing) if missing else None
 		for c, values in enumerate(consts):
 			lines.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
 		term = printer.doprint(loop.body)
@@ -627,18 +657,25 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 					prologue.append(f"\tdouble {name}_s{q}a = 0.0, {name}_s{q}b = 0.0, {name}_s{q}c = 0.0, {name}_s{q}d = 0.0;")
 					if not all_present:
 						prologue.append(f"\tconst unsigned {name}_present{q} = JB_TU[{low} + lane + {q * team}] | ((unsigned) JB_TU[{high} + lane + {q * team}] << 16);")
+				shared_by_all = [key for key, wanted in users.items() if all_present and blocked > 1 and len(wanted) == blocked]
+				if shared_by_all:
+					prologue.append(f"\tdouble {name}_core_a = 0.0, {name}_core_b = 0.0, {name}_core_c = 0.0, {name}_core_d = 0.0;")
 				for count, ((carry, source), wanted) in enumerate(sorted(users.items())):
 					prologue.append("\t{")
-					prologue.append(f"\t\tconst double {name}_w = y({lo + source*team} + {name}_l{tag(carry)});")
-					for q, k in wanted:
-						# a select on the VALUE keeps the selects off the dependent chain of additions
-						value = term.replace(reads, name + "_w")
-						value = value if all_present else f"(({name}_present{q} & {1 << k}u) ? {value} : 0.0)"
-						prologue.append(f"\t\t{name}_s{q}{'abcd'[count % 4]} += {value};")
+					prologue.append(f"\t\tconst double {name}_w = {term.replace(reads, f'y({lo + source*team} + {name}_l{tag(carry)})')};")
+					if (carry, source) in shared_by_all:
+						prologue.append(f"\t\t{name}_core_{'abcd'[count % 4]} += {name}_w;")       # a neighbour of every pass of this lane
+					else:
+						for q, k in wanted:
+							# a select on the VALUE keeps the selects off the dependent chain of additions
+							value = f"{name}_w" if all_present else f"(({name}_present{q} & {1 << k}u) ? {name}_w : 0.0)"
+							prologue.append(f"\t\t{name}_s{q}{('ab' if all_present else 'abcd')[count % (2 if all_present else 4)]} += {value};")
 					prologue.append("\t}")
+				if shared_by_all:
+					prologue.append(f"\tconst double {name}_core = ({name}_core_a + {name}_core_b) + ({name}_core_c + {name}_core_d);")
 				lines.append("\t\tswitch (pass) {      // a constant once the passes are unrolled")
 				for q in range(blocked):
-					lines.append(f"\t\tcase {q}: {name}_a = {name}_s{q}a + {name}_s{q}c; {name}_b = {name}_s{q}b + {name}_s{q}d; break;")
+					lines.append(f"\t\tcase {q}: {name}_a = {name}_s{q}a + {name}_s{q}c; {name}_b = {name}_s{q}b + {name}_s{q}d{f' + {name}_core' if shared_by_all else ''}; break;")
 				lines.append("\t\t}")
 			for k, d in enumerate([] if blocked else diagonals):
 				# first case: no thread of this pass wraps around the ring; second: all of them do (pass is a constant after unrolling)
@@ -651,17 +688,11 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 				else:
 					lines.append(f"\t\tif (present & {1 << k}u) {accumulator} += {value};")
 			lines.append("\t}")
-		if words:
-			lines.append("\t{")
-			lines.append(f"\t\tconstexpr int pass_base[{n_pass}] = {{ {', '.join(map(str, bases))} }}, pass_pairs[{n_pass}] = {{ {', '.join(map(str, widths))} }};")
-			lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
-			lines.append("#pragma unroll")
-			lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
-			lines.append(f"\t\t\tconst unsigned pair = pairs[k * {team}];")
-			lines.append(f"\t\t\t{name}_c += {term.replace(reads, 'y.at(pair & 0xffffu)')};")
-			lines.append(f"\t\t\t{name}_d += {term.replace(reads, 'y.at(pair >> 16)')};")
-			lines.append("\t\t}")
-			lines.append("\t}")
+		if extra_table:
+			print_pairs(extra_table, f"{name}_c", f"{name}_d", "+")
+		if missing_table:
+			# absent ring neighbours were summed with all the others: taken out again
+			print_pairs(missing_table, f"{name}_c", f"{name}_d", "-")
 		lines.append(f"\tconst double {name} = ({name}_a + {name}_b) + ({name}_c + {name}_d);")
 		return
 
