@@ -36,6 +36,7 @@ LOOP_MIN = 3        # a run of at least this many equally shaped terms in a sum 
 FUSE_MAX = 4        # groups of equal size printed into one loop
 SPREAD_OVER_BANKS = True
 SUBTRACT_MISSING = True
+SIGNED_PAIRS = True
 
 
 # ------------------------------------------------------------------ canonical trees
@@ -590,6 +591,14 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 				missing = [[lo + place((element(m) + d) % ring) for k, d in enumerate(diagonals) if not mask >> k & 1] for m, mask in enumerate(masks)]
 				masks = [full] * size
 
+		# one table for both kinds where the offsets leave a bit for the sign: padded to the longest statement of a pass
+		# once, not once per kind
+		signed_pairs = bool(missing) and 8 * zero_slot < 32768 and SIGNED_PAIRS
+		negative = [set(terms) for terms in missing] if signed_pairs else [set()] * size
+		if signed_pairs:
+			per_statement = [list(plus) + list(minus) for plus, minus in zip(per_statement, missing)]
+			missing = None
+
 		def pair_table(lists):
 			"""padded table of 16-bit byte offsets, two per 32-bit word, pass after pass → (offset, bases, pairs per pass)"""
 			words, bases, widths = [], [], []
@@ -604,7 +613,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 					for lane in range(team):
 						for k in (2*kp, 2*kp + 1):
 							where = placed[lane][k] if lane < len(placed) else None
-							words.append(8 * (zero_slot if where is None else where))
+							words.append(8 * (zero_slot if where is None else where) | (0x8000 if where in negative[min(team*p + lane, size - 1)] else 0))
 			return (tables.add_u(words, align=2), bases, widths) if words else None
 
 		def print_pairs(table, first, second, sign):
@@ -615,8 +624,12 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 			lines.append("#pragma unroll")
 			lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
 			lines.append(f"\t\t\tconst unsigned pair = pairs[k * {team}];")
-			lines.append(f"\t\t\t{first} {sign}= {term.replace(reads, 'y.at(pair & 0xffffu)')};")
-			lines.append(f"\t\t\t{second} {sign}= {term.replace(reads, 'y.at(pair >> 16)')};")
+			if signed_pairs:
+				lines.append(f"\t\t\t{first} += jb::flip_sign({term.replace(reads, 'y.at(pair & 0x7fffu)')}, pair << 16);")
+				lines.append(f"\t\t\t{second} += jb::flip_sign({term.replace(reads, 'y.at((pair >> 16) & 0x7fffu)')}, pair);")
+			else:
+				lines.append(f"\t\t\t{first} {sign}= {term.replace(reads, 'y.at(pair & 0xffffu)')};")
+				lines.append(f"\t\t\t{second} {sign}= {term.replace(reads, 'y.at(pair >> 16)')};")
 			lines.append("\t\t}")
 			lines.append("\t}")
 

@@ -75,6 +75,12 @@ struct PVec {
 	__device__ __forceinline__ void set(int q, double x) const { p[comp[q]] = x; }
 };
 
+// v with its sign flipped where bit 31 of `word` is set (signed entries of the vectoriser's gather tables)
+__device__ __forceinline__ double flip_sign(double v, unsigned word)
+{
+	return __hiloint2double(__double2hiint(v) ^ (int) (word & 0x80000000u), __double2loint(v));
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

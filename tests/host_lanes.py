@@ -16,6 +16,7 @@ SOURCE = r"""
 static std::vector<double> totals, partial;
 static int call_index;
 namespace jb {{
+static inline double flip_sign(double v, unsigned word) {{ return (word & 0x80000000u) ? -v : v; }}
 template <int W> struct Team {{
 	static double sum(double v, double *)
 	{{
