@@ -188,6 +188,28 @@ def test_printed_vectorised_code_on_host_lanes(name, team_warps, tmp_path):
 		np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("rewiring,expected", [(0.0, "complete"), (0.1, "subtract"), (0.3, "masks")])
+def test_printed_ring_variants_on_host_lanes(rewiring, expected, tmp_path):
+	"""the three ways a blocked ring is summed: complete ring (no masks, no corrections), nearly complete (all
+	neighbours summed, absent ones subtracted through the signed pair table), ragged (a mask bit per neighbour)"""
+	from jitcode_b200 import _vectorise
+	from host_lanes import evaluate_printed
+	n = 64
+	A = W.small_world_network(np.random.default_rng(11), n, 8, rewiring)
+	kappa = sympy.Symbol("kappa")
+	f = [-0.3 * y(i) + kappa * sympy.Add(*[sympy.sin(y(j)) for j in range(n) if A[i, j]]) for i in range(n)]
+	plan = _vectorise.make_plan(f, [], [kappa])
+	assert _vectorise.ring_blockings(plan, 32) == {64: (32, 2)}
+	lines, tables, component_of = _vectorise.warp_statements(plan)
+	text = "\n".join(lines)
+	assert ("flip_sign" in text, "_present0" in text) == {"complete": (False, False), "subtract": (True, False), "masks": (False, True)}[expected]
+	assert text.count("sin(") < 40        # the sine of a neighbour is taken once per window element, not once per use
+	state = np.random.default_rng(5).random(n)
+	direct = evaluate_large([entry.xreplace({kappa: 0.7}) for entry in f], [], state)
+	got = evaluate_printed(lines, tables, component_of, 1, 0.0, state, [0.7], 32, 1, tmp_path)
+	np.testing.assert_allclose(got, direct, rtol=1e-12, atol=1e-14)
+
+
 def test_warp_module_builds():
 	system = W.roessler_network(100)
 	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=300, control_pars=system["control_pars"], verbose=False)
