@@ -799,6 +799,7 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 				loop.indices = [[slot[k] for k in by_position] for slot in loop.indices]
 				loop.consts = [[slot[k] for k in by_position] for slot in loop.consts]
 			lines.append(f"\tdouble {loop.symbol.name}_acc = 0.0;")
+			lines.append("#pragma unroll" if count <= 16 * team else "#pragma unroll 4")      # independent loads in flight, not one dependent load per trip
 			lines.append(f"\tfor (int k = lane; k < {count}; k += {team}) {{")
 			slot_preamble(loop.prefix, loop.consts, loop.indices, "k", "\t\t")
 			lines.append(f"\t\t{loop.symbol.name}_acc += {printer.doprint(loop.body)};")
