@@ -20,6 +20,20 @@ This module finds that structure:
 Helpers (e.g. a mean field Σ_j y(3j+2)) are evaluated cooperatively: their loops are spread over
 the lanes and reduced with shuffles; the scalar rest is computed redundantly by every lane.
 
+What the printer does beyond that, all of it measured on the B200 (profiles/):
+
+  * components are permuted so that the outputs of a group are contiguous (`component_positions`);
+  * bare neighbour sums Σ g(y[idx]) use 16-bit pre-scaled byte offsets, two per word, padded per pass
+    to compile-time trip counts, and dealt to their slots by shared-memory bank (`_spread_over_banks`);
+  * lattice-like sums need no table for the neighbours most statements share ("diagonals");
+  * rings whose size splits into lanes × passes are printed in BLOCKED order (`ring_blockings`): a lane runs
+    consecutive ring elements and reads their overlapping neighbourhoods once; nearly complete rings are
+    summed without masks and the absent neighbours subtracted through the (signed) pair table;
+  * groups of equal size share one loop, so that operands common to their equations are loaded once.
+
+`tests/host_lanes.py` compiles the printed code for the host and runs it lane after lane: the printer is
+tested on a machine without a GPU.
+
 `evaluate_plan` is a NumPy interpreter of the same plan, used by the CPU tests to check the
 vectoriser against direct evaluation of the symbolic input.
 """
