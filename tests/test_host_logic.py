@@ -210,6 +210,22 @@ def test_printed_ring_variants_on_host_lanes(rewiring, expected, tmp_path):
 	np.testing.assert_allclose(got, direct, rtol=1e-12, atol=1e-14)
 
 
+def test_warp_configuration_rule():
+	"""cached rows / threads / team size of a warp-storage module follow the measured rule"""
+	from jitcode_b200._jitcode import _warp_configuration
+	ode, dense = _codegen.JB_DRV_ODE, _codegen.JB_DRV_IVP_DENSE
+	assert _warp_configuration(300, _codegen.JB_DP5, ode, 3000) == (3, 384, 1)        # 12 resident warps suffice: more rows in registers
+	assert _warp_configuration(150, _codegen.JB_DP5, ode, 3000) == (7, 384, 1)
+	assert _warp_configuration(600, _codegen.JB_DP5, ode, 3000) == (3, 256, 1)        # shared memory limits: the most trajectories first
+	assert _warp_configuration(1500, _codegen.JB_DP5, ode, 3000)[2] == 8              # teams: one trajectory per 8 warps
+	kregs, threads, team = _warp_configuration(300, _codegen.JB_DP5, dense, 3000, kregs=0)
+	assert kregs == 0 and threads % 32 == 0 and team == 1
+	for n in (64, 150, 300, 600, 1500):
+		for method in (_codegen.JB_DP5, _codegen.JB_DOP853, _codegen.JB_RK23):
+			kregs, threads, team = _warp_configuration(n, method, ode, 3000)
+			assert threads % (32 * team) == 0 and threads <= 1024 and kregs >= 0
+
+
 def test_warp_module_builds():
 	system = W.roessler_network(100)
 	ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=300, control_pars=system["control_pars"], verbose=False)
