@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 #include "jb_rk.cuh"
@@ -89,6 +90,16 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 		if (b >= a.B) return;
 		run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b);
 	}
+}
+
+// lane refill for the register kernels (jb_rk.cuh, run_lanes): persistent warps, trajectories from a queue
+__device__ unsigned long long jb_queue[16];       // one counter per launch in flight (slots used round-robin)
+constexpr bool MODULE_REFILL = MODULE_MODE == JB_STORE_REGISTERS && JB_MODULE_DRIVER == JB_DRV_ODE;
+
+__global__ void __launch_bounds__(JB_MODULE_THREADS, JB_MODULE_MIN_BLOCKS)
+jb_integrate_refill_kernel(const __grid_constant__ Params a, const int slot)
+{
+	if constexpr (MODULE_REFILL) run_lanes<Sys, Tab>(a, jb_queue + slot);
 }
 
 // dY = f(t, Y): the batched counterpart of py_f (jitced_template.c:67-116)
@@ -313,6 +324,27 @@ int jb_integrate(const jb_integrate_args *x)
 		int blocks = 0;
 		if (const int err = jb::warp_grid(x->B, jb::Shared::BYTES, (const void *) jb::jb_integrate_kernel<jb::MODULE_MODE>, &blocks)) return err;
 		jb::jb_integrate_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, jb::Shared::BYTES, (cudaStream_t) x->stream>>>(a);
+		return jb::launched("jb_integrate");
+	}
+	if (jb::MODULE_REFILL && x->n_times == 1 && x->post == JB_POST_NONE && x->B >= 4 * JB_MODULE_THREADS && !std::getenv("JITCODE_B200_NO_LANE_REFILL")) {
+		// plain integrate(T) of a large ensemble: persistent warps whose lanes take trajectories from a queue
+		static int resident = 0;
+		if (resident == 0) {
+			int device = 0, sms = 0, per_sm = 0;
+			cudaError_t err = cudaGetDevice(&device);
+			if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+			if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb::jb_integrate_refill_kernel, JB_MODULE_THREADS, 0);
+			if (err != cudaSuccess || sms <= 0 || per_sm <= 0) return jb::fail((int) err, "querying the device");
+			resident = sms * per_sm;
+		}
+		static std::atomic<unsigned> next_slot{0};
+		const int slot = (int) (next_slot.fetch_add(1, std::memory_order_relaxed) % 16u);
+		void *queue = nullptr;
+		cudaError_t err = cudaGetSymbolAddress(&queue, jb::jb_queue);
+		if (err == cudaSuccess) err = cudaMemsetAsync(static_cast<unsigned long long *>(queue) + slot, 0, sizeof(unsigned long long), (cudaStream_t) x->stream);
+		if (err != cudaSuccess) return jb::fail((int) err, "resetting the trajectory queue");
+		const int64_t needed = (x->B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS;
+		jb::jb_integrate_refill_kernel<<<(unsigned) (needed < resident ? needed : resident), JB_MODULE_THREADS, 0, (cudaStream_t) x->stream>>>(a, slot);
 		return jb::launched("jb_integrate");
 	}
 	const unsigned blocks = (unsigned) ((x->B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);

@@ -1070,4 +1070,144 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+#ifndef JB_REFILL_LANES
+#define JB_REFILL_LANES 4      // idle lanes that start new trajectories together (measured: see DESIGN.md)
+#endif
+// Lane refill (register storage, Hairer's driver, one sample time, no post-step).  With one thread per trajectory
+// the lanes of a warp wait for the trajectory that needs most steps (Lotka–Volterra ensemble: 24 % of the lane
+// slots idle).  Here the warps are persistent and a lane whose trajectory has landed on T takes the next one from a
+// queue while its neighbours keep stepping.  Starting a trajectory (f(t, y), HINIT) is code the stepping lanes cannot
+// share, so idle lanes wait until REFILL of them can start together (or nobody is stepping).  The arithmetic of
+// a trajectory is exactly that of run_trajectory: the same Stepper calls in the same order.
+template <class Sys, class Tab>
+__device__ __forceinline__ void run_lanes(const Params &a, unsigned long long *queue)
+{
+	using Store = ThreadStore<Sys, Tab, JB_DRV_ODE, JB_STORE_REGISTERS>;
+	using ST = Stepper<Sys, Tab, JB_DRV_ODE, Store>;
+	using UVec = typename ST::UVec;
+	constexpr int N = Sys::N;
+	constexpr int S = Tab::NSTAGE;
+	constexpr unsigned FULL = 0xffffffffu;
+	constexpr int REFILL = JB_REFILL_LANES;
+	ST st;
+	st.rtol = a.rtol;
+	st.atol_s = a.atol;
+	st.atol_vec = a.atol_vec;
+	st.comp = nullptr;
+	const double T = a.times[0];
+	const int64_t nmax = a.nsteps > 0 ? a.nsteps : 100000;
+	const int lane = threadIdx.x & 31;
+	int64_t b = -1;             // the trajectory this lane integrates; −1: none
+	bool more = true;           // the queue may still hold trajectories
+	double t = 0.0, h = 0.0, hmax = 0.0, log_facold = 0.0;
+	bool reject = false, last = false;
+	int64_t nstep = 0, n_acc = 0, n_rej = 0;
+	int status = JB_OK;
+	while (true) {
+		const unsigned idle = __ballot_sync(FULL, b < 0);
+		const unsigned hungry = __ballot_sync(FULL, b < 0 && more);
+		if (idle == FULL && hungry == 0) break;
+		if (hungry != 0 && (__popc(hungry) >= REFILL || idle == FULL)) {
+			// ---- the idle lanes take the next trajectories of the queue (one atomic per warp) and start them
+			const int leader = __ffs(hungry) - 1;
+			unsigned long long base = 0;
+			if (lane == leader) base = atomicAdd(queue, (unsigned long long) __popc(hungry));
+			base = __shfl_sync(FULL, base, leader);
+			if (b < 0 && more) {
+				const int64_t mine = (int64_t) base + __popc(hungry & ((1u << lane) - 1u));
+				if (mine >= a.B) {
+					more = false;
+				} else {
+					status = a.status[mine];
+					t = a.t[mine];
+					if (status == JB_OK && T > t) {
+						b = mine;
+						const UVec Yc{a.Y + tile_offset(b, N)};
+#pragma unroll
+						for (int i = 0; i < N; ++i) st.Y.v[i] = Yc(i);
+#pragma unroll
+						for (int k = 0; k < Sys::NP; ++k) st.par.v[k] = a.P[tile_offset(b, Sys::NP) + k * TILE];
+						st.template rhs_y<0>(t);
+						hmax = a.max_step > 0.0 ? a.max_step : fabs(T - t);
+						if (a.first_step > 0.0) {
+							h = a.first_step;
+						} else {
+							// HINIT
+							const double dnf = st.weighted_sq([&](int i, auto r) { return st.template k<0>(i, r); });
+							const double dny = st.weighted_sq([&](int i, auto r) { return st.y(i, r); });
+							h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+							h = fmin(h, hmax);
+							st.euler_probe(h);
+							st.template rhs_z<1>(t + h);
+							const double der2 = sqrt(st.weighted_sq([&](int i, auto r) { return st.template k<1>(i, r) - st.template k<0>(i, r); })) / h;
+							const double der12 = fmax(fabs(der2), sqrt(dnf));
+							const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h) * 1e-3)
+									: pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
+							h = fmin(fmin(100.0 * fabs(h), h1), hmax);
+						}
+						log_facold = -9.210340371976182;      // facold = 1e-4
+						reject = last = false;
+						nstep = n_acc = n_rej = 0;
+					}
+					// else: nothing to integrate for this one; the lane asks again
+				}
+			}
+		}
+		if (b >= 0) {
+			// ---- one step attempt (the body of the loop of run_trajectory's JB_DRV_ODE branch)
+			bool finished = false;
+			if (nstep > nmax) { status = JB_TOO_MANY_STEPS; finished = true; }
+			else if (0.1 * fabs(h) <= fabs(t) * 2.3e-16) { status = JB_STEP_TOO_SMALL; finished = true; }
+			else if (!(h == h)) { status = JB_NONFINITE; finished = true; }
+			else {
+				if (t + 1.01 * h - T > 0.0) { h = T - t; last = true; }
+				++nstep;
+				const double err = st.attempt(t, h);
+				const double log_err = log(err);
+				if (err <= 1.0) {
+					double fac = exp(a.expo1 * log_err - a.beta * log_facold);
+					fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
+					double hnew = h / fac;
+					log_facold = fmax(log_err, -9.210340371976182);
+					++n_acc;
+					st.finish_accepted(t, h);
+					st.accept_y();
+					st.template fsal<0, S>();
+					t = last ? T : t + h;
+					if (fabs(hnew) > hmax) hnew = hmax;
+					if (reject) hnew = fmin(fabs(hnew), fabs(h));
+					reject = false;
+					if (last) finished = true;
+					else h = hnew;
+				} else {
+					if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
+						h = h / fmin(a.facc1, exp(a.expo1 * log_err) / a.safety);
+					else
+						h = h / a.facc1;
+					reject = true;
+					last = false;
+					++n_rej;
+				}
+			}
+			if (finished) {
+				const UVec Yc{a.Y + tile_offset(b, N)};
+#pragma unroll
+				for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
+				if (a.Yrec) {
+					const UVec rec{a.Yrec + tile_offset(b, N)};
+#pragma unroll
+					for (int i = 0; i < N; ++i) rec.set(i, st.Y.v[i]);
+				}
+				a.t[b] = t;
+				a.status[b] = status;
+				if (a.n_accepted) a.n_accepted[b] += n_acc;
+				if (a.n_rejected) a.n_rejected[b] += n_rej;
+				b = -1;
+			}
+		}
+	}
+}
+
+
 }  // namespace jb
