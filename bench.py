@@ -119,7 +119,7 @@ def cpu_baseline(wl, per_core):
 	cpu_run(wl, handle, min(n_sample, 2 * cores))     # warm the pool and the page cache
 	attempts, seconds, cores = cpu_run(wl, handle, n_sample)
 	return {"value": attempts / seconds, "unit": UNIT, "cores": cores, "kind": kind,
-			"sample": f"{n_sample} trajectories of the same ensemble, {wl['integrator']} via scipy.integrate.ode, t=0..{wl['T']:g}, {seconds:.1f} s"}
+			"sample": f"{n_sample} trajectories of the same ensemble, {wl['integrator']} via {'scipy.integrate.ode' if wl['integrator'] in ('dopri5', 'dop853') else 'scipy.integrate.solve_ivp steppers'}, t=0..{wl['T']:g}, {seconds:.1f} s"}
 
 
 def run_reference(args):
@@ -132,6 +132,8 @@ def run_reference(args):
 	from oracle import ensemble
 	cores = ensemble.available_cores()
 	wl = workload(args.workload, per_core * cores)
+	if args.integrator:
+		wl["integrator"] = args.integrator
 	handle, kind = cpu_reference_handle(wl["system"], wl["label"])
 	for _ in range(args.warmup):
 		cpu_run(wl, handle, min(len(wl["Y0"]), 4 * cores))
@@ -222,6 +224,8 @@ def run_ours(args):
 
 	B = args.trajectories
 	wl = workload(args.workload, B, seed_offset=1000 * rank)      # every rank integrates its own shard
+	if args.integrator:
+		wl["integrator"] = args.integrator
 	system = wl["system"]
 	n = system["n"]
 	dense = "sine_coupling" in system
@@ -394,6 +398,8 @@ def main():
 	parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
 	parser.add_argument("--workload", default="roessler", choices=["roessler", "lv", "fhn_lyap", "kuramoto"])
 	parser.add_argument("--trajectories", type=int, default=1 << 20, help="per GPU")
+	parser.add_argument("--integrator", default=None, choices=[None, "dopri5", "dop853", "RK45", "DOP853", "RK23"],
+			help="instead of the workload's own (dopri5, as in the reference's examples); RK45 = the same pair under solve_ivp's controller")
 	parser.add_argument("--storage", default=None, choices=[None, "registers", "global", "warp"])
 	parser.add_argument("--kregs", type=int, default=None)
 	parser.add_argument("--chunks", type=int, default=8, help="pieces of the host-resident ensemble in the end-to-end arm")
@@ -407,6 +413,8 @@ def main():
 	args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 	if args.cpu_sample_per_core is None:
 		args.cpu_sample_per_core = {"roessler": 2048, "lv": 16384, "fhn_lyap": 4096}.get(args.workload, 256)
+		if args.integrator in ("RK45", "DOP853", "RK23"):
+			args.cpu_sample_per_core = max(64, args.cpu_sample_per_core // 8)     # SciPy's solve_ivp steppers are Python: ≈ 10× slower per step
 	result = keep_stdout_for_the_result()
 	line = run_reference(args) if args.impl == "reference" else run_ours(args)
 	if line is not None:
