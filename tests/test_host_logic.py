@@ -210,6 +210,29 @@ def test_printed_ring_variants_on_host_lanes(rewiring, expected, tmp_path):
 	np.testing.assert_allclose(got, direct, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("n,neighbours,rewiring,team_warps,seed", [(33, 4, 0.1, 1, 1), (128, 12, 0.2, 1, 4), (250, 20, 0.1, 2, 5), (100, 40, 0.1, 1, 9)])
+def test_printed_code_on_varied_networks(n, neighbours, rewiring, team_warps, seed, tmp_path):
+	"""two equations per node (a weighted neighbour sum; a mean field through a helper) on small-world rings of various
+	sizes, degrees and raggedness, single warps and teams: printed code on host lanes ≡ the plan's interpreter"""
+	from jitcode_b200 import _vectorise
+	from host_lanes import evaluate_printed
+	A = W.small_world_network(np.random.default_rng(seed), n, neighbours, rewiring)
+	kappa, mean = sympy.symbols("kappa mean")
+	helpers = [(mean, sympy.Add(*[y(2*j + 1) for j in range(n)]) / n)]
+	f = []
+	for i in range(n):
+		f.append(-0.3 * y(2*i) + y(2*i + 1) + kappa * sympy.Add(*[1.5 * y(2*j) for j in range(n) if A[i, j]]))
+		f.append(0.1 * y(2*i) - 0.2 * y(2*i + 1) * mean)
+	f, dimension = _symbolic.handle_input(f, 2 * n)
+	plan = _vectorise.make_plan(f, _symbolic.sort_helpers(helpers), [kappa])
+	assert n in _vectorise.ring_blockings(plan, 32 * team_warps)
+	lines, tables, component_of = _vectorise.warp_statements(plan, team_warps)
+	state = np.random.default_rng(seed).random(dimension)
+	expected = _vectorise.evaluate_plan(plan, 0.3, state, [0.7])
+	got = evaluate_printed(lines, tables, component_of, 1, 0.3, state, [0.7], 32 * team_warps, 2, tmp_path)
+	np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-13)
+
+
 def test_warp_configuration_rule():
 	"""cached rows / threads / team size of a warp-storage module follow the measured rule"""
 	from jitcode_b200._jitcode import _warp_configuration
