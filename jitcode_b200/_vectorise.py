@@ -431,7 +431,7 @@ def _ring_split(size, team):
 	order needs; None if the ring cannot be cut that way."""
 	least = -(-size // team)
 	for passes in range(max(2, least), least + max(1, least // 4) + 1):
-		if size % passes == 0 and size // passes <= team:
+		if size % passes == 0 and 16 <= size // passes <= team:      # at least half a warp at work
 			return size // passes, passes
 	return None
 

@@ -210,7 +210,7 @@ def test_printed_ring_variants_on_host_lanes(rewiring, expected, tmp_path):
 	np.testing.assert_allclose(got, direct, rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("n,neighbours,rewiring,team_warps,seed", [(33, 4, 0.1, 1, 1), (128, 12, 0.2, 1, 4), (250, 20, 0.1, 2, 5), (100, 40, 0.1, 1, 9)])
+@pytest.mark.parametrize("n,neighbours,rewiring,team_warps,seed", [(36, 4, 0.1, 1, 1), (128, 12, 0.2, 1, 4), (250, 20, 0.1, 2, 5), (100, 40, 0.1, 1, 9)])
 def test_printed_code_on_varied_networks(n, neighbours, rewiring, team_warps, seed, tmp_path):
 	"""two equations per node (a weighted neighbour sum; a mean field through a helper) on small-world rings of various
 	sizes, degrees and raggedness, single warps and teams: printed code on host lanes ≡ the plan's interpreter"""
@@ -226,6 +226,7 @@ def test_printed_code_on_varied_networks(n, neighbours, rewiring, team_warps, se
 	f, dimension = _symbolic.handle_input(f, 2 * n)
 	plan = _vectorise.make_plan(f, _symbolic.sort_helpers(helpers), [kappa])
 	assert n in _vectorise.ring_blockings(plan, 32 * team_warps)
+	assert _vectorise._ring_split(33, 32) is None and _vectorise._ring_split(101, 32) is None     # 11 lanes × 3; a prime
 	lines, tables, component_of = _vectorise.warp_statements(plan, team_warps)
 	state = np.random.default_rng(seed).random(dimension)
 	expected = _vectorise.evaluate_plan(plan, 0.3, state, [0.7])
