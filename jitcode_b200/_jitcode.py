@@ -678,15 +678,25 @@ class jitcode_lyap(jitcode):
 		if rows2.shape[1] != self.n_basic:
 			raise ValueError("The dimension of the initial value does not match the dimension of your differential equations.")
 		B = rows2.shape[0]
+		# large host-resident ensembles: the tangent vectors are drawn where they are needed (100k × 16 normal deviates
+		# cost 25 ms on the host, none to speak of on the GPU); what `integrate` returns keeps the kind of the input
+		device = getattr(self.integrator, "device", None)
+		kind = None
+		if device is not None and not rows2.is_cuda and B >= 4096:
+			kind = "torch" if is_tensor else "numpy"
+			rows2 = rows2.to(device)
 		generator = self._generators.on(rows2.device)
 		tangents = torch.cat([random_directions(B, self.n_basic, generator, rows2.device) for _ in range(self._n_lyap)], dim=1)
 		full = torch.cat([rows2.to(torch.float64), tangents], dim=1)
 		if single:
 			full = full[0]
-		return full if is_tensor else full.numpy()
+		return (full if is_tensor or kind else full.numpy()), kind
 
 	def set_initial_value(self, y, time=0.0):
-		super().set_initial_value(self._with_tangent_vectors(y), time)
+		full, kind = self._with_tangent_vectors(y)
+		super().set_initial_value(full, time)
+		if kind:
+			self.integrator._out_kind = kind
 
 	def set_integrator(self, name, interpolate=None, **kwargs):
 		"""
@@ -719,7 +729,7 @@ class jitcode_lyap(jitcode):
 		if integrator._single:
 			lyaps = lyaps[:, 0]
 		if integrator._out_kind != "cuda":
-			lyaps = lyaps.cpu() if integrator._out_kind == "torch" else lyaps.cpu().numpy()
+			lyaps = integrator._to_host(lyaps)
 		return states[..., :self.n_basic], lyaps
 
 	@property
@@ -835,7 +845,7 @@ class jitcode_transversal_lyap(jitcode, GroupHandler):
 		if integrator._single:
 			lyaps = lyaps[:, 0]
 		if integrator._out_kind != "cuda":
-			lyaps = lyaps.cpu() if integrator._out_kind == "torch" else lyaps.cpu().numpy()
+			lyaps = integrator._to_host(lyaps)
 		return states[..., self.main_indices], lyaps
 
 	@property
