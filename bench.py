@@ -402,7 +402,7 @@ def main():
 			help="instead of the workload's own (dopri5, as in the reference's examples); RK45 = the same pair under solve_ivp's controller")
 	parser.add_argument("--storage", default=None, choices=[None, "registers", "global", "warp"])
 	parser.add_argument("--kregs", type=int, default=None)
-	parser.add_argument("--chunks", type=int, default=8, help="pieces of the host-resident ensemble in the end-to-end arm")
+	parser.add_argument("--chunks", type=int, default=None, help="pieces of the host-resident ensemble in the end-to-end arm (default: one per 256 MB of state, at most 8)")
 	parser.add_argument("--cpu-sample-per-core", type=int, default=None)
 	parser.add_argument("--no-cpu-baseline", action="store_true")
 	args = parser.parse_args()

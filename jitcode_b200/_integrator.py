@@ -390,12 +390,14 @@ class CudaEnsembleIntegrator:
 		"""element offset of trajectory b0 (a multiple of 32) in an array of `rows`-component vectors"""
 		return b0 * rows           # tiled: (b0/32)·rows·32; row layout: b0·rows
 
-	def integrate_streamed(self, initial_value, T, out, time=0.0, chunks=8):
+	def integrate_streamed(self, initial_value, T, out, time=0.0, chunks=None):
 		"""
 		`set_initial_value(initial_value, time)` followed by `integrate(T, out=out)` for an ensemble that lives in
 		(pinned) host memory, with the copies hidden behind the kernels: the batch is cut into `chunks` pieces; while
 		piece c is integrated, piece c+1 is uploaded and the result of piece c-1 is downloaded on separate streams.
 		initial_value, out : (B, n) float64 CPU tensors (pinned for truly asynchronous copies).  Returns `out`.
+		chunks : default one piece per 256 MB of state, at most 8 (measured: 2.5 GB of Rössler states gain from 8 pieces,
+		16 MB of Lotka–Volterra states lose 27 % against a single piece).
 		"""
 		if self.post != JB_POST_NONE:
 			raise NotImplementedError("integrate_streamed does not run Lyapunov post-steps.")
@@ -414,6 +416,8 @@ class CudaEnsembleIntegrator:
 		if self.sstate is not None:
 			self.sstate.zero_()
 		self._upload_parameters()
+		if chunks is None:
+			chunks = max(1, min(8, (8 * B * n) >> 28))
 		step = max(JB_TILE, (-(-B // max(1, chunks)) + JB_TILE - 1) // JB_TILE * JB_TILE)
 		bounds = [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
 		main = torch.cuda.current_stream(self.device)

@@ -602,7 +602,7 @@ class jitcode:
 			raise RuntimeError("You must call set_integrator first.")
 		return self.integrator.integrate_many(times)
 
-	def integrate_streamed(self, initial_value, target_time, out, time=0.0, chunks=8):
+	def integrate_streamed(self, initial_value, target_time, out, time=0.0, chunks=None):
 		"""`set_initial_value` + `integrate` for an ensemble in pinned host memory, uploads and downloads overlapped with
 		the kernels (see CudaEnsembleIntegrator.integrate_streamed)."""
 		if not isinstance(self.integrator, CudaEnsembleIntegrator):
