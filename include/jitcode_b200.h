@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define JB_ABI_VERSION 5
+#define JB_ABI_VERSION 6
 #define JB_TILE 32
 
 enum jb_method  { JB_DP5 = 0, JB_DOP853 = 1, JB_RK23 = 2 /* solve_ivp drivers only */ };
@@ -124,6 +124,10 @@ typedef struct jb_integrate_args {
 	int32_t *status;          /* [B] enum jb_status, sticky: a failed trajectory is not advanced further */
 	int64_t *n_accepted;      /* [B] += accepted steps, or NULL */
 	int64_t *n_rejected;      /* [B] += rejected step attempts, or NULL (a trajectory-step = accepted + rejected) */
+	unsigned long long *queue;/* [1] device scratch owned by the caller, or NULL: the counter from which persistent kernels draw
+	                             trajectories (lane refill of the register kernels, work queue of the warp-storage kernels).
+	                             One counter per stream with launches in flight; reset by jb_integrate itself on `stream`.
+	                             NULL selects the static distribution (one thread / one strided sequence per trajectory). */
 	void    *stream;          /* cudaStream_t */
 } jb_integrate_args;
 

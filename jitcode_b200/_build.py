@@ -10,6 +10,7 @@ or the shared object is missing, this raises.
 """
 
 import ctypes
+import fcntl
 import hashlib
 import os
 import shutil
@@ -19,7 +20,7 @@ from pathlib import Path
 PACKAGE_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PACKAGE_DIR / "csrc"
 INCLUDE_DIR = PACKAGE_DIR.parent / "include"
-JB_ABI_VERSION = 5
+JB_ABI_VERSION = 6
 JB_TILE = 32
 
 DEFAULT_COMPILE_ARGS = [
@@ -50,11 +51,25 @@ def header_digest():
 		_header_digest = digest.hexdigest()
 	return _header_digest
 
+_nvcc_version = None
+def nvcc_version():
+	"""release line of `nvcc --version` (part of the cache key: another toolkit must not reuse old binaries)."""
+	global _nvcc_version
+	if _nvcc_version is None:
+		try:
+			text = subprocess.run([find_nvcc(), "--version"], capture_output=True, text=True).stdout
+		except OSError:
+			text = ""
+		lines = [line.strip() for line in text.splitlines() if "release" in line or line.startswith("Build")]
+		_nvcc_version = " ".join(lines) or "unknown"
+	return _nvcc_version
+
 def module_key(source, compile_args):
 	digest = hashlib.sha256()
 	digest.update(source.encode())
 	digest.update("\0".join(compile_args).encode())
 	digest.update(header_digest().encode())
+	digest.update(nvcc_version().encode())
 	return digest.hexdigest()[:20]
 
 def compile_module(source, extra_compile_args=(), extra_link_args=(), verbose=False):
@@ -65,20 +80,32 @@ def compile_module(source, extra_compile_args=(), extra_link_args=(), verbose=Fa
 	target = directory / f"jb_{key}.so"
 	if target.exists():
 		return target
-	source_path = directory / f"jb_{key}.cu"
-	source_path.write_text(source)
-	tmp = directory / f"jb_{key}.{os.getpid()}.tmp.so"
-	cmd = [find_nvcc(), *args, "-shared", f"-I{INCLUDE_DIR}", f"-I{CSRC_DIR}", str(source_path), "-o", str(tmp), *extra_link_args]
-	if verbose:
-		cmd.insert(1, "-Xptxas=-v")
-		print(" ".join(cmd))
-	result = subprocess.run(cmd, capture_output=True, text=True)
-	if verbose:
-		print(result.stdout, result.stderr)
-	if result.returncode != 0:
-		raise RuntimeError(f"nvcc failed for {source_path}:\n{result.stderr[-4000:]}")
-	os.replace(tmp, target)
-	return target
+	# Several processes may want the same module at once (torchrun: every rank calls set_integrator).  One of them
+	# compiles while the others wait on a file lock and then find the finished shared object; source and binary are
+	# written under private names and renamed into place, so nobody ever reads a half-written file.
+	with open(directory / f"jb_{key}.lock", "w") as lock:
+		fcntl.flock(lock, fcntl.LOCK_EX)
+		try:
+			if target.exists():
+				return target
+			source_path = directory / f"jb_{key}.cu"
+			private_source = directory / f"jb_{key}.{os.getpid()}.tmp.cu"
+			private_source.write_text(source)
+			os.replace(private_source, source_path)
+			tmp = directory / f"jb_{key}.{os.getpid()}.tmp.so"
+			cmd = [find_nvcc(), *args, "-shared", f"-I{INCLUDE_DIR}", f"-I{CSRC_DIR}", str(source_path), "-o", str(tmp), *extra_link_args]
+			if verbose:
+				cmd.insert(1, "-Xptxas=-v")
+				print(" ".join(cmd))
+			result = subprocess.run(cmd, capture_output=True, text=True)
+			if verbose:
+				print(result.stdout, result.stderr)
+			if result.returncode != 0:
+				raise RuntimeError(f"nvcc failed for {source_path}:\n{result.stderr[-4000:]}")
+			os.replace(tmp, target)
+			return target
+		finally:
+			fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 # ------------------------------------------------------------------ ctypes view of include/jitcode_b200.h
@@ -105,6 +132,7 @@ class IntegrateArgs(ctypes.Structure):
 		("Yres", ctypes.c_void_p), ("Yrec", ctypes.c_void_p),
 		("lyap_rec", ctypes.c_void_p), ("lyap_acc", ctypes.c_void_p), ("proj", ctypes.c_void_p),
 		("status", ctypes.c_void_p), ("n_accepted", ctypes.c_void_p), ("n_rejected", ctypes.c_void_p),
+		("queue", ctypes.c_void_p),
 		("stream", ctypes.c_void_p),
 	]
 

@@ -146,6 +146,8 @@ class CudaEnsembleIntegrator:
 		self.lyap_acc = torch.zeros(2 * self.n_out * ld, **f64) if self.n_out else None
 		self._times_host = torch.empty(1, dtype=torch.float64).pin_memory()
 		self._pars_on_device = False
+		# the counter from which persistent kernels draw trajectories: one per integrator (its launches share a stream)
+		self.queue = torch.zeros(1, dtype=torch.int64, device=dev)
 
 	def _to_device_rows(self, array, width, what):
 		"""(B, width) float64 contiguous CUDA tensor from numpy / torch / list input; returns (tensor, kind, single)."""
@@ -299,6 +301,7 @@ class CudaEnsembleIntegrator:
 		a.proj = None if self.proj is None else self.proj.data_ptr()
 		a.status = self.status.data_ptr()
 		a.n_accepted, a.n_rejected = self.n_accepted.data_ptr(), self.n_rejected.data_ptr()
+		a.queue = None if self.queue is None else self.queue.data_ptr()
 		a.stream = self.stream
 		return a
 
@@ -316,6 +319,8 @@ class CudaEnsembleIntegrator:
 			raise RuntimeError("You must call set_initial_value first.")
 		self._upload_parameters()
 		times = [float(T) for T in times]
+		if any(later < earlier for earlier, later in zip(times, times[1:])):
+			raise ValueError("Sample times must not decrease. Cannot integrate backwards in time")
 		if self.driver != JB_DRV_IVP_DENSE and times and times[0] < self.time:
 			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
 		if len(times) == 1:

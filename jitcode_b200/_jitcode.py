@@ -619,6 +619,22 @@ class jitcode:
 		return self.integrator.step_counts()
 
 
+NORMS_WARNING = "Norms of perturbation vectors for Lyapunov exponents out of numerical bounds. You probably waited too long before renormalising and should call integrate with smaller intervals between steps (as renormalisations happen once with every call of integrate)."
+NORM_WARNING = "Norm of perturbation vector for Lyapunov exponent out of numerical bounds. You probably waited too long before renormalising and should call integrate with smaller intervals between steps (as renormalisations happen once with every call of integrate)."
+
+
+def _warn_if_not_finite(lyaps, message, stacklevel=3):
+	"""the reference warns when a tangent-vector norm is not finite (_jitcode.py:747-748, 890-891, 944-945); here the
+	norms stay on the device and the local exponents ln(norm)/Δt carry the same information."""
+	if lyaps is None or bool(torch.isfinite(lyaps).all().item()):
+		return
+	bad = (~torch.isfinite(lyaps)).any(dim=-1)                 # (B,) or (samples, B)
+	if bad.dim() == 2:
+		bad = bad.any(dim=0)
+	bad = bad.nonzero().flatten()
+	warn(f"{message} (trajectories: {bad[:8].tolist()}{' …' if bad.numel() > 8 else ''})", stacklevel=stacklevel)
+
+
 def random_directions(B, n, generator=None, device="cpu"):
 	"""B isotropic unit vectors of dimension n (random_direction of jitcxde_common, _jitcode.py:729,873)."""
 	vectors = torch.randn((B, n), dtype=torch.float64, generator=generator, device=device)
@@ -712,10 +728,23 @@ class jitcode_lyap(jitcode):
 		tangents = state[..., n:].reshape(*state.shape[:-1], k, n)
 		return state[..., :n], tangents
 
-	def integrate(self, *args, **kwargs):
+	_warning = NORMS_WARNING
+
+	def _local_exponents(self, integrator, target_time, time_before):
+		"""device tensor (B, n_out) of the local exponents of the call that just ended.  A call that does not advance
+		the time launches nothing: the reference then divides ln(norm) = ln(1) = 0 by Δt = 0 (_jitcode.py:771), i.e.
+		returns NaN with NumPy's warning — the same is returned here."""
+		if float(target_time) == time_before and integrator.driver == _codegen.JB_DRV_ODE:
+			warn("The target time equals the current time: the local Lyapunov exponents are 0/0.", stacklevel=3)
+			return torch.full((integrator.B, integrator.n_out), float("nan"), dtype=torch.float64, device=integrator.device)
+		_warn_if_not_finite(integrator.last_lyaps, self._warning, stacklevel=4)
+		return integrator.last_lyaps
+
+	def integrate(self, target_time, *args, **kwargs):
 		integrator = self.integrator
-		state = integrator.integrate(*args, **kwargs)
-		lyaps = integrator._export(integrator.last_lyaps)
+		time_before = integrator.t
+		state = integrator.integrate(target_time, *args, **kwargs)
+		lyaps = integrator._export(self._local_exponents(integrator, target_time, time_before))
 		basic, tangents = self._split(state)
 		return basic, lyaps, tangents
 
@@ -726,6 +755,7 @@ class jitcode_lyap(jitcode):
 		integrator.lyap_discard = discard
 		states = integrator.integrate_many(times, record_states)
 		lyaps = integrator.last_lyaps
+		_warn_if_not_finite(lyaps, self._warning)
 		if integrator._single:
 			lyaps = lyaps[:, 0]
 		if integrator._out_kind != "cuda":
@@ -746,6 +776,7 @@ class jitcode_restricted_lyap(jitcode_lyap):
 	"""
 
 	_post = JB_POST_LYAP_RESTRICTED
+	_warning = NORM_WARNING
 
 	def __init__(self, f_sym=(), vectors=(), **kwargs):
 		kwargs["n_lyap"] = 1
@@ -830,10 +861,14 @@ class jitcode_transversal_lyap(jitcode, GroupHandler):
 		kwargs.setdefault("nsteps", 0)
 		super().set_integrator(name, interpolate=True, **kwargs)
 
-	def integrate(self, *args, **kwargs):
+	_warning = NORM_WARNING
+	_local_exponents = jitcode_lyap._local_exponents
+
+	def integrate(self, target_time, *args, **kwargs):
 		integrator = self.integrator
-		state = integrator.integrate(*args, **kwargs)
-		lyap = integrator._export(integrator.last_lyaps)[..., 0]
+		time_before = integrator.t
+		state = integrator.integrate(target_time, *args, **kwargs)
+		lyap = integrator._export(self._local_exponents(integrator, target_time, time_before))[..., 0]
 		return state[..., self.main_indices], lyap
 
 	def integrate_many(self, times, discard=0):
@@ -841,6 +876,7 @@ class jitcode_transversal_lyap(jitcode, GroupHandler):
 		integrator = self.integrator
 		integrator.lyap_discard = discard
 		states = integrator.integrate_many(times)
+		_warn_if_not_finite(integrator.last_lyaps, self._warning)
 		lyaps = integrator.last_lyaps[..., 0]
 		if integrator._single:
 			lyaps = lyaps[:, 0]

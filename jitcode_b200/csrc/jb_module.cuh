@@ -75,10 +75,24 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 		using T = Team<Sys::TEAM_WARPS>;
 		const int team = T::index();
 		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) team * (Shared::ROWS * Sys::NROW + Shared::SCRATCH);
-		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
-		for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + team; b < a.B; b += stride) {
-			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
-			T::sync();
+		if (a.queue) {
+			// work queue: a team takes the next trajectory when it has finished its own (adaptive step counts differ)
+			double *const slot = mine + Shared::ROWS * Sys::NROW;      // the team's reduction scratch doubles as mailbox
+			while (true) {
+				if (T::rank() == 0) *reinterpret_cast<unsigned long long *>(slot) = atomicAdd(a.queue, 1ull);
+				T::sync();
+				const int64_t b = (int64_t) *reinterpret_cast<const unsigned long long *>(slot);
+				T::sync();
+				if (b >= a.B) break;
+				run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
+				T::sync();
+			}
+		} else {
+			const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
+			for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + team; b < a.B; b += stride) {
+				run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
+				T::sync();
+			}
 		}
 	} else if constexpr (MODE == JB_STORE_SHARED) {
 		extern __shared__ __align__(16) double jb_smem[];
@@ -92,14 +106,13 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 	}
 }
 
-// lane refill for the register kernels (jb_rk.cuh, run_lanes): persistent warps, trajectories from a queue
-__device__ unsigned long long jb_queue[16];       // one counter per launch in flight (slots used round-robin)
+// lane refill for the register kernels (jb_rk.cuh, run_lanes): persistent warps, trajectories from the caller's queue
 constexpr bool MODULE_REFILL = MODULE_MODE == JB_STORE_REGISTERS && JB_MODULE_DRIVER == JB_DRV_ODE;
 
 __global__ void __launch_bounds__(JB_MODULE_THREADS, JB_MODULE_MIN_BLOCKS)
-jb_integrate_refill_kernel(const __grid_constant__ Params a, const int slot)
+jb_integrate_refill_kernel(const __grid_constant__ Params a)
 {
-	if constexpr (MODULE_REFILL) run_lanes<Sys, Tab>(a, jb_queue + slot);
+	if constexpr (MODULE_REFILL) run_lanes<Sys, Tab>(a);
 }
 
 // dY = f(t, Y): the batched counterpart of py_f (jitced_template.c:67-116)
@@ -204,21 +217,45 @@ static int fail(int code, const char *what)
 	return code;
 }
 
+// what the launch code needs to know about the current device; queried once per device and process (the values never
+// change; a race between two host threads writes the same numbers twice)
+constexpr int MAX_DEVICES = 64;
+struct DeviceFacts { std::atomic<int> sm_count{0}, refill_blocks{0}; };
+static DeviceFacts device_facts[MAX_DEVICES];
+
+static int current_device_facts(DeviceFacts **facts)
+{
+	int device = 0;
+	cudaError_t err = cudaGetDevice(&device);
+	if (err != cudaSuccess || device < 0 || device >= MAX_DEVICES) return fail(err != cudaSuccess ? (int) err : JB_E_UNSUPPORTED, "querying the device");
+	DeviceFacts &f = device_facts[device];
+	if (f.sm_count.load(std::memory_order_acquire) == 0) {
+		int sms = 0;
+		err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+		if (err != cudaSuccess || sms <= 0) return fail((int) err, "querying the device");
+		f.sm_count.store(sms, std::memory_order_release);
+	}
+	*facts = &f;
+	return 0;
+}
+
 // persistent grid of the warp-storage kernels: one block per SM (its warps share the staged tables)
 static int warp_grid(int64_t B, size_t shared_bytes, const void *kernel, int *blocks)
 {
-	static int sm_count = 0;
-	if (sm_count == 0) {
-		int device = 0;
-		cudaError_t err = cudaGetDevice(&device);
-		if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
-		if (err != cudaSuccess) return fail((int) err, "querying the device");
-	}
+	DeviceFacts *facts = nullptr;
+	if (const int bad = current_device_facts(&facts)) return bad;
+	const int sm_count = facts->sm_count.load(std::memory_order_relaxed);
 	const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) shared_bytes);
 	if (err != cudaSuccess) return fail((int) err, "reserving shared memory");
 	const int64_t needed = (B + Shared::WARPS - 1) / Shared::WARPS;
 	*blocks = (int) (needed < sm_count ? needed : sm_count);
 	return 0;
+}
+
+static int reset_queue(unsigned long long *queue, cudaStream_t stream)
+{
+	const cudaError_t err = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
+	return err == cudaSuccess ? 0 : fail((int) err, "resetting the trajectory queue");
 }
 
 static int launched(const char *what)
@@ -320,31 +357,34 @@ int jb_integrate(const jb_integrate_args *x)
 	a.Yres = x->Yres; a.Yrec = x->Yrec; a.lyap_rec = x->lyap_rec; a.lyap_acc = x->lyap_acc;
 	a.proj = x->proj;
 	a.status = x->status; a.n_accepted = x->n_accepted; a.n_rejected = x->n_rejected;
+	a.queue = nullptr;
 	if (jb::MODULE_WARP) {
 		int blocks = 0;
 		if (const int err = jb::warp_grid(x->B, jb::Shared::BYTES, (const void *) jb::jb_integrate_kernel<jb::MODULE_MODE>, &blocks)) return err;
+		if (x->queue && x->B > (int64_t) blocks * jb::Shared::WARPS) {
+			// more trajectories than resident teams: teams draw them from the caller's counter
+			if (const int err = jb::reset_queue(x->queue, (cudaStream_t) x->stream)) return err;
+			a.queue = x->queue;
+		}
 		jb::jb_integrate_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, jb::Shared::BYTES, (cudaStream_t) x->stream>>>(a);
 		return jb::launched("jb_integrate");
 	}
-	if (jb::MODULE_REFILL && x->n_times == 1 && x->post == JB_POST_NONE && x->B >= 4 * JB_MODULE_THREADS && !std::getenv("JITCODE_B200_NO_LANE_REFILL")) {
-		// plain integrate(T) of a large ensemble: persistent warps whose lanes take trajectories from a queue
-		static int resident = 0;
+	if (jb::MODULE_REFILL && x->queue && x->n_times == 1 && x->post == JB_POST_NONE && x->B >= 4 * JB_MODULE_THREADS && !std::getenv("JITCODE_B200_NO_LANE_REFILL")) {
+		// plain integrate(T) of a large ensemble: persistent warps whose lanes take trajectories from the caller's queue
+		jb::DeviceFacts *facts = nullptr;
+		if (const int bad = jb::current_device_facts(&facts)) return bad;
+		int resident = facts->refill_blocks.load(std::memory_order_acquire);
 		if (resident == 0) {
-			int device = 0, sms = 0, per_sm = 0;
-			cudaError_t err = cudaGetDevice(&device);
-			if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-			if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb::jb_integrate_refill_kernel, JB_MODULE_THREADS, 0);
-			if (err != cudaSuccess || sms <= 0 || per_sm <= 0) return jb::fail((int) err, "querying the device");
-			resident = sms * per_sm;
+			int per_sm = 0;
+			const cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jb::jb_integrate_refill_kernel, JB_MODULE_THREADS, 0);
+			if (err != cudaSuccess || per_sm <= 0) return jb::fail((int) err, "querying the device");
+			resident = facts->sm_count.load(std::memory_order_relaxed) * per_sm;
+			facts->refill_blocks.store(resident, std::memory_order_release);
 		}
-		static std::atomic<unsigned> next_slot{0};
-		const int slot = (int) (next_slot.fetch_add(1, std::memory_order_relaxed) % 16u);
-		void *queue = nullptr;
-		cudaError_t err = cudaGetSymbolAddress(&queue, jb::jb_queue);
-		if (err == cudaSuccess) err = cudaMemsetAsync(static_cast<unsigned long long *>(queue) + slot, 0, sizeof(unsigned long long), (cudaStream_t) x->stream);
-		if (err != cudaSuccess) return jb::fail((int) err, "resetting the trajectory queue");
+		if (const int err = jb::reset_queue(x->queue, (cudaStream_t) x->stream)) return err;
+		a.queue = x->queue;
 		const int64_t needed = (x->B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS;
-		jb::jb_integrate_refill_kernel<<<(unsigned) (needed < resident ? needed : resident), JB_MODULE_THREADS, 0, (cudaStream_t) x->stream>>>(a, slot);
+		jb::jb_integrate_refill_kernel<<<(unsigned) (needed < resident ? needed : resident), JB_MODULE_THREADS, 0, (cudaStream_t) x->stream>>>(a);
 		return jb::launched("jb_integrate");
 	}
 	const unsigned blocks = (unsigned) ((x->B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);

@@ -175,6 +175,7 @@ struct Params {             // kernel argument block (by value)
 	const double *proj;
 	int32_t *status;
 	int64_t *n_accepted, *n_rejected;
+	unsigned long long *queue;     // caller-owned counter from which persistent kernels draw trajectories, or null
 };
 
 // persistent scalars of the IVP drivers, sstate[k*ld + b]
@@ -505,6 +506,24 @@ struct Stepper : Store {
 		if constexpr (!Tab::ERR_NEEDS_FSAL) this->template rhs_z<S>(t + h);
 	}
 
+	// Hairer's stiffness estimate (dopri5.f / dop853.f "STIFFNESS DETECTION"), evaluated on an accepted step before it
+	// is committed: ρ ≈ h·|f(t+h, y_new) − K[S-1]| / |y_new − g|, g = the input of the last stage (c = 1).  K[S] must
+	// hold f(t+h, y_new), Z = y_new.  g is recomputed (the check runs once in 1000 steps unless a suspicion is pending).
+	__device__ __forceinline__ void stiffness_sums(double h, double &stnum, double &stden)
+	{
+		this->sum2([&](int i, auto r, double &num, double &den) {
+			double acc = 0.0;
+			static_for<0, S - 1>([&](auto j) {
+				constexpr double a = Coef<Tab>::a(S - 1, j);
+				if constexpr (a != 0.0) acc = fma(a, this->template k<j>(i, r), acc);
+			});
+			const double dk = this->template k<S>(i, r) - this->template k<S - 1>(i, r);
+			const double dy = this->z(i, r) - fma(h, acc, this->y(i, r));
+			num = fma(dk, dk, num);
+			den = fma(dy, dy, den);
+		}, stnum, stden);
+	}
+
 	// Σ_i (v_i / (atol_i + rtol |Y_i|))², the weighted norms of both start-up rules
 	template <class F>
 	__device__ __forceinline__ double weighted_sq(F &&value)
@@ -519,6 +538,33 @@ struct Stepper : Store {
 	__device__ __forceinline__ void euler_probe(double h)
 	{
 		this->for_each([&](int i, auto r) { this->set_z(i, r, fma(h, this->template k<0>(i, r), this->y(i, r))); });
+	}
+};
+
+// Bookkeeping of Hairer's stiffness test for one call of the solver: it looks at every NSTIFF-th accepted step and
+// at every step while a suspicion is pending; 15 suspicious steps in a row end the call with IDID = −4 (which
+// ODE_wrapper.integrate, integrator_tools.py:137-140, turns into UnsuccessfulIntegration), 6 harmless ones clear it.
+struct StiffnessWatch {
+	static constexpr int NSTIFF = 1000;
+	int countdown, iasti, nonsti;
+	double hlamb;
+	__device__ __forceinline__ void reset() { countdown = NSTIFF; iasti = nonsti = 0; hlamb = 0.0; }
+	// called once per accepted step; true if the sums are wanted for this step
+	__device__ __forceinline__ bool due()
+	{
+		if (--countdown == 0) { countdown = NSTIFF; return true; }
+		return iasti > 0;
+	}
+	// returns true if the solver gives up
+	__device__ __forceinline__ bool judge(double h, double stnum, double stden, double limit)
+	{
+		if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
+		if (hlamb > limit) {
+			nonsti = 0;
+			return ++iasti == 15;
+		}
+		if (++nonsti == 6) iasti = 0;
+		return false;
 	}
 };
 
@@ -784,6 +830,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 				bool reject = false, last = false;
 				int64_t nstep = 0;
 				const int64_t nmax = a.nsteps > 0 ? a.nsteps : 100000;
+				StiffnessWatch stiff;
+				stiff.reset();
 				while (true) {
 					if (nstep > nmax) { status = JB_TOO_MANY_STEPS; break; }
 					if (0.1 * fabs(h) <= fabs(t) * 2.3e-16) { status = JB_STEP_TOO_SMALL; break; }
@@ -800,6 +848,11 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 						log_facold = fmax(log_err, -9.210340371976182);     // facold = max(err, 1e-4)
 						++n_acc;
 						st.finish_accepted(t, h);
+						if (stiff.due()) {
+							double stnum, stden;
+							st.stiffness_sums(h, stnum, stden);
+							if (stiff.judge(h, stnum, stden, Tab::STIFF_LIMIT)) { status = JB_STIFF; break; }
+						}
 						st.accept_y();
 						st.template fsal<0, S>();
 						t = last ? T : t + h;
@@ -1081,7 +1134,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 // share, so idle lanes wait until REFILL of them can start together (or nobody is stepping).  The arithmetic of
 // a trajectory is exactly that of run_trajectory: the same Stepper calls in the same order.
 template <class Sys, class Tab>
-__device__ __forceinline__ void run_lanes(const Params &a, unsigned long long *queue)
+__device__ __forceinline__ void run_lanes(const Params &a)
 {
 	using Store = ThreadStore<Sys, Tab, JB_DRV_ODE, JB_STORE_REGISTERS>;
 	using ST = Stepper<Sys, Tab, JB_DRV_ODE, Store>;
@@ -1104,6 +1157,8 @@ __device__ __forceinline__ void run_lanes(const Params &a, unsigned long long *q
 	bool reject = false, last = false;
 	int64_t nstep = 0, n_acc = 0, n_rej = 0;
 	int status = JB_OK;
+	StiffnessWatch stiff;
+	stiff.reset();
 	while (true) {
 		const unsigned idle = __ballot_sync(FULL, b < 0);
 		const unsigned hungry = __ballot_sync(FULL, b < 0 && more);
@@ -1112,7 +1167,7 @@ __device__ __forceinline__ void run_lanes(const Params &a, unsigned long long *q
 			// ---- the idle lanes take the next trajectories of the queue (one atomic per warp) and start them
 			const int leader = __ffs(hungry) - 1;
 			unsigned long long base = 0;
-			if (lane == leader) base = atomicAdd(queue, (unsigned long long) __popc(hungry));
+			if (lane == leader) base = atomicAdd(a.queue, (unsigned long long) __popc(hungry));
 			base = __shfl_sync(FULL, base, leader);
 			if (b < 0 && more) {
 				const int64_t mine = (int64_t) base + __popc(hungry & ((1u << lane) - 1u));
@@ -1149,8 +1204,14 @@ __device__ __forceinline__ void run_lanes(const Params &a, unsigned long long *q
 						log_facold = -9.210340371976182;      // facold = 1e-4
 						reject = last = false;
 						nstep = n_acc = n_rej = 0;
+						stiff.reset();
+					} else if (a.Yrec) {
+						// nothing to integrate (already at T, or failed earlier): the sample is the state as it stands,
+						// as in run_trajectory; the lane asks again
+						const UVec Yc{a.Y + tile_offset(mine, N)}, rec{a.Yrec + tile_offset(mine, N)};
+#pragma unroll
+						for (int i = 0; i < N; ++i) rec.set(i, Yc(i));
 					}
-					// else: nothing to integrate for this one; the lane asks again
 				}
 			}
 		}
@@ -1172,14 +1233,25 @@ __device__ __forceinline__ void run_lanes(const Params &a, unsigned long long *q
 					log_facold = fmax(log_err, -9.210340371976182);
 					++n_acc;
 					st.finish_accepted(t, h);
-					st.accept_y();
-					st.template fsal<0, S>();
-					t = last ? T : t + h;
-					if (fabs(hnew) > hmax) hnew = hmax;
-					if (reject) hnew = fmin(fabs(hnew), fabs(h));
-					reject = false;
-					if (last) finished = true;
-					else h = hnew;
+					bool gave_up = false;
+					if (stiff.due()) {
+						double stnum, stden;
+						st.stiffness_sums(h, stnum, stden);
+						gave_up = stiff.judge(h, stnum, stden, Tab::STIFF_LIMIT);
+					}
+					if (gave_up) {
+						status = JB_STIFF;
+						finished = true;
+					} else {
+						st.accept_y();
+						st.template fsal<0, S>();
+						t = last ? T : t + h;
+						if (fabs(hnew) > hmax) hnew = hmax;
+						if (reject) hnew = fmin(fabs(hnew), fabs(h));
+						reject = false;
+						if (last) finished = true;
+						else h = hnew;
+					}
 				} else {
 					if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
 						h = h / fmin(a.facc1, exp(a.expo1 * log_err) / a.safety);

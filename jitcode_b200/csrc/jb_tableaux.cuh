@@ -17,6 +17,7 @@ struct DP5 {
 	static constexpr int KROWS_DENSE = 7;   // no extra stages for dense output
 	static constexpr int ERR_ORDER = 4;     // error estimator order → exponent -1/5
 	static constexpr int HAIRER_ORDER = 5;  // iord of HINIT
+	static constexpr double STIFF_LIMIT = 3.25;   // dopri5.f: HLAMB > 3.25 counts as a sign of stiffness
 	static constexpr int NDENSE = 4;        // dense-output vectors persisted between calls
 	static constexpr bool ERR_NEEDS_FSAL = true;
 	JB_TABLE double C[7] = { 0.0, 1.0/5, 3.0/10, 4.0/5, 8.0/9, 1.0, 1.0 };
@@ -49,6 +50,7 @@ struct RK23 {
 	static constexpr int KROWS_DENSE = 4;
 	static constexpr int ERR_ORDER = 2;     // exponent -1/3
 	static constexpr int HAIRER_ORDER = 3;  // (no Hairer code of this order; only the solve_ivp drivers use the pair)
+	static constexpr double STIFF_LIMIT = 1e300;
 	static constexpr int NDENSE = 3;        // cubic dense output
 	static constexpr bool ERR_NEEDS_FSAL = true;
 	JB_TABLE double C[4] = { 0.0, 1.0/2, 3.0/4, 1.0 };
@@ -73,6 +75,7 @@ struct DOP853 {
 	static constexpr int KROWS_DENSE = 16;  // three extra stages for the 7th-order dense output
 	static constexpr int ERR_ORDER = 7;
 	static constexpr int HAIRER_ORDER = 8;
+	static constexpr double STIFF_LIMIT = 6.1;    // dop853.f
 	static constexpr int NDENSE = 7;
 	static constexpr bool ERR_NEEDS_FSAL = false;  // error uses K[0..11] only (Hairer evaluates it before f(t+h,y_new))
 };

@@ -315,6 +315,11 @@ class HairerDopri:
 			h = self._hinit(t, Y, K1, hmax, everyone)
 		facold = np.full(B, 1e-4)
 		reject = np.zeros(B, dtype=bool)
+		# stiffness detection (dopri5.f / dop853.f "STIFFNESS DETECTION": every NSTIFF = 1000 accepted steps, or while
+		# a suspicion is pending): h·|f(y_new) − f(last stage)| / |y_new − last stage input| estimates h·λ
+		iasti = np.zeros(B, dtype=np.int64)
+		nonsti = np.zeros(B, dtype=np.int64)
+		hlamb = np.zeros(B)
 		active = t < T
 		facc1, facc2 = 1.0/self.dfactor, 1.0/self.ifactor
 		dp5 = self.method == "dopri5"
@@ -369,14 +374,37 @@ class HairerDopri:
 				n_acc[a] += 1
 				if not dp5:
 					K[12][ok] = self._f(tp[ok] + hp[ok], Y_new[ok], a)
-				K1[a] = K[S-1][ok]
-				Y[a] = Y_new[ok]
-				t[a] = np.where(last[ok], T, tp[ok] + hp[ok])
-				hn = np.minimum(np.abs(hnew[ok]), hmax[a])
-				hn = np.where(reject[a], np.minimum(hn, np.abs(hp[ok])), hn)
+				check = (n_acc[a] % 1000 == 0) | (iasti[a] > 0)
+				if check.any():
+					c = np.flatnonzero(ok)[check]          # positions in p
+					w = a[check]
+					row = S - 2                            # the last proper stage: its input is y + h Σ a(row, j) K_j
+					A_row = DP5_A[row] if dp5 else self.co.A[row]
+					stage_input = Yp[c] + hp[c, None]*_combine(K[:, c], A_row, row)
+					stnum = np.sum((K[S-1][c] - K[row][c])**2, axis=-1)
+					stden = np.sum((Y_new[c] - stage_input)**2, axis=-1)
+					with np.errstate(divide="ignore", invalid="ignore"):
+						hlamb[w] = np.where(stden > 0, np.abs(hp[c])*np.sqrt(stnum/stden), hlamb[w])
+					stiff = hlamb[w] > (3.25 if dp5 else 6.1)
+					nonsti[w] = np.where(stiff, 0, nonsti[w] + 1)
+					iasti[w] = np.where(stiff, iasti[w] + 1, np.where(nonsti[w] == 6, 0, iasti[w]))
+				# IDID = −4 (scipy.integrate.ode: "problem is probably stiff (interrupted)"): the solver returns before it
+				# commits the step that raised the 15th suspicion — t and y stay where they were
+				gave_up = iasti[a] == 15
+				status[a[gave_up]] = 3
+				active[a[gave_up]] = False
+				keep = ~gave_up
+				a, ok_keep = a[keep], np.flatnonzero(ok)[keep]
+				K1[a] = K[S-1][ok_keep]
+				Y[a] = Y_new[ok_keep]
+				t[a] = np.where(last[ok_keep], T, tp[ok_keep] + hp[ok_keep])
+				hn = np.minimum(np.abs(hnew[ok_keep]), hmax[a])
+				hn = np.where(reject[a], np.minimum(hn, np.abs(hp[ok_keep])), hn)
 				reject[a] = False
 				h[a] = hn
-				active[a[last[ok]]] = False
+				active[a[last[ok_keep]]] = False
+				if getattr(self, "trace", None) is not None:
+					self.trace.append((t[a].copy(), hp[ok_keep].copy(), err[ok_keep].copy()))
 			r = p[~ok]
 			if len(r):
 				if dp5 or not self.verbatim_dop853_reject:
@@ -385,5 +413,7 @@ class HairerDopri:
 					h[r] = hp[~ok] * self.dfactor
 				reject[r] = True
 				n_rej[r] += (n_acc[r] >= 1)
+				if getattr(self, "trace_rejected", None) is not None:
+					self.trace_rejected.append((tp[~ok].copy(), hp[~ok].copy(), err[~ok].copy()))
 		return {"y": Y, "t": t, "status": status, "n_accepted": n_acc, "n_rejected": n_rej,
 				"n_attempts": nstep, "nfev": self.nfev.copy()}

@@ -256,3 +256,74 @@ def test_warp_storage_options(name, interpolate):
 		looped = np.stack([ODE.integrate(T) for T in times])
 		assert_allclose(results[storage], looped, rtol=1e-12, atol=1e-14)
 	assert_allclose(results["warp"], results["global"], rtol=1e-9, atol=1e-12)
+
+
+def _relaxation_system():
+	"""y0 relaxes towards cos(t) at rate lam (control parameter), y1 decays slowly: stiff for large lam"""
+	lam = sympy.Symbol("lam")
+	return {"f_sym": [-lam * (y(0) - sympy.cos(t)), -0.5 * y(1)], "helpers": [], "control_pars": [lam], "n": 2}
+
+
+@pytest.mark.parametrize("B,storage", [(40, None), (600, None), (40, "global"), (40, "shared")])
+def test_stiffness_detection(B, storage):
+	"""Hairer's stiffness test (dopri5.f: every 1000 accepted steps; 15 suspicious steps in a row → IDID −4 →
+	UnsuccessfulIntegration, integrator_tools.py:137-140), per trajectory: the stiff members of a mixed ensemble stop
+	where SciPy's dopri5 stops, the others arrive.  B = 600 takes the lane-refill kernel."""
+	from oracle import rk_numpy
+	system = _relaxation_system()
+	rates = np.where(np.arange(B) % 3 == 0, 1e4, 1e3)
+	Y0 = np.tile([0.0, 1.0], (B, 1)) + 0.01 * np.random.default_rng(2).normal(size=(B, 2))
+	ODE = make(system)
+	ODE.set_integrator("dopri5", rtol=RTOL, atol=ATOL, **({"storage": storage} if storage else {}))
+	ODE.set_parameters(rates)
+	ODE.set_initial_value(Y0, 0.0)
+	with pytest.raises(UnsuccessfulIntegration) as failure:
+		ODE.integrate(20.0)
+	stiff = np.flatnonzero(rates == 1e4)
+	assert np.array_equal(failure.value.indices, stiff) and set(failure.value.status) == {3}
+	state = ODE.integrator.y_device.cpu().numpy()
+	times = ODE.integrator.tt[:B].cpu().numpy()
+	sample = np.r_[stiff[:4], np.flatnonzero(rates == 1e3)[:4]]
+	for b in sample:
+		def batched(tt, Y, lam=rates[b]):
+			return np.stack([-lam * (Y[:, 0] - np.cos(tt)), -0.5 * Y[:, 1]], axis=1)
+		ref = rk_numpy.HairerDopri(batched, "dopri5", nsteps=10**6, rtol=RTOL, atol=ATOL).integrate(0.0, Y0[b:b+1], 20.0)
+		assert ref["status"][0] == (3 if rates[b] == 1e4 else 0)
+		assert_allclose(times[b], ref["t"][0], rtol=1e-6)
+		assert_allclose(state[b], ref["y"][0], rtol=1e-5, atol=1e-9)
+	accepted = ODE.integrator.n_accepted[:B].cpu().numpy()
+	assert np.all(accepted[stiff] == 1014)            # the 1000th accepted step raises the first suspicion, the 1014th the 15th
+
+
+def test_sample_at_the_current_time_for_large_ensembles():
+	"""integrate_many([t_now, …]) with enough trajectories for the lane-refill kernel: the sample at the current time
+	is the current state (ODE_wrapper.integrate returns self._y for t == self.t, integrator_tools.py:142-143)"""
+	system = W.lotka_volterra()
+	Y0, _ = W.lotka_volterra_ensemble(1024, seed=12)
+	ODE = make(system)
+	ODE.set_integrator("dopri5", rtol=RTOL, atol=ATOL)
+	ODE.set_initial_value(Y0, 0.0)
+	assert_allclose(ODE.integrate_many([0.0])[0], Y0, rtol=0, atol=0)
+	both = ODE.integrate_many([0.0, 3.0])
+	assert_allclose(both[0], Y0, rtol=0, atol=0)
+	within_tolerance(both[1][:32], oracle(system, "dopri5", Y0[:32], [3.0], rtol=RTOL, atol=ATOL)[0])
+	with pytest.raises(ValueError):
+		ODE.integrate_many([5.0, 4.0])                  # sample times must not decrease
+
+
+def test_work_queue_of_warp_storage_changes_nothing():
+	"""warp storage with more trajectories than resident warps draws them from a queue; without the caller's counter
+	(queue = NULL) the warps stride statically: same results bit for bit"""
+	system = W.roessler_network(100)
+	B = 148 * 14 + 77
+	Y0, pars = W.roessler_ensemble(B, seed=31)
+	results = []
+	for use_queue in (True, False):
+		ODE = make(system)
+		ODE.set_integrator("dopri5", storage="warp", rtol=RTOL, atol=ATOL)
+		ODE.set_parameters(pars[:, 0])
+		ODE.set_initial_value(Y0, 0.0)
+		if not use_queue:
+			ODE.integrator.queue = None
+		results.append((ODE.integrate(1.0), ODE.step_counts()))
+	assert np.array_equal(results[0][0], results[1][0]) and results[0][1] == results[1][1]

@@ -171,3 +171,37 @@ def test_restricted_and_transversal_in_warp_storage():
 		assert_allclose(got, expected, rtol=1e-8, atol=1e-10)
 	for got, expected in zip(outcomes["warp"][1], outcomes["global"][1]):
 		assert_allclose(got, expected, rtol=1e-8, atol=1e-10)
+
+
+def test_non_finite_norms_warn_like_the_reference():
+	"""a tangent vector that overflows between two renormalisations: the reference warns (jitcode_lyap.norms,
+	_jitcode.py:747-748; restricted :944-945; transversal :890-891) and returns non-finite exponents; so does this"""
+	# dy/dt = 40·y: the tangent vector grows like exp(40 t) and leaves the double range before t = 20
+	ODE = jitcode_lyap([40.0 * y(0)], n_lyap=1, verbose=False, seed=3)
+	ODE.set_integrator("dopri5", nsteps=10**6)
+	states = np.full((5, 1), 1e-300)
+	ODE.set_initial_value(states, 0.0)
+	state, lyaps, vectors = ODE.integrate(1.0)
+	assert_allclose(lyaps, 40.0, rtol=1e-5)                       # finite interval: no warning, exponent 40
+	with pytest.warns(UserWarning, match="out of numerical bounds"):
+		state, lyaps, vectors = ODE.integrate(21.0)
+	assert not np.any(np.isfinite(lyaps))
+	ODE = jitcode_restricted_lyap([40.0 * y(0), -y(1)], vectors=[[0.0, 1.0]], verbose=False, seed=3)
+	ODE.set_integrator("dopri5", nsteps=10**6)
+	ODE.set_initial_value(np.full((3, 2), 1e-300), 0.0)
+	with pytest.warns(UserWarning, match="Norm of perturbation vector"):
+		ODE.integrate_many([20.0, 21.0])
+
+
+def test_lyapunov_call_that_does_not_advance_time():
+	"""integrate(t_now) on the ode back end launches nothing; the reference's ln(1)/0 is NaN (with a warning)"""
+	ODE = jitcode_lyap(W.fhn()["f_sym"], n_lyap=2, verbose=False, seed=5)
+	ODE.set_integrator("dopri5")
+	ODE.set_initial_value(np.tile(W.FHN_Y0, (3, 1)), 0.0)
+	with pytest.warns(UserWarning, match="equals the current time"):
+		state, lyaps, vectors = ODE.integrate(0.0)
+	assert state.shape == (3, 4) and lyaps.shape == (3, 2) and vectors.shape == (3, 2, 4)
+	assert np.all(np.isnan(lyaps))
+	assert_allclose(state, np.tile(W.FHN_Y0, (3, 1)), rtol=0, atol=0)
+	state, lyaps, vectors = ODE.integrate(5.0)
+	assert np.all(np.isfinite(lyaps))

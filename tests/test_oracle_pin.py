@@ -168,3 +168,55 @@ def test_lyapunov_spectrum_short():
 	res = ensemble.run_ensemble(handle, "dopri5", Y0, range(10, 12010, 10), lyap=(4, 4), processes=2)
 	lyaps = res["lyaps"][200:].mean(axis=(0, 1))
 	assert_allclose(lyaps, W.FHN_LYAPS, atol=0.015)
+
+
+def _stiff(lam):
+	"""fast relaxation towards cos(t) plus a slow decay: stiff for the explicit pairs once lam·h reaches their stability limit"""
+	def scalar(t, y):
+		return [-lam * (y[0] - np.cos(t)), -0.5 * y[1]]
+	def batched(t, Y):
+		return np.stack([-lam * (Y[:, 0] - np.cos(t)), -0.5 * Y[:, 1]], axis=1)
+	return scalar, batched
+
+
+@pytest.mark.parametrize("lam,T,expect_stiff", [(1e4, 20.0, True), (1e3, 20.0, False)])
+def test_stiffness_detection_dopri5_matches_scipy(lam, T, expect_stiff):
+	# Hairer's stiffness test (dopri5.f; IDID = −4 → scipy "problem is probably stiff (interrupted)"), which
+	# ODE_wrapper.integrate turns into UnsuccessfulIntegration (integrator_tools.py:137-140): the restatement
+	# stops at the same time, in the same state, after the same number of right-hand-side evaluations
+	import warnings
+	from scipy.integrate import ode
+	scalar, batched = _stiff(lam)
+	calls = [0]
+	def counted(t, y):
+		calls[0] += 1
+		return scalar(t, y)
+	solver = ode(counted).set_integrator("dopri5", nsteps=10**6, **TOL)
+	solver.set_initial_value([0.0, 1.0], 0.0)
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		y_scipy = solver.integrate(T)
+	assert (solver.get_return_code() == -4) == expect_stiff
+	result = rk_numpy.HairerDopri(batched, "dopri5", nsteps=10**6, **TOL).integrate(0.0, np.array([[0.0, 1.0]]), T)
+	assert result["status"][0] == (3 if expect_stiff else 0)
+	assert result["nfev"][0] == calls[0]
+	assert_allclose(result["t"][0], solver.t, rtol=1e-9)
+	assert_allclose(result["y"][0], y_scipy, rtol=1e-7)
+
+
+def test_stiffness_detection_dop853():
+	# dop853.f (limit 6.1): at the stability limit the error estimate amplifies rounding differences, so the step
+	# sequences of SciPy's build and of the restatement drift apart after ~20 steps; both give up as stiff, in the
+	# same window of accepted steps (1000 + 15 k) and at comparable times
+	import warnings
+	from scipy.integrate import ode
+	scalar, batched = _stiff(1e6)
+	solver = ode(scalar).set_integrator("dop853", nsteps=10**6, **TOL)
+	solver.set_initial_value([0.0, 1.0], 0.0)
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		solver.integrate(1.0)
+	assert solver.get_return_code() == -4
+	result = rk_numpy.HairerDopri(batched, "dop853", nsteps=10**6, **TOL).integrate(0.0, np.array([[0.0, 1.0]]), 1.0)
+	assert result["status"][0] == 3
+	assert_allclose(result["t"][0], solver.t, rtol=0.2)
