@@ -212,11 +212,21 @@ class CudaDenseSineIntegrator:
 			return out
 		if self._out_kind == "cuda":
 			return rows
-		host = rows.cpu()
+		return self._to_host(rows)
+
+	def _to_host(self, rows):
+		"""CPU tensor or NumPy array (the kind of the initial value); large results go through page-locked memory"""
+		if rows.numel() >= 1 << 20 and rows.is_cuda:
+			host = torch.empty(rows.shape, dtype=rows.dtype, pin_memory=True)
+			host.copy_(rows, non_blocking=True)
+			torch.cuda.current_stream(self.device).synchronize()
+		else:
+			host = rows.cpu()
 		return host if self._out_kind == "torch" else host.numpy()
 
-	def _rows_from(self, soa):
-		rows = torch.empty((self.B, self.n), dtype=torch.float64, device=self.device)
+	def _rows_from(self, soa, rows=None):
+		if rows is None:
+			rows = torch.empty((self.B, self.n), dtype=torch.float64, device=self.device)
 		_check(self.lib, self.lib.jb_dense_transpose(soa.data_ptr(), rows.data_ptr(), self.n, self.B, self.ld, self.n, self.stream), "jb_dense_transpose")
 		return rows
 
@@ -255,14 +265,8 @@ class CudaDenseSineIntegrator:
 	def successful(self):
 		return not bool((self.status[:self.B] != 0).any().item())
 
-	def integrate(self, T, out=None):
-		T = float(T)
-		if self.B is None:
-			raise RuntimeError("You must call set_initial_value first.")
-		if T < self.time:
-			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
-		if T == self.time:
-			return self._export(self._rows, out)
+	def _advance(self, T, rows=None):
+		"""one call of jb_dense_integrate: every trajectory to T; the state there as (B, n) device rows (`rows`: where to)"""
 		args = self._args(T)
 		if self.kernel_events is not None:
 			start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,17 +277,48 @@ class CudaDenseSineIntegrator:
 			self.kernel_events.append((start, end))
 		self.rounds += int(self.rounds_host[0])
 		self.time = T
-		self._rows = self._rows_from(self.Y)
+		self._rows = self._rows_from(self.Y, rows)
+
+	def _check_failures(self):
 		failed = (self.status[:self.B] != 0).nonzero().flatten()
 		if failed.numel():
 			indices = failed.cpu().numpy()
 			status = self.status[:self.B][failed].cpu().numpy()
 			raise UnsuccessfulIntegration(
 				f"{len(indices)} of {self.B} trajectories failed (first: #{indices[0]}, {STATUS_TEXT.get(int(status[0]), status[0])}).", indices, status)
+
+	def integrate(self, T, out=None):
+		T = float(T)
+		if self.B is None:
+			raise RuntimeError("You must call set_initial_value first.")
+		if T < self.time:
+			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
+		if T == self.time:
+			return self._export(self._rows, out)
+		self._advance(T)
+		self._check_failures()
 		return self._export(self._rows, out)
 
-	def integrate_many(self, times):
-		return np.stack([np.asarray(torch.as_tensor(self.integrate(T)).cpu()) for T in times])
+	def integrate_many(self, times, record_states=True):
+		"""the loop `for T in times: integrate(T)` (examples/kuramoto_network.py:34-35) without leaving the device between
+		the calls: (len(times), B, n) in the kind of the initial value; record_states=False keeps only the last state (1, B, n)."""
+		times = [float(T) for T in times]
+		if self.B is None:
+			raise RuntimeError("You must call set_initial_value first.")
+		if any(later < earlier for earlier, later in zip([self.time] + times, times)):
+			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
+		out = torch.empty((len(times) if record_states else 1, self.B, self.n), dtype=torch.float64, device=self.device)
+		for i, T in enumerate(times):
+			slot = out[i if record_states else 0]
+			if T == self.time:
+				slot.copy_(self._rows)
+			else:
+				self._advance(T, slot)
+		self._rows = out[-1]
+		self._check_failures()
+		if self._single:
+			out = out[:, 0]
+		return out if self._out_kind == "cuda" else self._to_host(out)
 
 	def eval_f(self, state):
 		rows, kind, single = self._to_device_rows(state)

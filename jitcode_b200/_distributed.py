@@ -56,6 +56,44 @@ def gather_states(local, B=None):
 	return result
 
 
+class GatheredEnsemble:
+	"""
+	One ensemble of B trajectories sharded over the ranks of the default process group, with the result of every
+	`integrate` call gathered on all ranks: each rank integrates its contiguous shard, its
+	integrate kernel's result is written straight into the rank's slot of the gather buffer (no staging copy), and one
+	in-place `all_gather_into_tensor` (ncclAllGather over NVLink) of (B/G)·n doubles per rank completes the global
+	state.  Shards must be even (B divisible by the world size) for the in-place collective; otherwise `gather_states`
+	is used on the shard.
+
+	ODE : a jitcode object with its integrator set; Y0 / pars : the WHOLE ensemble ((B, n) and (B, p), host or device —
+	every rank passes the same arrays and keeps only its shard).
+	"""
+
+	def __init__(self, ODE, Y0, pars=None, time=0.0):
+		self.ODE = ODE
+		self.rank, self.size = world()
+		self.B = len(Y0)
+		self.begin, self.end = shard_bounds(self.B, self.size, self.rank)
+		self.even = self.B % self.size == 0
+		if pars is not None and pars.shape[1]:
+			ODE.set_parameters(pars[self.begin:self.end])
+		ODE.set_initial_value(Y0[self.begin:self.end], time)
+		device = ODE.integrator.device
+		self.gathered = torch.empty((self.B, ODE.n), dtype=torch.float64, device=device)
+
+	def integrate(self, T):
+		"""advance all shards to T; returns the (B, n) CUDA tensor of the whole ensemble (valid on every rank)."""
+		slot = self.gathered[self.begin:self.end]
+		if self.even or self.size == 1:
+			self.ODE.integrator.integrate(T, into=slot)
+			if self.size > 1:
+				dist.all_gather_into_tensor(self.gathered, slot)
+		else:
+			self.ODE.integrator.integrate(T)
+			self.gathered.copy_(gather_states(self.ODE.integrator.y_device, self.B))
+		return self.gathered
+
+
 def reduce_lyapunov(local_exponents):
 	"""ensemble mean and standard error of the mean of local Lyapunov exponents.
 

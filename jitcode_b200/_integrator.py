@@ -167,8 +167,13 @@ class CudaEnsembleIntegrator:
 	def _pack(self, rows, tiled, width):
 		self.module.pack(rows.data_ptr(), tiled.data_ptr(), rows.shape[0], width, self.ld, self.stream)
 
-	def _unpack(self, tiled, width, B=None):
-		rows = torch.empty((self.B, width), dtype=torch.float64, device=self.device)
+	def _unpack(self, tiled, width, rows=None):
+		"""tiled device vector → (B, width) device rows; `rows`: a contiguous (B, width) CUDA tensor to write into (for
+		example this rank's slot of an all-gather buffer) instead of a fresh one."""
+		if rows is None:
+			rows = torch.empty((self.B, width), dtype=torch.float64, device=self.device)
+		elif not (rows.is_cuda and rows.dtype == torch.float64 and rows.is_contiguous() and tuple(rows.shape) == (self.B, width)):
+			raise ValueError(f"The device buffer for the result must be a contiguous ({self.B}, {width}) float64 CUDA tensor.")
 		self.module.unpack(tiled.data_ptr(), rows.data_ptr(), self.B, width, self.ld, self.stream)
 		return rows
 
@@ -344,20 +349,24 @@ class CudaEnsembleIntegrator:
 		self._sampled = True
 		return Yrec, lyap_rec
 
-	def _current_rows(self):
+	def _current_rows(self, rows=None):
 		source = self.Yres if (self.driver == JB_DRV_IVP_DENSE) else self.Y
-		return self._unpack(source, self.n)
+		return self._unpack(source, self.n, rows)
 
-	def integrate(self, T, out=None):
+	def integrate(self, T, out=None, into=None):
 		"""advance every trajectory to T and return the state there: (B, n), or (n,) if the initial value was 1-D.
-		out: optional CPU tensor (ideally pinned) that receives the result."""
+		out: optional CPU tensor (ideally pinned) that receives the result.
+		into: optional (B, n) CUDA tensor the kernel's result is written to directly (it becomes the state that is
+		returned for a CUDA-resident ensemble) — e.g. this rank's slot of an all-gather buffer (_distributed.py)."""
 		T = float(T)
 		if self.B is None:
 			raise RuntimeError("You must call set_initial_value first.")
 		if T == self.time and self.driver != JB_DRV_IVP_DENSE:
+			if into is not None:
+				into.copy_(self._rows)
 			return self._export(self._rows)       # ODE_wrapper.integrate :142-143
 		_, lyap_rec = self._launch([T], record=False)
-		self._rows = self._current_rows()
+		self._rows = self._current_rows(into)
 		if self.n_out:
 			self.last_lyaps = self._unpack(lyap_rec, self.n_out)
 		self._check_failures()

@@ -77,3 +77,71 @@ def test_single_process_is_identity():
 	x = torch.arange(6.0).reshape(3, 2)
 	assert D.gather_states(x) is x
 	assert D.shard_bounds(5) == (0, 5)
+
+
+class _StubIntegrator:
+	"""stands where CudaEnsembleIntegrator stands in GatheredEnsemble: 'integrating' doubles the state"""
+	device = torch.device("cpu")
+
+	def __init__(self):
+		self.rows = None
+
+	def integrate(self, T, into=None):
+		result = self.rows * 2.0 + T
+		if into is not None:
+			into.copy_(result)
+			result = into
+		self.rows = result
+		return result
+
+	@property
+	def y_device(self):
+		return self.rows
+
+
+class _StubODE:
+	n = 3
+
+	def __init__(self):
+		self.integrator = _StubIntegrator()
+		self.pars = None
+
+	def set_parameters(self, pars):
+		self.pars = pars
+
+	def set_initial_value(self, rows, time=0.0):
+		self.integrator.rows = torch.as_tensor(rows).clone()
+
+
+def _gather_worker(rank, world_size, port, B, queue):
+	os.environ["MASTER_ADDR"] = "127.0.0.1"
+	os.environ["MASTER_PORT"] = str(port)
+	dist.init_process_group("gloo", rank=rank, world_size=world_size)
+	try:
+		states = torch.as_tensor(np.random.default_rng(1).random((B, 3)))
+		pars = torch.arange(float(B)).reshape(B, 1)
+		ensemble = D.GatheredEnsemble(_StubODE(), states, pars)
+		result = ensemble.integrate(0.5).clone()
+		queue.put((rank, ensemble.begin, ensemble.end, ensemble.ODE.pars.numpy(), result.numpy()))
+	finally:
+		dist.destroy_process_group()
+
+
+def test_gathered_ensemble_two_ranks_gloo():
+	"""the strong-scaling path of bench.py: every rank integrates its shard into its slot of the gather buffer, one
+	in-place all-gather completes it (even shards) or gather_states does (uneven shards)"""
+	for B in (12, 11):
+		port = _free_port()
+		ctx = mp.get_context("spawn")
+		queue = ctx.Queue()
+		procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, B, queue)) for r in range(2)]
+		for p in procs:
+			p.start()
+		results = [queue.get(timeout=120) for _ in procs]
+		for p in procs:
+			p.join(timeout=60)
+			assert p.exitcode == 0
+		states = np.random.default_rng(1).random((B, 3))
+		for rank, begin, end, pars, result in results:
+			np.testing.assert_allclose(pars[:, 0], np.arange(begin, end))
+			np.testing.assert_allclose(result, 2.0 * states + 0.5)

@@ -176,7 +176,8 @@ def test_restricted_and_transversal_in_warp_storage():
 def test_non_finite_norms_warn_like_the_reference():
 	"""a tangent vector that overflows between two renormalisations: the reference warns (jitcode_lyap.norms,
 	_jitcode.py:747-748; restricted :944-945; transversal :890-891) and returns non-finite exponents; so does this"""
-	# dy/dt = 40·y: the tangent vector grows like exp(40 t) and leaves the double range before t = 20
+	# dy/dt = 40·y: the tangent vector grows like exp(40 t); after Δt = 11.5 its components are ≈ 1e200 — finite, so the
+	# integration itself succeeds, but their squares overflow and the norm is not finite
 	ODE = jitcode_lyap([40.0 * y(0)], n_lyap=1, verbose=False, seed=3)
 	ODE.set_integrator("dopri5", nsteps=10**6)
 	states = np.full((5, 1), 1e-300)
@@ -184,13 +185,13 @@ def test_non_finite_norms_warn_like_the_reference():
 	state, lyaps, vectors = ODE.integrate(1.0)
 	assert_allclose(lyaps, 40.0, rtol=1e-5)                       # finite interval: no warning, exponent 40
 	with pytest.warns(UserWarning, match="out of numerical bounds"):
-		state, lyaps, vectors = ODE.integrate(21.0)
+		state, lyaps, vectors = ODE.integrate(12.5)
 	assert not np.any(np.isfinite(lyaps))
 	ODE = jitcode_restricted_lyap([40.0 * y(0), -y(1)], vectors=[[0.0, 1.0]], verbose=False, seed=3)
 	ODE.set_integrator("dopri5", nsteps=10**6)
 	ODE.set_initial_value(np.full((3, 2), 1e-300), 0.0)
 	with pytest.warns(UserWarning, match="Norm of perturbation vector"):
-		ODE.integrate_many([20.0, 21.0])
+		ODE.integrate_many([11.5, 12.0])
 
 
 def test_lyapunov_call_that_does_not_advance_time():

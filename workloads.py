@@ -111,13 +111,29 @@ def small_world_network(rng, number_of_nodes, nearest_neighbours, rewiring_proba
 						break
 	return A
 
-def roessler_network(N=100, seed=42, k_as_parameter=True):
+def erdos_renyi_network(rng, number_of_nodes, mean_degree):
+	"""symmetric random graph without self-loops, every pair linked with probability mean_degree/(n−1)"""
+	n = number_of_nodes
+	upper = np.triu(rng.random((n, n)) < mean_degree / (n - 1), k=1)
+	return upper | upper.T
+
+def roessler_network(N=100, seed=42, k_as_parameter=True, topology="small_world"):
 	"""3N-dimensional system; data layout x0,v0,z0,x1,… (SW_of_Roesslers.py:110).
-	Draw order as in the example (:69-84): ω first, then the adjacency matrix."""
+	Draw order as in the example (:69-84): ω first, then the adjacency matrix.
+	topology: "small_world" — the example's small_world_network(N, 20, 0.1); "random" — the same construction with
+	rewiring probability 1 (no lattice left); "erdos_renyi" — G(N, p) of the same mean degree 20.  The two variants
+	exist to measure the engine where the lattice-specific code paths of the vectoriser do not apply."""
 	rng = np.random.default_rng(seed)
 	omega = rng.uniform(0.8, 1.0, N)
 	a, b, c = 0.165, 0.2, 10.0
-	A = small_world_network(rng, N, 20, 0.1)
+	if topology == "small_world":
+		A = small_world_network(rng, N, 20, 0.1)
+	elif topology == "random":
+		A = small_world_network(rng, N, 20, 1.0)
+	elif topology == "erdos_renyi":
+		A = erdos_renyi_network(rng, N, 20)
+	else:
+		raise ValueError(topology)
 	if k_as_parameter:
 		k = sympy.Symbol("k")
 		control_pars = [k]
