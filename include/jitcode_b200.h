@@ -64,7 +64,10 @@ enum jb_storage {
 	JB_STORE_REGISTERS = 0, /* thread per trajectory, state and stages in registers; tiled layout */
 	JB_STORE_GLOBAL = 1,    /* thread per trajectory, stages in the caller's tiled workspace */
 	JB_STORE_WARP = 2,      /* warp per trajectory, stages in shared memory; ROW layout (see below) */
-	JB_STORE_SHARED = 3     /* thread per trajectory, stages in the block's shared memory; tiled layout */
+	JB_STORE_SHARED = 3,    /* thread per trajectory, stages in the block's shared memory; tiled layout */
+	JB_STORE_QUAD = 5       /* Lyapunov modules: a group of 2^k >= n_lyap lanes per trajectory, lane j integrates the state
+	                           (redundantly) and tangent vector j in registers; norms and Gram–Schmidt are shuffles within
+	                           the group; tiled layout.  (4 is the dense engine's tag in bench.py / _dense.DenseInfo.) */
 };
 enum jb_status  { JB_OK = 0, JB_STEP_TOO_SMALL = 1, JB_TOO_MANY_STEPS = 2, JB_STIFF = 3, JB_NONFINITE = 4 };
 enum jb_post    {

@@ -18,11 +18,11 @@ from sympy.printing.c import C99CodePrinter
 
 JB_DP5, JB_DOP853, JB_RK23 = 0, 1, 2
 JB_DRV_ODE, JB_DRV_IVP_DENSE, JB_DRV_IVP_LAND = 0, 1, 2
-JB_STORE_REGISTERS, JB_STORE_GLOBAL, JB_STORE_WARP, JB_STORE_SHARED = 0, 1, 2, 3
+JB_STORE_REGISTERS, JB_STORE_GLOBAL, JB_STORE_WARP, JB_STORE_SHARED, JB_STORE_QUAD = 0, 1, 2, 3, 5
 
 METHOD_NAMES = {JB_DP5: "JB_DP5", JB_DOP853: "JB_DOP853", JB_RK23: "JB_RK23"}
 DRIVER_NAMES = {JB_DRV_ODE: "JB_DRV_ODE", JB_DRV_IVP_DENSE: "JB_DRV_IVP_DENSE", JB_DRV_IVP_LAND: "JB_DRV_IVP_LAND"}
-STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL", JB_STORE_WARP: "JB_STORE_WARP", JB_STORE_SHARED: "JB_STORE_SHARED"}
+STORAGE_NAMES = {JB_STORE_REGISTERS: "JB_STORE_REGISTERS", JB_STORE_GLOBAL: "JB_STORE_GLOBAL", JB_STORE_WARP: "JB_STORE_WARP", JB_STORE_SHARED: "JB_STORE_SHARED", JB_STORE_QUAD: "JB_STORE_QUAD"}
 
 
 class CudaPrinter(C99CodePrinter):
@@ -131,13 +131,14 @@ def _c_array(values, per_line=16):
 	return ",\n\t".join(", ".join(values[k:k+per_line]) for k in range(0, len(values), per_line))
 
 
-def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None, component_of=None, kregs=0, min_blocks=1, team_warps=1):
+def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, method, driver, storage, threads, tables=None, component_of=None, kregs=0, min_blocks=1, team_warps=1, group=1):
 	"""the complete translation unit of one module (what _render_template produces from
 	jitced_template.c in the reference, _jitcode.py:397-406).
 
 	statements : body of the right-hand side — of Sys::rhs (thread storage: `y(i)` / `dy.set(i, …)` on whatever
 		vector type the stepper uses) or of Sys::rhs_warp (warp storage: the vectorised form of _vectorise.py,
-		with `tables` = its _vectorise.Tables)."""
+		with `tables` = its _vectorise.Tables; quad storage: the system with ONE tangent vector, 2·n_basic statements).
+	group : quad storage: lanes per trajectory (power of two ≥ n_lyap)."""
 	tangent_indices = list(tangent_indices or [])
 	if tangent_indices:
 		table = ", ".join(str(int(k)) for k in tangent_indices)
@@ -197,6 +198,7 @@ struct Sys {{
 	static constexpr int TF_COUNT = {len(tf)}, TU_COUNT = {len(tu)};
 	static constexpr int NROW = {n_row};   // shared-memory row length (warp storage): position N holds 0
 	static constexpr int TEAM_WARPS = {int(team_warps)};   // warps that share one trajectory (warp storage)
+	static constexpr int GROUP = {int(group)};   // lanes that share one trajectory (quad storage)
 	static constexpr int THREADS = {int(threads)};   // threads per block (= row stride of shared storage)
 	typedef {tu_type} TU;
 	static __device__ __forceinline__ const TU *components(const void *tables)

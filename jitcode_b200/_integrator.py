@@ -12,6 +12,7 @@ There is no CPU path: constructing the integrator without a CUDA device raises.
 """
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -147,7 +148,7 @@ class CudaEnsembleIntegrator:
 		self._times_host = torch.empty(1, dtype=torch.float64).pin_memory()
 		self._pars_on_device = False
 		# the counter from which persistent kernels draw trajectories: one per integrator (its launches share a stream)
-		self.queue = torch.zeros(1, dtype=torch.int64, device=dev)
+		self.queue = None if os.environ.get("JITCODE_B200_NO_QUEUE") else torch.zeros(1, dtype=torch.int64, device=dev)
 
 	def _to_device_rows(self, array, width, what):
 		"""(B, width) float64 contiguous CUDA tensor from numpy / torch / list input; returns (tensor, kind, single)."""

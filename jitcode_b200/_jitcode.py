@@ -48,7 +48,8 @@ _used_module_names = set()
 
 SHARED_MEMORY_PER_BLOCK = 227 * 1024      # sm_100a: opt-in maximum of dynamic shared memory per block
 STORAGE_BY_NAME = {"registers": _codegen.JB_STORE_REGISTERS, "global": _codegen.JB_STORE_GLOBAL, "warp": _codegen.JB_STORE_WARP,
-		"shared": _codegen.JB_STORE_SHARED, "dense": "dense"}
+		"shared": _codegen.JB_STORE_SHARED, "quad": _codegen.JB_STORE_QUAD, "dense": "dense"}
+REGISTER_DOUBLES = 88                     # state + stages a thread keeps in registers (measured: 80 doubles compile without spills)
 # The dense engine costs 4·n² flops per right-hand side and trajectory, the written-out form ≈ 40 per sine term:
 # measured on the reference's own example (examples/kuramoto_network.py: n = 100, 20 % density) the GEMM form is
 # 4.5× faster than the generated code, so it is chosen from 10 % density on.
@@ -73,7 +74,7 @@ def _storage_for(n, method, driver):
 	warps of trajectories fit it (mid-size systems: the stages stay on chip, 30 instead of 250 cycles away); else the
 	tiled global workspace (warp storage is chosen on top of this when the system vectorises well, see jitcode._module)."""
 	rows = _stage_rows(method, driver) + 3
-	if rows * n <= 88:
+	if rows * n <= REGISTER_DOUBLES:
 		return _codegen.JB_STORE_REGISTERS
 	return _codegen.JB_STORE_SHARED if _shared_threads(n, method, driver) >= 128 else _codegen.JB_STORE_GLOBAL
 
@@ -332,8 +333,21 @@ class jitcode:
 					pass
 		return self._plans[team_warps]
 
+	def _quad_group(self, method, driver):
+		"""lanes per trajectory of quad storage, or 0 if it does not apply: jitcode_lyap with at least two tangent vectors
+		whose state plus ONE tangent vector fit a thread's registers (lane j of the group integrates the state and
+		tangent vector j; norms and Gram–Schmidt are shuffles within the group)."""
+		k = self._n_lyap_module
+		if self._post != JB_POST_LYAP_QR or k < 2 or k > 32 or not getattr(self, "_f_basic", None):
+			return 0
+		if (_stage_rows(method, driver) + 3) * 2 * self._n_basic_module > REGISTER_DOUBLES:
+			return 0
+		return 1 << (k - 1).bit_length()
+
 	def _choose_storage(self, method, driver):
 		storage = _storage_for(self.n, method, driver)
+		if storage != _codegen.JB_STORE_REGISTERS and self._quad_group(method, driver):
+			return _codegen.JB_STORE_QUAD
 		if storage != _codegen.JB_STORE_REGISTERS and self.n >= 64:
 			plan = self._warp_plan()
 			if plan is not None and plan[0].efficiency >= 0.5:
@@ -353,7 +367,18 @@ class jitcode:
 			if not self._f_list:
 				raise RuntimeError("This object was created from a saved module for another integrator configuration and has no f_sym to compile.")
 			tables = component_of = None
-			if storage == _codegen.JB_STORE_WARP:
+			group = 1
+			if storage == _codegen.JB_STORE_QUAD:
+				group = self._quad_group(method, driver)
+				if not group:
+					raise ValueError("Quad storage needs a jitcode_lyap system with 2 … 32 tangent vectors whose state plus one tangent vector fit a thread's registers.")
+				self.check()
+				# the right-hand side every lane runs: the state and ONE tangent vector (_jitcode.py:697-714 with n_lyap = 1)
+				local = lyapunov_system(self._f_basic, self.helpers, self._n_basic_module, 1)
+				statements = _codegen.rhs_statements(local, self.helpers, self.control_pars)
+				if threads is None:
+					threads = 128
+			elif storage == _codegen.JB_STORE_WARP:
 				plan = self._warp_plan()
 				if plan is None:
 					raise NotImplementedError("This system cannot be vectorised for warp storage.")
@@ -376,7 +401,7 @@ class jitcode:
 				statements, self.n, len(self.control_pars),
 				self._n_basic_module, self._n_lyap_module, self._tangent_indices_module,
 				method, driver, storage, threads, tables=tables, component_of=component_of, kregs=kregs or 0,
-				min_blocks=min_blocks or 1, team_warps=team_warps or 1,
+				min_blocks=min_blocks or 1, team_warps=team_warps or 1, group=group,
 			)
 			path = _build.compile_module(
 				source, self._compile_options["extra_compile_args"], self._compile_options["extra_link_args"],
@@ -677,6 +702,7 @@ class jitcode_lyap(jitcode):
 			warn(f"You are about to calculate {self._n_lyap} Lyapunov exponents. This is very likely more than you need and may lead to severe difficulties with compilation and integration.", stacklevel=2)
 		helpers = sort_helpers(kwargs.pop("helpers", None))
 		full = lyapunov_system(f_basic, helpers, self.n_basic, self._n_lyap)
+		self._f_basic = list(f_basic)
 		if simplify:
 			full = full[:self.n_basic] + [entry.simplify(ratio=1.0) for entry in full[self.n_basic:]]
 		super().__init__(full, helpers=helpers, n=self.n_basic*(self._n_lyap+1), **kwargs)

@@ -29,6 +29,8 @@ constexpr int MODULE_MODE = JB_MODULE_STORAGE;
 constexpr bool MODULE_REG = MODULE_MODE == JB_STORE_REGISTERS;
 constexpr bool MODULE_WARP = MODULE_MODE == JB_STORE_WARP;
 constexpr bool MODULE_SHARED = MODULE_MODE == JB_STORE_SHARED;
+constexpr bool MODULE_QUAD = MODULE_MODE == JB_STORE_QUAD;
+constexpr int MODULE_GROUP = MODULE_QUAD ? Sys::GROUP : 1;      // threads per trajectory of the thread-storage kernels
 // thread-per-trajectory with the stages in shared memory: (Y, Z, K rows, y_old) × N × threads doubles per block
 constexpr size_t THREAD_SHARED_BYTES = MODULE_SHARED
 		? sizeof(double) * (size_t) (2 + Layout<Tab, JB_MODULE_DRIVER>::KR + (Layout<Tab, JB_MODULE_DRIVER>::DENSE ? 1 : 0)) * Sys::N * JB_MODULE_THREADS : 0;
@@ -100,7 +102,8 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 		if (b >= a.B) return;
 		run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b, jb_smem + threadIdx.x);
 	} else {
-		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+		// one thread per trajectory — or, in quad storage, one group of lanes (the whole group leaves together)
+		const int64_t b = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) / MODULE_GROUP;
 		if (b >= a.B) return;
 		run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE>(a, b);
 	}
@@ -141,13 +144,24 @@ jb_eval_f_kernel(const double *t, const double *Y, const double *P, double *dY, 
 			T::sync();
 		}
 	} else {
-		const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+		const int64_t b = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) / MODULE_GROUP;
 		if (b >= B) return;
 		typename S::Par par;
 #pragma unroll
 		for (int k = 0; k < S::NP; ++k) par.v[k] = P[tile_offset(b, S::NP) + k * TILE];
 		const int64_t off = tile_offset(b, S::N);
-		if constexpr (MODE == JB_STORE_REGISTERS) {
+		if constexpr (MODE == JB_STORE_QUAD) {
+			// lane k of the group evaluates the state's derivative and that of tangent vector k
+			const int member = (int) (threadIdx.x % (unsigned) S::GROUP);
+			const bool owner = member < S::NL;
+			const QVec<S::NB> in{const_cast<double *>(Y) + off, S::NB * member, member == 0, owner}, out{dY + off, S::NB * member, member == 0, owner};
+			RVec<2 * S::NB> y, dy;
+#pragma unroll
+			for (int i = 0; i < 2 * S::NB; ++i) y.v[i] = in(i);
+			S::rhs(t[b], y, dy, par);
+#pragma unroll
+			for (int i = 0; i < 2 * S::NB; ++i) out.set(i, dy.v[i]);
+		} else if constexpr (MODE == JB_STORE_REGISTERS) {
 			RVec<S::N> y, dy;
 #pragma unroll
 			for (int i = 0; i < S::N; ++i) y.v[i] = Y[off + i * TILE];
@@ -307,7 +321,7 @@ int jb_eval_f(const double *t, const double *Y, const double *P, double *dY, int
 		jb::jb_eval_f_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, jb::Shared::EVAL_BYTES, (cudaStream_t) stream>>>(t, Y, P, dY, B);
 		return jb::launched("jb_eval_f");
 	}
-	const unsigned blocks = (unsigned) ((B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);
+	const unsigned blocks = (unsigned) ((B * jb::MODULE_GROUP + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);
 	jb::jb_eval_f_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, 0, (cudaStream_t) stream>>>(t, Y, P, dY, B);
 	return jb::launched("jb_eval_f");
 }
@@ -325,7 +339,7 @@ int jb_integrate(const jb_integrate_args *x)
 			|| (jb::ModuleLayout::DENSE && !x->Yres))
 		return jb::fail(JB_E_BAD_ARGUMENT, "jb_integrate: missing or inconsistent buffers");
 	if (x->post != JB_POST_NONE) {
-		if (jb::Sys::NL <= 0 || (x->post == JB_POST_LYAP_TRANSVERSAL && jb::Sys::NT <= 0)
+		if (jb::Sys::NL <= 0 || (jb::MODULE_QUAD && x->post != JB_POST_LYAP_QR) || (x->post == JB_POST_LYAP_TRANSVERSAL && jb::Sys::NT <= 0)
 				|| (x->post == JB_POST_LYAP_RESTRICTED && (jb::Sys::NL != 1 || (x->n_proj > 0 && !x->proj))))
 			return jb::fail(JB_E_UNSUPPORTED, "jb_integrate: this module has no tangent vectors for the requested post-step");
 	}
@@ -387,7 +401,7 @@ int jb_integrate(const jb_integrate_args *x)
 		jb::jb_integrate_refill_kernel<<<(unsigned) (needed < resident ? needed : resident), JB_MODULE_THREADS, 0, (cudaStream_t) x->stream>>>(a);
 		return jb::launched("jb_integrate");
 	}
-	const unsigned blocks = (unsigned) ((x->B + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);
+	const unsigned blocks = (unsigned) ((x->B * jb::MODULE_GROUP + JB_MODULE_THREADS - 1) / JB_MODULE_THREADS);
 	if (jb::MODULE_SHARED) {
 		const cudaError_t err = cudaFuncSetAttribute((const void *) jb::jb_integrate_kernel<jb::MODULE_MODE>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int) jb::THREAD_SHARED_BYTES);

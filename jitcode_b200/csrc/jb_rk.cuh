@@ -55,6 +55,27 @@ struct StrideVec {          // element i at p[i*STRIDE]: consecutive threads tou
 };
 using GVec = StrideVec<TILE>;       // one trajectory's column of a tile in global memory
 
+// Quad storage: what lane k of a trajectory's group sees of a caller-visible (tiled) vector of the full Lyapunov
+// system — local component i < NB is state component i (every lane reads it, lane 0 writes it), local component
+// NB + i is component NB·(1 + k) + i, i.e. its own tangent vector.  Lanes beyond the last tangent vector ("phantom"
+// lanes of a group padded to a power of two) read zeros there and write nothing.
+template <int NB>
+struct QVec {
+	double *p;
+	int shift;          // NB · k
+	bool first, real;   // lane 0 of the group / a lane that owns a tangent vector
+	__device__ __forceinline__ double operator()(int i) const
+	{
+		if (i < NB) return p[i * TILE];
+		return real ? p[(i + shift) * TILE] : 0.0;
+	}
+	__device__ __forceinline__ void set(int i, double x) const
+	{
+		if (i < NB) { if (first) p[i * TILE] = x; }
+		else if (real) p[(i + shift) * TILE] = x;
+	}
+};
+
 struct SVec {               // contiguous vector: shared memory (warp storage) or one row of a (B, n) global array
 	double *p;
 	__device__ __forceinline__ double operator()(int i) const { return p[i]; }
@@ -85,6 +106,30 @@ __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
 	for (int offset = 16; offset > 0; offset >>= 1) v += __shfl_xor_sync(0xffffffffu, v, offset);
+	return v;
+}
+
+// Σ over the G = 2^k lanes of a group (quad storage); only the group's own lanes take part, so groups of one warp
+// may be in different places of the code
+template <int G>
+__device__ __forceinline__ double group_sum(double v)
+{
+	if constexpr (G > 1) {
+		const unsigned lane = threadIdx.x & 31u;
+		const unsigned mask = (G >= 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(unsigned) (G - 1));
+#pragma unroll
+		for (int offset = G / 2; offset > 0; offset >>= 1) v += __shfl_xor_sync(mask, v, offset);
+	}
+	return v;
+}
+template <int G>
+__device__ __forceinline__ double group_broadcast(double v, int source)
+{
+	if constexpr (G > 1) {
+		const unsigned lane = threadIdx.x & 31u;
+		const unsigned mask = (G >= 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(unsigned) (G - 1));
+		v = __shfl_sync(mask, v, source, G);
+	}
 	return v;
 }
 
@@ -232,19 +277,24 @@ __device__ __noinline__ void rhs_warp_outlined(double t, const double *__restric
 
 template <class Sys, class Tab, int DRIVER, int MODE>
 struct ThreadStore {        // one thread per trajectory: registers (MODE 0), the caller's tiled workspace (MODE 1)
-	                            // or the block's shared memory (MODE 3: rows of one word per thread)
-	static constexpr int N = Sys::N;
+	                            // or the block's shared memory (MODE 3: rows of one word per thread);
+	                            // quad storage (MODE 5): a group of lanes per trajectory, each with the state and ONE
+	                            // tangent vector in registers (Sys::rhs is then the system with a single tangent vector)
 	using L = Layout<Tab, DRIVER>;
-	static constexpr bool REG = MODE == JB_STORE_REGISTERS;
+	static constexpr bool QUAD = MODE == JB_STORE_QUAD;
+	static constexpr bool REG = MODE == JB_STORE_REGISTERS || QUAD;
 	static constexpr bool SHARED = MODE == JB_STORE_SHARED;
 	static constexpr bool WARP = false;
+	static constexpr int N = QUAD ? 2 * Sys::NB : Sys::N;      // length of this thread's vectors
+	static constexpr int GROUP = QUAD ? Sys::GROUP : 1;         // lanes per trajectory
+	static constexpr int NSPLIT = QUAD ? Sys::NB : N;           // components [NSPLIT, N) are summed over the group
 	static constexpr int KR = L::KR;
 	static constexpr int UNR = REG ? (N > 0 ? N : 1) : 4;   // unroll factor of component loops
 	static constexpr int STRIDE = SHARED ? Sys::THREADS : TILE;
 	static constexpr int ROWS = 2 + KR + (L::DENSE ? 1 : 0);    // shared storage: Y, Z, K rows, y_old
 	using Vec = typename std::conditional<REG, RVec<N>, StrideVec<STRIDE>>::type;
-	using IVec = GVec;      // persistent solver vectors in the caller's memory
-	using UVec = GVec;      // the caller's state and samples
+	using IVec = typename std::conditional<QUAD, QVec<Sys::NB>, GVec>::type;      // persistent solver vectors in the caller's memory
+	using UVec = IVec;      // the caller's state and samples
 
 	Vec Y, Z, YO, K[KR];
 	typename Sys::Par par;
@@ -254,18 +304,33 @@ struct ThreadStore {        // one thread per trajectory: registers (MODE 0), th
 #pragma unroll UNR
 		for (int i = 0; i < N; ++i) body(i, Idx<0>{});
 	}
+	// quad storage: every lane of the group holds the state's contribution, the tangent vectors' are added up over
+	// the group (butterfly: all lanes get bit-identical totals, so the group's control flow stays uniform)
 	template <class F> __device__ __forceinline__ double sum(F &&value)
 	{
 		double total = 0.0;
 #pragma unroll UNR
-		for (int i = 0; i < N; ++i) total += value(i, Idx<0>{});
+		for (int i = 0; i < NSPLIT; ++i) total += value(i, Idx<0>{});
+		if constexpr (QUAD) {
+			double own = 0.0;
+#pragma unroll UNR
+			for (int i = NSPLIT; i < N; ++i) own += value(i, Idx<0>{});
+			total += group_sum<GROUP>(own);
+		}
 		return total;
 	}
 	template <class F> __device__ __forceinline__ void sum2(F &&value, double &s0, double &s1)
 	{
 		s0 = s1 = 0.0;
 #pragma unroll UNR
-		for (int i = 0; i < N; ++i) value(i, Idx<0>{}, s0, s1);
+		for (int i = 0; i < NSPLIT; ++i) value(i, Idx<0>{}, s0, s1);
+		if constexpr (QUAD) {
+			double o0 = 0.0, o1 = 0.0;
+#pragma unroll UNR
+			for (int i = NSPLIT; i < N; ++i) value(i, Idx<0>{}, o0, o1);
+			s0 += group_sum<GROUP>(o0);
+			s1 += group_sum<GROUP>(o1);
+		}
 	}
 
 	template <class R> __device__ __forceinline__ double y(int i, R) const { return Y(i); }
@@ -297,6 +362,7 @@ struct WarpStore {          // one team of warps per trajectory, lanes across co
 	using L = Layout<Tab, DRIVER>;
 	static constexpr bool REG = false;
 	static constexpr bool WARP = true;
+	static constexpr bool QUAD = false;
 	static constexpr int KR = L::KR;
 	static constexpr bool CACHED = KREGS > 0;           // Y and K[0 … KREGS) live in registers, lane-strided
 	static constexpr int NP = (N + T::SIZE - 1) / T::SIZE;   // passes of a loop strided over the team
@@ -430,14 +496,17 @@ struct Stepper : Store {
 	static constexpr bool IVP = L::IVP;
 	static constexpr int S = Tab::NSTAGE;
 	static constexpr bool WARP = Store::WARP;
+	static constexpr bool MODE_QUAD = Store::QUAD;
 
 	double atol_s, rtol;
 	const double *atol_vec;
 	const typename Sys::TU *comp;     // warp storage: component stored at each position
+	int shift;                        // quad storage: offset of this lane's tangent vector in the full system
 
 	__device__ __forceinline__ double atol(int i) const
 	{
 		if constexpr (WARP) return atol_vec ? atol_vec[comp[i]] : atol_s;
+		else if constexpr (MODE_QUAD) return atol_vec ? atol_vec[i < Sys::NB ? i : i + shift] : atol_s;
 		else return atol_vec ? atol_vec[i] : atol_s;
 	}
 
@@ -607,6 +676,39 @@ __device__ __forceinline__ void lyap_orthonormalise(Vec &Y, double *norms)
 	}
 }
 
+// The same Gram–Schmidt for quad storage: tangent vector k lives in the registers of lane k of the group (components
+// NB … 2·NB−1 of its vector).  For j = 0, 1, …: lane j normalises its vector and hands it round (shuffles within the
+// group), every later lane removes its projection on it — the same operations in the same order as above.  Returns
+// this lane's norm |R_kk|.
+template <int NB, int NL, int G, class Vec>
+__device__ __forceinline__ double group_orthonormalise(Vec &Y, int member)
+{
+	double own_norm = 1.0;
+#pragma unroll
+	for (int j = 0; j < NL; ++j) {
+		double q[NB];
+		if (member == j) {
+			double sq = 0.0;
+#pragma unroll
+			for (int i = 0; i < NB; ++i) sq = fma(Y(NB + i), Y(NB + i), sq);
+			own_norm = sqrt(sq);
+			const double inv = 1.0 / own_norm;
+#pragma unroll
+			for (int i = 0; i < NB; ++i) Y.set(NB + i, Y(NB + i) * inv);
+		}
+#pragma unroll
+		for (int i = 0; i < NB; ++i) q[i] = group_broadcast<G>(Y(NB + i), j);
+		if (member > j) {
+			double dot = 0.0;
+#pragma unroll
+			for (int i = 0; i < NB; ++i) dot = fma(q[i], Y(NB + i), dot);
+#pragma unroll
+			for (int i = 0; i < NB; ++i) Y.set(NB + i, fma(-dot, q[i], Y(NB + i)));
+		}
+	}
+	return own_norm;
+}
+
 // jitcode_restricted_lyap.norms (_jitcode.py:937-946): remove the projections onto the given
 // (orthonormalised) vectors from the single tangent vector, then normalise.
 template <int NB, bool REG, class Vec>
@@ -720,21 +822,28 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	using UVec = typename ST::UVec;
 	constexpr int N = Sys::N;
 	constexpr int S = Tab::NSTAGE;
-	constexpr bool REG = MODE == JB_STORE_REGISTERS;
+	constexpr bool QUAD = MODE == JB_STORE_QUAD;
+	constexpr bool REG = MODE == JB_STORE_REGISTERS || QUAD;
+	constexpr int NV = Store::N;                                            // length of this thread's vectors (N unless QUAD)
 	constexpr bool DENSE = ST::DENSE;
 	constexpr bool IVP = ST::IVP;
-	constexpr int NLY = Sys::NL > 0 ? Sys::NL : 1;
+	constexpr int NLY = QUAD ? 1 : (Sys::NL > 0 ? Sys::NL : 1);             // exponents this thread computes
 	const int64_t ld = a.ld;
 	const int64_t vec = (int64_t) N * ld;                                   // one caller-visible vector
 	const int64_t off = WARP ? b * (int64_t) N : tile_offset(b, N);         // this trajectory inside it
 	bool leader = true;                                                     // writes the per-trajectory scalars
 	if constexpr (WARP) leader = Team<Sys::TEAM_WARPS>::rank() == 0;
+	// quad storage: this lane's place in the trajectory's group and whether it owns a tangent vector
+	const int member = QUAD ? (int) (threadIdx.x % (unsigned) Sys::GROUP) : 0;
+	const bool owner = !QUAD || member < Sys::NL;
+	if constexpr (QUAD) leader = member == 0;
 
 	ST st;
 	st.rtol = a.rtol;
 	st.atol_s = a.atol;
 	st.atol_vec = a.atol_vec;
 	st.comp = nullptr;
+	st.shift = owner ? Sys::NB * member : 0;
 #pragma unroll
 	for (int k = 0; k < Sys::NP; ++k)
 		st.par.v[k] = WARP ? a.P[b * Sys::NP + k] : a.P[tile_offset(b, Sys::NP) + k * TILE];
@@ -746,21 +855,26 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	// ---- canonical (caller-visible) locations
 	auto user = [&](double *base) {
 		if constexpr (WARP) return UVec{base, st.comp};
+		else if constexpr (QUAD) return UVec{base, Sys::NB * member, member == 0, owner};
 		else return UVec{base};
+	};
+	auto persistent = [&](double *base) {
+		if constexpr (QUAD) return IVec{base, Sys::NB * member, member == 0, owner};
+		else return IVec{base};
 	};
 	if constexpr (WARP) {
 		st.tables = tables;
 		st.comp = Sys::components(tables);
 	}
 	const UVec Yc = user(a.Y + off);
-	const IVec Fc{IVP ? a.state + SV_F * vec + off : nullptr};
-	const IVec Oc{DENSE ? a.state + SV_YOLD * vec + off : nullptr};
-	auto Qc = [&](int p) { return IVec{a.state + (SV_DENSE0 + p) * vec + off}; };
+	const IVec Fc = persistent(IVP ? a.state + SV_F * vec + off : nullptr);
+	const IVec Oc = persistent(DENSE ? a.state + SV_YOLD * vec + off : nullptr);
+	auto Qc = [&](int p) { return persistent(a.state + (SV_DENSE0 + p) * vec + off); };
 
 	// ---- bind working storage
 	if constexpr (REG) {
 #pragma unroll
-		for (int i = 0; i < N; ++i) st.Y.v[i] = Yc(i);
+		for (int i = 0; i < NV; ++i) st.Y.v[i] = Yc(i);
 	} else if constexpr (WARP) {
 		st.bind(smem);
 		st.for_each([&](int i, auto r) { st.set_y(i, r, Yc(i)); });
@@ -1041,6 +1155,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					st.for_each([&](int i, auto r) { st.set_z(i, r, st.y(i, r)); });
 					team_lyap<Sys>(a.post, st.pZ, Sys::positions(tables), a.proj, a.n_proj, norms, st.scratch);
 					st.for_each([&](int i, auto r) { st.set_y(i, r, st.z(i, r)); });
+				} else if constexpr (QUAD) {
+					norms[0] = group_orthonormalise<Sys::NB, Sys::NL, Sys::GROUP>(st.Y, member);
 				} else {
 					if (a.post == JB_POST_LYAP_QR)
 						lyap_orthonormalise<Sys::NB, Sys::NL, REG>(st.Y, norms);
@@ -1051,6 +1167,16 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 				}
 			}
 			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+			if constexpr (QUAD) {
+				// every owning lane reports the exponent of its own tangent vector
+				const double lyap = log(norms[0]) / dt_lyap;
+				if (a.lyap_rec && owner)
+					a.lyap_rec[tile_offset(b, a.n_times * n_out) + (int64_t) (it * n_out + member) * TILE] = lyap;
+				if (it >= a.lyap_discard) {
+					lyap_sum[0] += lyap;
+					lyap_sq[0] = fma(lyap, lyap, lyap_sq[0]);
+				}
+			} else
 			for (int k = 0; k < NLY; ++k) {
 				if (k >= n_out) break;
 				const double lyap = log(norms[k]) / dt_lyap;
@@ -1084,7 +1210,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	// ================= write the solver back
 	if constexpr (REG) {
 #pragma unroll
-		for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
+		for (int i = 0; i < NV; ++i) Yc.set(i, st.Y.v[i]);
 	} else {
 		bool copy_back = WARP || MODE == JB_STORE_SHARED;
 		if constexpr (MODE == JB_STORE_GLOBAL) copy_back = st.Y.p != Yc.p;
@@ -1108,6 +1234,13 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 		if (a.n_accepted) a.n_accepted[b] += n_acc;
 		if (a.n_rejected) a.n_rejected[b] += n_rej;
 	}
+	if constexpr (QUAD) {
+		if (a.lyap_acc && a.post != JB_POST_NONE && owner) {
+			const int n_out = Sys::NL;
+			a.lyap_acc[tile_offset(b, n_out) + member * TILE] += lyap_sum[0];
+			a.lyap_acc[(int64_t) n_out * ld + tile_offset(b, n_out) + member * TILE] += lyap_sq[0];
+		}
+	} else
 	if (a.lyap_acc && a.post != JB_POST_NONE && leader) {
 		const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
 		for (int k = 0; k < NLY; ++k) {

@@ -206,3 +206,59 @@ def test_lyapunov_call_that_does_not_advance_time():
 	assert_allclose(state, np.tile(W.FHN_Y0, (3, 1)), rtol=0, atol=0)
 	state, lyaps, vectors = ODE.integrate(5.0)
 	assert np.all(np.isfinite(lyaps))
+
+
+def _tangent_ensemble(B, n_lyap, seed):
+	rng = np.random.default_rng(seed)
+	base = W.FHN_Y0 + 1e-3 * rng.normal(size=(B, 4))
+	tangents = rng.normal(size=(B, n_lyap, 4))
+	tangents /= np.linalg.norm(tangents, axis=2, keepdims=True)
+	return np.hstack([base, tangents.reshape(B, 4 * n_lyap)])
+
+
+@pytest.mark.parametrize("n_lyap", [2, 3, 4])
+@pytest.mark.parametrize("name", ["dopri5", "RK45"])
+def test_quad_storage_equals_thread_storage(n_lyap, name):
+	"""quad storage (a group of lanes per trajectory, lane j integrates the state and tangent vector j in registers, norms
+	and Gram–Schmidt by shuffles within the group; n_lyap = 3: one idle lane per group) against the
+	thread-per-trajectory kernel with the whole system in shared memory: the same arithmetic up to the order of the sums
+	over components.  B = 101: groups of the last warp leave early."""
+	B, times = 101, [10.0, 20.0, 25.0]
+	Y0 = _tangent_ensemble(B, n_lyap, seed=n_lyap)
+	atol = np.r_[np.full(4, 1e-12), 10.0 ** np.random.default_rng(1).uniform(-12, -10, 4 * n_lyap)]
+	outcome = {}
+	for storage in ("quad", "shared"):
+		ODE = jitcode_lyap(W.fhn()["f_sym"], n_lyap=n_lyap, verbose=False)
+		ODE.set_integrator(name, storage=storage, rtol=1e-6, atol=atol)
+		assert ODE.integrator.module.info.storage == {"quad": 5, "shared": 3}[storage]
+		jitcode.set_initial_value(ODE, Y0, 0.0)
+		states, lyaps = ODE.integrate_many(times)
+		tangents = ODE.y[:, 4:].reshape(B, n_lyap, 4)
+		outcome[storage] = (states, lyaps, tangents, ODE.step_counts())
+		assert_allclose(np.einsum("bki,bli->bkl", tangents, tangents), np.broadcast_to(np.eye(n_lyap), (B, n_lyap, n_lyap)), atol=1e-12)
+		# f of the full system through the module's own evaluation kernel
+		full = np.hstack([states[-1], tangents.reshape(B, -1)])
+		outcome[storage] += (ODE.f(25.0, full),)
+	quad, shared = outcome["quad"], outcome["shared"]
+	assert_allclose(quad[0], shared[0], rtol=1e-9, atol=1e-12)
+	assert_allclose(quad[1], shared[1], rtol=1e-7, atol=1e-9)
+	assert_allclose(quad[2], shared[2], rtol=0, atol=1e-7)
+	assert abs(sum(quad[3]) - sum(shared[3])) <= 0.01 * sum(shared[3])
+	assert_allclose(quad[4], shared[4], rtol=1e-12, atol=1e-15)
+
+
+def test_quad_storage_is_the_default_for_small_lyapunov_systems():
+	ODE = jitcode_lyap(W.fhn()["f_sym"], n_lyap=4, verbose=False, seed=1)
+	ODE.set_integrator("dopri5")
+	assert ODE.integrator.module.info.storage == 5
+	# 8th-order pair: 16 stage rows × 8 components do not fit a thread's registers
+	ODE.set_integrator("dop853")
+	assert ODE.integrator.module.info.storage != 5
+	# accumulated exponents (lyap_acc) of a quad launch equal the mean of the recorded ones
+	ODE.set_integrator("dopri5")
+	ODE.set_initial_value(np.tile(W.FHN_Y0, (37, 1)), 0.0)
+	ODE.integrator.lyap_acc.zero_()
+	states, lyaps = ODE.integrate_many([10.0 * k for k in range(1, 9)], discard=2)
+	from jitcode_b200._integrator import padded
+	acc = ODE.integrator._unpack(ODE.integrator.lyap_acc[:4 * padded(37)], 4).cpu().numpy()
+	assert_allclose(acc, lyaps[2:].sum(axis=0), rtol=1e-12, atol=1e-14)
