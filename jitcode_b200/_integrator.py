@@ -365,12 +365,15 @@ class CudaEnsembleIntegrator:
 		if T == self.time and self.driver != JB_DRV_IVP_DENSE:
 			if into is not None:
 				into.copy_(self._rows)
+				return into
 			return self._export(self._rows)       # ODE_wrapper.integrate :142-143
 		_, lyap_rec = self._launch([T], record=False)
 		self._rows = self._current_rows(into)
 		if self.n_out:
 			self.last_lyaps = self._unpack(lyap_rec, self.n_out)
 		self._check_failures()
+		if into is not None and out is None:
+			return into                           # the caller's device buffer is the result: no copy to the host
 		return self._export(self._rows, out)
 
 	def integrate_many(self, times, record_states=True):

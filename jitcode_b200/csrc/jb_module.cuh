@@ -77,24 +77,23 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 		using T = Team<Sys::TEAM_WARPS>;
 		const int team = T::index();
 		double *const mine = jb_smem + Shared::TABLE_DOUBLES + (size_t) team * (Shared::ROWS * Sys::NROW + Shared::SCRATCH);
-		if (a.queue) {
-			// work queue: a team takes the next trajectory when it has finished its own (adaptive step counts differ)
-			double *const slot = mine + Shared::ROWS * Sys::NROW;      // the team's reduction scratch doubles as mailbox
-			while (true) {
+		// with the caller's counter: work queue — a team takes the next trajectory when it has finished its own (adaptive
+		// step counts differ); without: every team strides statically over the ensemble
+		double *const slot = mine + Shared::ROWS * Sys::NROW;      // the team's reduction scratch doubles as mailbox
+		const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
+		int64_t b = (int64_t) blockIdx.x * Shared::WARPS + team - stride;
+		while (true) {
+			if (a.queue) {
 				if (T::rank() == 0) *reinterpret_cast<unsigned long long *>(slot) = atomicAdd(a.queue, 1ull);
 				T::sync();
-				const int64_t b = (int64_t) *reinterpret_cast<const unsigned long long *>(slot);
+				b = (int64_t) *reinterpret_cast<const unsigned long long *>(slot);
 				T::sync();
-				if (b >= a.B) break;
-				run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
-				T::sync();
+			} else {
+				b += stride;
 			}
-		} else {
-			const int64_t stride = (int64_t) gridDim.x * Shared::WARPS;
-			for (int64_t b = (int64_t) blockIdx.x * Shared::WARPS + team; b < a.B; b += stride) {
-				run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
-				T::sync();
-			}
+			if (b >= a.B) break;
+			run_trajectory<Sys, Tab, JB_MODULE_DRIVER, MODE, JB_MODULE_KREGS>(a, b, mine, jb_smem);
+			T::sync();
 		}
 	} else if constexpr (MODE == JB_STORE_SHARED) {
 		extern __shared__ __align__(16) double jb_smem[];

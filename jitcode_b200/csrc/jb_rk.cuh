@@ -614,25 +614,27 @@ struct Stepper : Store {
 // at every step while a suspicion is pending; 15 suspicious steps in a row end the call with IDID = −4 (which
 // ODE_wrapper.integrate, integrator_tools.py:137-140, turns into UnsuccessfulIntegration), 6 harmless ones clear it.
 struct StiffnessWatch {
-	static constexpr int NSTIFF = 1000;
-	int countdown, iasti, nonsti;
-	double hlamb;
-	__device__ __forceinline__ void reset() { countdown = NSTIFF; iasti = nonsti = 0; hlamb = 0.0; }
+	static constexpr unsigned NSTIFF = 1000;
+	// one register: bits 0-9 accepted steps until the next look, 10-13 IASTI (suspicious steps in a row), 14-16 NONSTI
+	// (harmless steps in a row), 17 whether the last estimate exceeded the limit (HLAMB is only ever compared with it)
+	unsigned bits;
+	__device__ __forceinline__ void reset() { bits = NSTIFF; }
 	// called once per accepted step; true if the sums are wanted for this step
 	__device__ __forceinline__ bool due()
 	{
-		if (--countdown == 0) { countdown = NSTIFF; return true; }
-		return iasti > 0;
+		if (((--bits) & 0x3ffu) == 0u) { bits |= NSTIFF; return true; }
+		return (bits & 0x3c00u) != 0u;
 	}
 	// returns true if the solver gives up
 	__device__ __forceinline__ bool judge(double h, double stnum, double stden, double limit)
 	{
-		if (stden > 0.0) hlamb = fabs(h) * sqrt(stnum / stden);
-		if (hlamb > limit) {
-			nonsti = 0;
-			return ++iasti == 15;
+		if (stden > 0.0) bits = (fabs(h) * sqrt(stnum / stden) > limit) ? (bits | 0x20000u) : (bits & ~0x20000u);
+		if (bits & 0x20000u) {
+			bits = (bits & ~0x1c000u) + 0x400u;                 // NONSTI = 0, ++IASTI
+			return ((bits >> 10) & 0xfu) == 15u;
 		}
-		if (++nonsti == 6) iasti = 0;
+		if (((bits >> 14) & 0x7u) < 7u) bits += 0x4000u;       // ++NONSTI (the Fortran counts on; only "== 6" matters, so 7 = "more")
+		if (((bits >> 14) & 0x7u) == 6u) bits &= ~0x3c00u;     // IASTI = 0
 		return false;
 	}
 };
@@ -850,7 +852,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 
 	int status = a.status[b];
 	double t = a.t[b];
-	int64_t n_acc = 0, n_rej = 0;
+	int n_acc = 0, n_rej = 0;       // of this launch (one register each; the caller's totals are 64-bit)
 
 	// ---- canonical (caller-visible) locations
 	auto user = [&](double *base) {
@@ -942,8 +944,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 				}
 				double log_facold = -9.210340371976182;      // facold = 1e-4
 				bool reject = false, last = false;
-				int64_t nstep = 0;
-				const int64_t nmax = a.nsteps > 0 ? a.nsteps : 100000;
+				int nstep = 0;
+				const int nmax = a.nsteps > 0 ? (int) (a.nsteps < 2000000000 ? a.nsteps : 2000000000) : 100000;
 				StiffnessWatch stiff;
 				stiff.reset();
 				while (true) {
@@ -956,17 +958,19 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					// fac11 = err^expo1 and facold^beta through one logarithm per attempt (facold is the previous error)
 					const double log_err = log(err);
 					if (err <= 1.0) {
-						double fac = exp(a.expo1 * log_err - a.beta * log_facold);
-						fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
-						double hnew = h / fac;
-						log_facold = fmax(log_err, -9.210340371976182);     // facold = max(err, 1e-4)
 						++n_acc;
 						st.finish_accepted(t, h);
-						if (stiff.due()) {
+#ifndef JB_NO_STIFFNESS
+						if (stiff.due()) {      // (before the new step size is worked out: fewer values alive across the sums)
 							double stnum, stden;
 							st.stiffness_sums(h, stnum, stden);
 							if (stiff.judge(h, stnum, stden, Tab::STIFF_LIMIT)) { status = JB_STIFF; break; }
 						}
+#endif
+						double fac = exp(a.expo1 * log_err - a.beta * log_facold);
+						fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
+						double hnew = h / fac;
+						log_facold = fmax(log_err, -9.210340371976182);     // facold = max(err, 1e-4)
 						st.accept_y();
 						st.template fsal<0, S>();
 						t = last ? T : t + h;
@@ -1013,8 +1017,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			const double max_step = a.max_step > 0.0 ? a.max_step : INFINITY;
 			const double t_bound = DENSE ? INFINITY : T;
 			// solve_ivp has no step limit; a launch must end nevertheless
-			constexpr int64_t ATTEMPT_CAP = (int64_t) 1 << 26;
-			int64_t attempts_here = 0;
+			constexpr int ATTEMPT_CAP = 1 << 26;
+			int attempts_here = 0;
 			while (status == JB_OK && (t < T || (DENSE && !(t_old == t_old)))) {
 				// ---- begin a step: K[0] = f(t, Y)
 				if (pending_f) {
@@ -1147,9 +1151,10 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			}
 		}
 
+		if constexpr (Sys::NL > 0)      // (modules without tangent vectors: nothing of this is compiled — six registers less)
 		if (a.post != JB_POST_NONE) {
 			double norms[NLY];
-			if constexpr (Sys::NL > 0) {
+			{
 				if constexpr (WARP) {
 					// through the Z row: the state may live in registers, the tangent vectors are needed by every thread
 					st.for_each([&](int i, auto r) { st.set_z(i, r, st.y(i, r)); });
@@ -1234,7 +1239,9 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 		if (a.n_accepted) a.n_accepted[b] += n_acc;
 		if (a.n_rejected) a.n_rejected[b] += n_rej;
 	}
-	if constexpr (QUAD) {
+	if constexpr (Sys::NL <= 0) {
+		// no tangent vectors, no exponents
+	} else if constexpr (QUAD) {
 		if (a.lyap_acc && a.post != JB_POST_NONE && owner) {
 			const int n_out = Sys::NL;
 			a.lyap_acc[tile_offset(b, n_out) + member * TILE] += lyap_sum[0];
@@ -1282,13 +1289,13 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 	st.atol_vec = a.atol_vec;
 	st.comp = nullptr;
 	const double T = a.times[0];
-	const int64_t nmax = a.nsteps > 0 ? a.nsteps : 100000;
+	const int nmax = a.nsteps > 0 ? (int) (a.nsteps < 2000000000 ? a.nsteps : 2000000000) : 100000;
 	const int lane = threadIdx.x & 31;
 	int64_t b = -1;             // the trajectory this lane integrates; −1: none
 	bool more = true;           // the queue may still hold trajectories
 	double t = 0.0, h = 0.0, hmax = 0.0, log_facold = 0.0;
 	bool reject = false, last = false;
-	int64_t nstep = 0, n_acc = 0, n_rej = 0;
+	int nstep = 0, n_acc = 0, n_rej = 0;
 	int status = JB_OK;
 	StiffnessWatch stiff;
 	stiff.reset();
@@ -1360,10 +1367,6 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 				const double err = st.attempt(t, h);
 				const double log_err = log(err);
 				if (err <= 1.0) {
-					double fac = exp(a.expo1 * log_err - a.beta * log_facold);
-					fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
-					double hnew = h / fac;
-					log_facold = fmax(log_err, -9.210340371976182);
 					++n_acc;
 					st.finish_accepted(t, h);
 					bool gave_up = false;
@@ -1376,6 +1379,10 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 						status = JB_STIFF;
 						finished = true;
 					} else {
+						double fac = exp(a.expo1 * log_err - a.beta * log_facold);
+						fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
+						double hnew = h / fac;
+						log_facold = fmax(log_err, -9.210340371976182);
 						st.accept_y();
 						st.template fsal<0, S>();
 						t = last ? T : t + h;
