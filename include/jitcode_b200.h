@@ -179,7 +179,7 @@ typedef struct jb_dense_args {
 	int64_t *n_accepted, *n_rejected;   /* [ld] += */
 	int32_t *scratch;          /* [ld/32 + 2] device scratch */
 	int32_t *host_flag;        /* one int32 in (pinned) host memory: the host polls the number of unfinished trajectories */
-	int32_t  rounds_per_check; /* lock-step rounds between two polls; 0 = default */
+	int32_t  rounds_per_check; /* lock-step rounds between two polls; 0 = default (1: a round takes milliseconds, a poll microseconds) */
 	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1) */
 	int64_t *rounds_out;       /* host: number of lock-step rounds of this call, or NULL */
 	void    *stream;
@@ -193,6 +193,8 @@ int jb_dense_integrate(const jb_dense_args *args);
 int jb_dense_eval_f(const jb_dense_args *args, double *dY);
 /* C[M][N] = A[M][K] * B[K][N], row-major FP64 on the FP64 tensor cores (exported for tests) */
 int jb_dense_gemm(const double *A, const double *B, double *C, int M, int N, int K, void *stream);
+/* the same with the block-tile shape given instead of chosen (0: 128 x 64, 1: 112 x 64, 2: 96 x 64, 3: 64 x 64; needs even K and N) */
+int jb_dense_gemm_shape(const double *A, const double *B, double *C, int M, int N, int K, int shape, void *stream);
 /* out[c*ld_out + r] = in[r*ld_in + c]: (B, n) rows <-> [n][ld] */
 int jb_dense_transpose(const double *in, double *out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, void *stream);
 

@@ -77,7 +77,7 @@ class DenseArgs(ctypes.Structure):
 	]
 
 DENSE_EXPORTS = ("jb_dense_work_vectors", "jb_dense_control_scalars", "jb_dense_last_error", "jb_dense_launch_count",
-		"jb_dense_integrate", "jb_dense_eval_f", "jb_dense_gemm", "jb_dense_transpose")
+		"jb_dense_integrate", "jb_dense_eval_f", "jb_dense_gemm", "jb_dense_gemm_shape", "jb_dense_transpose")
 
 _library = None
 
@@ -95,6 +95,7 @@ def dense_library():
 		lib.jb_dense_integrate.argtypes = [ctypes.POINTER(DenseArgs)]
 		lib.jb_dense_eval_f.argtypes = [ctypes.POINTER(DenseArgs), ctypes.c_void_p]
 		lib.jb_dense_gemm.argtypes = [ctypes.c_void_p]*3 + [ctypes.c_int]*3 + [ctypes.c_void_p]
+		lib.jb_dense_gemm_shape.argtypes = [ctypes.c_void_p]*3 + [ctypes.c_int]*4 + [ctypes.c_void_p]
 		lib.jb_dense_transpose.argtypes = [ctypes.c_void_p]*2 + [ctypes.c_int64]*4 + [ctypes.c_void_p]
 		lib.path = str(path)
 		_library = lib
@@ -128,7 +129,7 @@ class CudaDenseSineIntegrator:
 	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5") or DOP853 ("dop853")."""
 
 	def __init__(self, W, omega, *, method=0, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
-			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=4):
+			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=0):
 		self.device = require_cuda(device)
 		self.n = len(omega)
 		self.module = DenseModule(self.n)

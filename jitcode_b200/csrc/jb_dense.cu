@@ -132,8 +132,25 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
 // The same product, software-pipelined: tiles travel global → shared memory with cp.async (16-byte copies, zero
 // fill beyond the matrix edges) three chunks ahead of the tensor cores, so that the loads of chunk c+2 overlap
 // the DMMAs of chunk c.  Needs 16-byte aligned rows (K and N even); the kernel above is the fallback.
+//
+// The block tile is a template parameter: WM × WN warps, each with MI × NI DMMA tiles (8 × 8), i.e. a block tile of
+// (8·MI·WM) × (8·NI·WN).  Measured on 1000 × 8192 × 1000 (BASELINE config 5; profiles/r2_dgemm_*): 128 × 64 with two
+// blocks per SM runs at 30.7 TFLOP/s with the DMMA pipe 87 % busy while a block is resident (ncu: top stall
+// math_pipe_throttle, shared-memory bank conflicts 1.6 % of the wavefronts, L2 14 %) — 83 % of the measured DMMA peak
+// of 37.1 TFLOP/s; 64 × 64 30.2, 96 × 64 28.7, 112 × 64 (which would fill the last wave of blocks better) 28.0,
+// 128 × 128 and 256 × 64 with one block per SM 25.3 and 24.1.  So the tall tile is the default and the small one
+// serves matrices with few rows.
 constexpr int STAGES = 3;
-constexpr size_t PIPELINED_SHARED_BYTES = sizeof(double) * STAGES * (BM * LDA + BK * LDB);
+
+template <int WM_, int WN_, int MI_, int NI_>
+struct Shape {
+	static constexpr int WM = WM_, WN = WN_, MI = MI_, NI = NI_;
+	static constexpr int THREADS = 32 * WM * WN;
+	static constexpr int TM = 8 * MI * WM, TN = 8 * NI * WN;      // block tile
+	static constexpr int SA = BK + 4, SB = TN + 4;                 // padded rows: fragment reads hit 32 distinct banks
+	static constexpr size_t SHARED_BYTES = sizeof(double) * STAGES * (TM * SA + BK * SB);
+	static_assert(TN % 32 == 0, "column tiles are unions of 32-trajectory groups (tile_skip)");
+};
 
 __device__ __forceinline__ void cp_async_16(double *smem, const double *global, int bytes)
 {
@@ -141,45 +158,51 @@ __device__ __forceinline__ void cp_async_16(double *smem, const double *global, 
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(target), "l"(global), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+template <class S>
+__global__ void __launch_bounds__(S::THREADS)
 dgemm_dmma_pipelined_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
 		int M, int N, int K, const int *__restrict__ tile_skip, int64_t ld)
 {
+	constexpr int TM = S::TM, TN = S::TN, SA = S::SA, SB = S::SB, MI = S::MI, NI = S::NI, THREADS = S::THREADS;
 	if (tile_skip) {
-		const int64_t first = (((int64_t) blockIdx.x * BN) % ld) / 32;
-		if (tile_skip[first] && tile_skip[first + 1]) return;
+		// columns n0 … n0+TN−1 are trajectories (n0 mod ld) … of the sin or of the cos half; flags are per 32 trajectories
+		const int64_t first = (((int64_t) blockIdx.x * TN) % ld) / 32;
+		bool all = true;
+#pragma unroll
+		for (int g = 0; g < TN / 32; ++g) all = all && tile_skip[first + g];
+		if (all) return;
 	}
 	extern __shared__ __align__(16) double gemm_shared[];
-	double *const sA = gemm_shared;                                  // [STAGES][BM * LDA]
-	double *const sB = gemm_shared + STAGES * BM * LDA;               // [STAGES][BK * LDB]
+	double *const sA = gemm_shared;                                  // [STAGES][TM * SA]
+	double *const sB = gemm_shared + STAGES * TM * SA;                // [STAGES][BK * SB]
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int wm = warp >> 1, wn = warp & 1;
-	const int64_t m0 = (int64_t) blockIdx.y * BM, n0 = (int64_t) blockIdx.x * BN;
+	const int wm = warp / S::WN, wn = warp % S::WN;
+	const int64_t m0 = (int64_t) blockIdx.y * TM, n0 = (int64_t) blockIdx.x * TN;
 
-	double acc[4][4][2];
+	double acc[MI][NI][2];
 #pragma unroll
-	for (int i = 0; i < 4; ++i)
+	for (int i = 0; i < MI; ++i)
 #pragma unroll
-		for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+		for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 	auto issue = [&](int stage, int k0) {
-		// A tile: 128 rows × 8 chunks of 2 doubles; 4 chunks per thread
+		// A tile: TM rows × 8 chunks of 2 doubles
 #pragma unroll
-		for (int c = tid; c < BM * (BK / 2); c += 256) {
+		for (int c = tid; c < TM * (BK / 2); c += THREADS) {
 			const int row = c / (BK / 2), kk = (c % (BK / 2)) * 2;
 			const int64_t gm = m0 + row;
 			const int gk = k0 + kk;
 			const int bytes = (gm < M && gk < K) ? 16 : 0;
-			cp_async_16(sA + stage * BM * LDA + row * LDA + kk, A + (bytes ? gm * K + gk : 0), bytes);
+			cp_async_16(sA + stage * TM * SA + row * SA + kk, A + (bytes ? gm * K + gk : 0), bytes);
 		}
-		// B tile: 16 rows × 32 chunks; 2 chunks per thread
+		// B tile: 16 rows × TN/2 chunks
 #pragma unroll
-		for (int c = tid; c < BK * (BN / 2); c += 256) {
-			const int row = c / (BN / 2), col = (c % (BN / 2)) * 2;
+		for (int c = tid; c < BK * (TN / 2); c += THREADS) {
+			const int row = c / (TN / 2), col = (c % (TN / 2)) * 2;
 			const int gk = k0 + row;
 			const int64_t gn = n0 + col;
 			const int bytes = (gk < K && gn < N) ? 16 : 0;
-			cp_async_16(sB + stage * BK * LDB + row * LDB + col, B + (bytes ? (int64_t) gk * N + gn : 0), bytes);
+			cp_async_16(sB + stage * BK * SB + row * SB + col, B + (bytes ? (int64_t) gk * N + gn : 0), bytes);
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 	};
@@ -197,27 +220,27 @@ dgemm_dmma_pipelined_kernel(const double *__restrict__ A, const double *__restri
 		if (ahead < chunks) issue(ahead % STAGES, ahead * BK);
 		else asm volatile("cp.async.commit_group;" ::: "memory");
 		const int stage = chunk % STAGES;
-		const double *a = sA + stage * BM * LDA + (wm * 32 + (lane >> 2)) * LDA + (lane & 3);
-		const double *b = sB + stage * BK * LDB + (lane & 3) * LDB + wn * 32 + (lane >> 2);
+		const double *a = sA + stage * TM * SA + (wm * 8 * MI + (lane >> 2)) * SA + (lane & 3);
+		const double *b = sB + stage * BK * SB + (lane & 3) * SB + wn * 8 * NI + (lane >> 2);
 #pragma unroll
 		for (int kk = 0; kk < BK; kk += 4) {
-			double fa[4], fb[4];
+			double fa[MI], fb[NI];
 #pragma unroll
-			for (int i = 0; i < 4; ++i) fa[i] = a[i * 8 * LDA + kk];
+			for (int i = 0; i < MI; ++i) fa[i] = a[i * 8 * SA + kk];
 #pragma unroll
-			for (int j = 0; j < 4; ++j) fb[j] = b[kk * LDB + j * 8];
+			for (int j = 0; j < NI; ++j) fb[j] = b[kk * SB + j * 8];
 #pragma unroll
-			for (int i = 0; i < 4; ++i)
+			for (int i = 0; i < MI; ++i)
 #pragma unroll
-				for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+				for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
 		}
 	}
 #pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		const int64_t gm = m0 + wm * 32 + i * 8 + (lane >> 2);
+	for (int i = 0; i < MI; ++i) {
+		const int64_t gm = m0 + wm * 8 * MI + i * 8 + (lane >> 2);
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			const int64_t gn = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
+		for (int j = 0; j < NI; ++j) {
+			const int64_t gn = n0 + wn * 8 * NI + j * 8 + 2 * (lane & 3);
 			if (gm < M && gn < N) C[gm * N + gn] = acc[i][j][0];
 			if (gm < M && gn + 1 < N) C[gm * N + gn + 1] = acc[i][j][1];
 		}
@@ -618,20 +641,39 @@ static int fail(int code, const char *what)
 
 #define JBD_LAUNCH(kernel, grid, block, ...) do { kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); jbd::launch_counter.fetch_add(1, std::memory_order_relaxed); } while (0)
 
-static void launch_gemm(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream)
+// the block-tile shapes that are compiled, tallest first
+using Shape128 = Shape<4, 2, 4, 4>;      // 128 × 64, 256 threads
+using Shape112 = Shape<7, 2, 2, 4>;      // 112 × 64, 448 threads
+using Shape96 = Shape<4, 2, 3, 4>;       //  96 × 64, 256 threads
+using Shape64 = Shape<4, 2, 2, 4>;       //  64 × 64, 256 threads
+constexpr int N_SHAPES = 4;
+
+template <class S>
+static void launch_shape(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream)
 {
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SHARED_BYTES);
-		cudaFuncSetAttribute(dgemm_dmma_pipelined_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) PIPELINED_SHARED_BYTES);
-		configured = true;
-	}
-	const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+	// (the attribute is a per-device property of the function; setting it costs a microsecond and keeps this re-entrant)
+	cudaFuncSetAttribute(dgemm_dmma_pipelined_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) S::SHARED_BYTES);
+	const dim3 grid((N + S::TN - 1) / S::TN, (M + S::TM - 1) / S::TM);
+	dgemm_dmma_pipelined_kernel<S><<<grid, S::THREADS, S::SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
+}
+
+static void launch_gemm(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream, int shape = -1)
+{
 	const bool aligned = K % 2 == 0 && N % 2 == 0 && (((uintptr_t) A | (uintptr_t) B) & 15) == 0;
-	if (aligned)
-		dgemm_dmma_pipelined_kernel<<<grid, 256, PIPELINED_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
-	else
+	if (!aligned) {
+		cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SHARED_BYTES);
+		const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
 		dgemm_dmma_kernel<<<grid, 256, GEMM_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
+		launch_counter.fetch_add(1, std::memory_order_relaxed);
+		return;
+	}
+	if (shape < 0) shape = M <= 64 ? 3 : (M <= 96 ? 2 : 0);
+	switch (shape) {
+	case 1: launch_shape<Shape112>(A, B, C, M, N, K, tile_skip, ld, stream); break;
+	case 2: launch_shape<Shape96>(A, B, C, M, N, K, tile_skip, ld, stream); break;
+	case 3: launch_shape<Shape64>(A, B, C, M, N, K, tile_skip, ld, stream); break;
+	default: launch_shape<Shape128>(A, B, C, M, N, K, tile_skip, ld, stream); break;
+	}
 	launch_counter.fetch_add(1, std::memory_order_relaxed);
 }
 
@@ -655,6 +697,14 @@ int jb_dense_gemm(const double *A, const double *B, double *C, int M, int N, int
 	jbd::launch_gemm(A, B, C, M, N, K, nullptr, 0, stream);
 	const cudaError_t err = cudaGetLastError();
 	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_gemm");
+}
+
+int jb_dense_gemm_shape(const double *A, const double *B, double *C, int M, int N, int K, int shape, void *stream_)
+{
+	if (shape < 0 || shape >= jbd::N_SHAPES) return jbd::fail(JB_E_BAD_ARGUMENT, "jb_dense_gemm_shape: shapes are 0 (128 x 64), 1 (112 x 64), 2 (96 x 64), 3 (64 x 64)");
+	jbd::launch_gemm(A, B, C, M, N, K, nullptr, 0, (cudaStream_t) stream_, shape);
+	const cudaError_t err = cudaGetLastError();
+	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_gemm_shape");
 }
 
 int jb_dense_transpose(const double *in, double *out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, void *stream_)
@@ -761,7 +811,7 @@ static int integrate(const jb_dense_args *x)
 	JBD_LAUNCH(jbd::first_step_kernel<Tab>, tgrid, 256, d, have_probe);
 
 	// ---- rounds: one step attempt of every unfinished trajectory; the host looks at the counter every few rounds
-	const int check_every = x->rounds_per_check > 0 ? x->rounds_per_check : 4;
+	const int check_every = x->rounds_per_check > 0 ? x->rounds_per_check : 1;
 	int64_t rounds = 0;
 	while (true) {
 		for (int r = 0; r < check_every; ++r) {

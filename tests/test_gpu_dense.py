@@ -37,6 +37,45 @@ def test_dmma_gemm(M, N, K):
 	assert_allclose(C.cpu().numpy(), expected, rtol=1e-12, atol=1e-12 * np.sqrt(K))
 
 
+@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 1000), (250, 130, 62), (113, 64, 16)])
+def test_dmma_gemm_every_tile_shape(shape, M, N, K):
+	"""the pipelined GEMM is compiled for four block-tile shapes (launch_gemm picks the one whose last wave of blocks is
+	fullest); each of them on sizes with ragged edges in M, N and K"""
+	lib = _dense.dense_library()
+	rng = np.random.default_rng(shape + M + N + K)
+	A = torch.as_tensor(rng.normal(size=(M, K))).cuda()
+	B = torch.as_tensor(rng.normal(size=(K, N))).cuda()
+	C = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+	stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+	assert lib.jb_dense_gemm_shape(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, shape, stream) == 0
+	assert_allclose(C.cpu().numpy(), A.cpu().numpy() @ B.cpu().numpy(), rtol=1e-12, atol=1e-12 * np.sqrt(K))
+
+
+def test_dense_kuramoto_1000_against_the_oracle():
+	"""config 5 at its full system size against the CPU oracle: 32 trajectories of the 1000-oscillator network under the
+	example's integrator (dop853, atol 1e-6, rtol 0; examples/kuramoto_network.py:29) and under dopri5, sampled like the
+	example's loop; the oracle evaluates the reference's sum edge by edge (oracle/network_rhs.py), not the GEMM form."""
+	from oracle import ensemble, network_rhs
+	data = W.kuramoto_data(1000)
+	n = data["n"]
+	Wm = data["c"] / (n - 1) * data["A"].T.astype(float)
+	np.fill_diagonal(Wm, 0.0)
+	handle = network_rhs.NetworkRhsHandle(data["A"], data["omega"], data["c"])
+	Y0 = W.kuramoto_ensemble(32, n, seed=44)
+	assert_allclose(jitcode.from_sine_coupling(Wm, data["omega"]).f(0.0, Y0[:4]), handle.f_many(0.0, Y0[:4]), rtol=1e-11, atol=1e-12)
+	times = [1.0, 2.0, 3.0, 10.0]
+	for name, tol in (("dop853", {"atol": 1e-6, "rtol": 0.0}), ("dopri5", {"atol": 1e-9, "rtol": 1e-6})):
+		ODE = jitcode.from_sine_coupling(Wm, data["omega"])
+		ODE.set_integrator(name, **tol)
+		ODE.set_initial_value(Y0, 0.0)
+		result = ODE.integrate_many(times)
+		ref = ensemble.run_ensemble(handle, name, Y0, times, **tol)
+		within_tolerance(result, ref["y"], factor=10.0, **tol)
+		attempts = sum(ODE.step_counts())
+		assert abs(attempts - ref["attempts"]) <= 0.02 * ref["attempts"]
+
+
 def kuramoto_rhs(Wm, omega, Y):
 	diff = Y[:, None, :] - Y[:, :, None]            # [b, i, j] = y_j − y_i
 	return omega + np.einsum("ij,bij->bi", Wm, np.sin(diff))

@@ -220,3 +220,20 @@ def test_stiffness_detection_dop853():
 	result = rk_numpy.HairerDopri(batched, "dop853", nsteps=10**6, **TOL).integrate(0.0, np.array([[0.0, 1.0]]), 1.0)
 	assert result["status"][0] == 3
 	assert_allclose(result["t"][0], solver.t, rtol=0.2)
+
+
+def test_network_rhs_equals_the_written_out_form():
+	"""oracle/network_rhs.py (the Kuramoto sum as a loop over adjacency lists, for networks too large to write out) against
+	the written-out form of examples/kuramoto_network.py:19-26 compiled like every other oracle system"""
+	from oracle import network_rhs
+	system = W.kuramoto(40)
+	written_out = c_rhs.build_rhs(system["f_sym"], n=40)
+	loop = network_rhs.NetworkRhsHandle(system["A"], system["omega"], system["c"])
+	for state in W.kuramoto_ensemble(6, 40, seed=2):
+		assert_allclose(loop.f(0.0, state), written_out.f(0.0, state), rtol=1e-13, atol=1e-15)
+	backend = wrappers.make_backend("dop853", loop.f, atol=1e-6, rtol=0.0)
+	reference = wrappers.make_backend("dop853", written_out.f, atol=1e-6, rtol=0.0)
+	state = W.kuramoto_ensemble(1, 40, seed=3)[0]
+	backend.set_initial_value(state, 0.0)
+	reference.set_initial_value(state, 0.0)
+	assert_allclose(backend.integrate(5.0), reference.integrate(5.0), rtol=1e-10, atol=1e-12)
