@@ -495,12 +495,17 @@ class Bench:
 		else:
 			hbm_peak, hbm_source = 6650.0, "fallback of B200_PROFILING.md"
 		hbm_achieved = 280.0 * n * own_attempts / kernel_s / 1e9     # 35·n·8 B per trajectory-step if the stages streamed through HBM
-		traffic = None
+		traffic, traffic_note = None, None
 		traffic_file = ROOT / "profiles" / "traffic.json"
 		if traffic_file.exists():
-			# dram__bytes_read.sum + dram__bytes_write.sum per trajectory-step from the committed ncu --set full capture
-			per_step = json.loads(traffic_file.read_text()).get(f"{name}:{storage_name}")
-			traffic = None if per_step is None else per_step * own_attempts
+			# dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu --set full capture of this workload
+			entry = json.loads(traffic_file.read_text()).get(f"{name}:{storage_name}")
+			if entry and "per_trajectory_step" in entry:
+				traffic = entry["per_trajectory_step"] * own_attempts
+			elif entry and "per_launch" in entry:
+				traffic = entry["per_launch"] * B / entry["trajectories"]
+			elif entry and "per_gemm_launch" in entry:
+				traffic, traffic_note = entry["per_gemm_launch"], "per launch of the GEMM kernel (one right-hand-side evaluation of the ensemble)"
 		hbm_record = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": hbm_source,
 				"algorithmic_bytes_per_trajectory_step": 280 * n}
 		fp64_record = {"achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
@@ -516,6 +521,8 @@ class Bench:
 			# state and stages never leave the chip between the sample times: the FP64 pipe is the roof; what an
 			# HBM-streaming design would have needed is kept as a second figure ("report both")
 			roofline = dict(fp64_record, bound="fp64", hbm_streaming_equivalent=hbm_record)
+		if traffic_note:
+			roofline["traffic_note"] = traffic_note
 		roofline.update({"traffic": traffic, "kernel_ms": kernel_ms,
 				"kernel": "jb_dense_integrate: dgemm_dmma_pipelined_kernel + element-wise stage kernels" if kind == "dense" else "jb_integrate_kernel"})
 		line = {
@@ -598,16 +605,21 @@ class Bench:
 		collective_ms = sum(a.elapsed_time(b) for a, b in collective_events) / steps
 		stats = torch.tensor([seconds, collective_ms], dtype=torch.float64, device=self.device)
 		dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+		# the rank that arrives last at the collective measures the transfer alone; the others also wait for it
+		fastest = torch.tensor([collective_ms], dtype=torch.float64, device=self.device)
+		dist.all_reduce(fastest, op=dist.ReduceOp.MIN)
 		counts = torch.tensor([attempts], dtype=torch.float64, device=self.device)
 		dist.all_reduce(counts, op=dist.ReduceOp.SUM)
 		seconds, collective_ms = stats.tolist()
+		transfer_ms = fastest.item()
 		if self.rank != 0:
 			return None
 		return {"value": counts.item() / seconds, "unit": UNIT, "scaling": "strong", "n_gpus": self.world, "steps": steps, "warmup": warmup,
 				"ms_per_step": 1e3 * seconds / steps, "total_trajectories": total, "workload": wl["label"], "integrator": wl["integrator"],
 				"timed_region": "per step: H2D of the rank's shard (pinned), integrate, all-gather on NCCL, D2H of the gathered ensemble on rank 0; wall clock, max over ranks",
 				"collective": {"name": "ncclAllGather (torch.distributed.all_gather_into_tensor, in place: the integrate kernel's unpack writes into the rank's slot)" if even else "all_gather of padded shards",
-						"doubles_per_rank": (end - begin) * ODE.n, "ms_per_step": collective_ms, "share_of_step": collective_ms / (1e3 * seconds / steps)},
+						"doubles_per_rank": (end - begin) * ODE.n, "ms_per_step": transfer_ms, "share_of_step": transfer_ms / (1e3 * seconds / steps),
+						"ms_per_step_including_the_wait_for_the_slowest_rank": collective_ms},
 				"h2d_bytes_per_step_per_rank": int(Y0_host.numel() * 8 + (pars_host.numel() * 8 if pars_host is not None else 0)),
 				"d2h_bytes_per_step_rank0": int(total * ODE.n * 8)}
 
