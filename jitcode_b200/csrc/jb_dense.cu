@@ -250,8 +250,11 @@ dgemm_dmma_pipelined_kernel(const double *__restrict__ A, const double *__restri
 // ---------------------------------------------------------------------------------------------
 // per-trajectory control block (structure of arrays, ctrl[k*ld + b])
 
-enum { C_H = 0, C_HMAX, C_FACOLD, C_ERR2, C_DNF, C_DNY, C_DER2, C_FLAGS, C_NSTEP, C_ERR3, C_COUNT };
-enum { F_ACTIVE = 1, F_LAST = 2, F_REJECT = 4, F_ACCEPTED = 8 };      // C_FLAGS (stored as a double holding a small int)
+enum { C_H = 0, C_HMAX, C_FACOLD, C_ERR2, C_DNF, C_DNY, C_DER2, C_FLAGS, C_NSTEP, C_ERR3,
+		C_NACC /* accepted steps of this call */, C_STIFF /* IASTI + 16·NONSTI + 128·(last estimate above the limit) */,
+		C_STNUM, C_STDEN /* sums of Hairer's stiffness estimate */, C_COUNT };
+enum { F_ACTIVE = 1, F_LAST = 2, F_REJECT = 4, F_ACCEPTED = 8, F_STIFF = 16 /* this attempt, if accepted, is looked at by the stiffness test */ };
+// C_FLAGS is stored as a double holding a small int
 // work vectors, work[k*n*ld + i*ld + b]
 enum { W_Z = 0, W_K0 = 1 /* … W_K0+12 */, W_XS = 14 /* sin | cos: 2 vectors */, W_G = 16 /* G_s | G_c: 2 vectors */, W_COUNT = 18 };
 
@@ -395,6 +398,11 @@ __device__ __forceinline__ void begin_attempt(const Dense &d, int64_t b, double 
 	if (!(h == h)) { d.status[b] = JB_NONFINITE; flags &= ~F_ACTIVE; return; }
 	if (t + 1.01 * h - d.T > 0.0) { h = d.T - t; flags |= F_LAST; }
 	nstep += 1.0;
+	// Hairer's stiffness test (dopri5.f / dop853.f) looks at every 1000th accepted step of a call and at every step while
+	// a suspicion is pending; whether THIS attempt would be such a step is known before it is made
+	const int64_t accepted_then = (int64_t) d.ctrl[C_NACC * d.ld + b] + 1;
+	const int iasti = (int) d.ctrl[C_STIFF * d.ld + b] & 15;
+	flags = (accepted_then % 1000 == 0 || iasti > 0) ? (flags | F_STIFF) : (flags & ~F_STIFF);
 }
 
 __device__ __forceinline__ void publish_activity(const Dense &d, int64_t b, bool active)
@@ -419,6 +427,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const Dense d)
 		d.ctrl[C_FACOLD * d.ld + b] = 1e-4;
 		d.ctrl[C_NSTEP * d.ld + b] = 0.0;
 		d.ctrl[C_DNF * d.ld + b] = d.ctrl[C_DNY * d.ld + b] = d.ctrl[C_DER2 * d.ld + b] = d.ctrl[C_ERR2 * d.ld + b] = d.ctrl[C_ERR3 * d.ld + b] = 0.0;
+		d.ctrl[C_NACC * d.ld + b] = d.ctrl[C_STIFF * d.ld + b] = d.ctrl[C_STNUM * d.ld + b] = d.ctrl[C_STDEN * d.ld + b] = 0.0;
 	}
 	publish_activity(d, b, active);
 }
@@ -526,8 +535,10 @@ __global__ void __launch_bounds__(256) error_kernel(const Dense d)
 {
 	constexpr int S = Tab::NSTAGE;
 	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
-	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
-	double sum = 0.0;
+	const int flags = b < d.B ? flags_of(d, b) : 0;
+	const bool active = flags & F_ACTIVE;
+	const bool stiff_due = active && (flags & F_STIFF);
+	double sum = 0.0, stnum = 0.0, stden = 0.0;
 	if (active) {
 		const double h = d.ctrl[C_H * d.ld + b];
 		for_rows(d, [&](int i, int64_t, int64_t at) {
@@ -542,9 +553,25 @@ __global__ void __launch_bounds__(256) error_kernel(const Dense d)
 				const double q = h * e / sk;
 				sum = fma(q, q, sum);
 			}
+			if (stiff_due) {
+				// ρ ≈ h·|f(t+h, y_new) − K[S-1]| / |y_new − g|, g = the input of the last stage (jb_rk.cuh, stiffness_sums)
+				double acc = 0.0;
+				static_for<0, S - 1>([&](auto j) {
+					constexpr double a = Coef<Tab>::a(S - 1, j);
+					if constexpr (a != 0.0) acc = fma(a, vec(d, W_K0 + j)[at], acc);
+				});
+				const double dk = last - vec(d, W_K0 + S - 1)[at];
+				const double dy = vec(d, W_Z)[at] - fma(h, acc, d.Y[at]);
+				stnum = fma(dk, dk, stnum);
+				stden = fma(dy, dy, stden);
+			}
 		});
 	}
 	if constexpr (Tab::ERR_NEEDS_FSAL) reduce_to(d.ctrl + C_ERR2 * d.ld, b, active, sum);
+	if (__syncthreads_or(stiff_due)) {
+		reduce_to(d.ctrl + C_STNUM * d.ld, b, stiff_due, stnum);
+		reduce_to(d.ctrl + C_STDEN * d.ld, b, stiff_due, stden);
+	}
 }
 
 // one thread per trajectory: accept or reject, new step size, and the top of the next pass of the step loop
@@ -573,9 +600,32 @@ __global__ void __launch_bounds__(256) control_kernel(const Dense d)
 			double fac = d.beta > 0.0 ? fac11 / pow(facold, d.beta) : fac11;
 			fac = fmax(d.facc2, fmin(d.facc1, fac / d.safety));
 			double hnew = h / fac;
+			bool gave_up = false;
 			if (err <= 1.0) {
-				facold = fmax(err, 1e-4);
 				d.n_accepted[b] += 1;
+				d.ctrl[C_NACC * d.ld + b] += 1.0;
+				if (flags & F_STIFF) {
+					int watch = (int) d.ctrl[C_STIFF * d.ld + b];
+					int iasti = watch & 15, nonsti = (watch >> 4) & 7, above = watch >> 7;
+					const double stnum = d.ctrl[C_STNUM * d.ld + b], stden = d.ctrl[C_STDEN * d.ld + b];
+					if (stden > 0.0) above = fabs(h) * sqrt(stnum / stden) > Tab::STIFF_LIMIT;
+					if (above) {
+						nonsti = 0;
+						gave_up = ++iasti == 15;
+					} else {
+						if (nonsti < 7) ++nonsti;
+						if (nonsti == 6) iasti = 0;
+					}
+					d.ctrl[C_STIFF * d.ld + b] = (double) ((iasti & 15) | (nonsti << 4) | (above << 7));
+				}
+			}
+			d.ctrl[C_STNUM * d.ld + b] = d.ctrl[C_STDEN * d.ld + b] = 0.0;
+			if (gave_up) {
+				// IDID = −4: the solver returns before it commits the step (t and Y stay)
+				d.status[b] = JB_STIFF;
+				flags &= ~(F_ACTIVE | F_LAST);
+			} else if (err <= 1.0) {
+				facold = fmax(err, 1e-4);
 				flags |= F_ACCEPTED;
 				t = (flags & F_LAST) ? d.T : t + h;
 				if (fabs(hnew) > hmax) hnew = hmax;

@@ -72,8 +72,9 @@ def test_dense_kuramoto_1000_against_the_oracle():
 		result = ODE.integrate_many(times)
 		ref = ensemble.run_ensemble(handle, name, Y0, times, **tol)
 		within_tolerance(result, ref["y"], factor=10.0, **tol)
-		attempts = sum(ODE.step_counts())
-		assert abs(attempts - ref["attempts"]) <= 0.02 * ref["attempts"]
+		# the oracle counts right-hand-side evaluations (÷ 12 or 6), which include the two of every fresh start
+		evaluations = {"dop853": 12, "dopri5": 6}[name] * sum(ODE.step_counts()) + 2 * len(times) * len(Y0)
+		assert abs(evaluations - ref["nfev"].sum()) <= 0.03 * ref["nfev"].sum()
 
 
 def kuramoto_rhs(Wm, omega, Y):
@@ -168,3 +169,37 @@ def test_dense_kuramoto_1000():
 	# the mean phase velocity is the mean frequency plus the antisymmetric-part imbalance; for every trajectory
 	# Σ_i dy_i/dt = Σω + Σ_ij W_ij sin(y_j − y_i) holds — check f at the final state against NumPy once more
 	assert_allclose(ODE.f(0.0, fine[:8]), kuramoto_rhs(Wm, data["omega"], fine[:8]), rtol=1e-11, atol=1e-12)
+
+
+def test_dense_stiffness_detection():
+	"""Hairer's stiffness test in the dense engine (control block C_NACC / C_STIFF / C_STNUM / C_STDEN): strongly coupled
+	oscillators lock within a fraction of a time unit and the locked state is stiff for an explicit pair — SciPy's
+	dopri5 gives up after 1000 + 14 accepted steps (IDID −4 → UnsuccessfulIntegration, integrator_tools.py:137-140);
+	so does every trajectory here, at the oracle's time and state; a weakly coupled ensemble of the same size arrives."""
+	from jitcode_b200 import UnsuccessfulIntegration
+	from oracle import rk_numpy
+	n, B = 32, 6
+	rng = np.random.default_rng(11)
+	omega = rng.uniform(-0.5, 0.5, n)
+	Y0 = rng.uniform(0, 0.3, (B, n))
+	for strength, stiff in ((1e4, True), (1.0, False)):
+		Wm = np.full((n, n), strength / n)
+		np.fill_diagonal(Wm, 0.0)
+		ODE = jitcode.from_sine_coupling(Wm, omega)
+		ODE.set_integrator("dopri5", rtol=1e-6, atol=1e-12)
+		assert ODE.integrator.module.info.storage == 4
+		ODE.set_initial_value(Y0, 0.0)
+		ref = rk_numpy.HairerDopri(lambda t, Y: kuramoto_rhs(Wm, omega, Y), "dopri5", rtol=1e-6, atol=1e-12, nsteps=10**6).integrate(0.0, Y0, 2.0)
+		if stiff:
+			with pytest.raises(UnsuccessfulIntegration) as failure:
+				ODE.integrate(2.0)
+			assert list(failure.value.indices) == list(range(B)) and set(failure.value.status) == {3}
+			assert set(ref["status"]) == {3}
+			assert np.all(ODE.integrator.n_accepted[:B].cpu().numpy() == 1014)
+		else:
+			ODE.integrate(2.0)
+			assert set(ref["status"]) == {0}
+		# at the stability limit the step sequence amplifies rounding differences (tests/test_oracle_pin.py): the time at
+		# which the test gives up agrees to a few per cent there, and to rounding where the problem is not stiff
+		assert_allclose(ODE.integrator.tt[:B].cpu().numpy(), ref["t"], rtol=0.05 if stiff else 1e-12)
+		assert_allclose(ODE.integrator.y_device.cpu().numpy(), ref["y"], rtol=1e-6, atol=0.05 if stiff else 1e-9)
