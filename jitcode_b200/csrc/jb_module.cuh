@@ -356,6 +356,8 @@ int jb_integrate(const jb_integrate_args *x)
 	const double dfactor = x->dfactor > 0.0 ? x->dfactor : (dp5 ? 0.2 : 0.3);
 	a.facc1 = 1.0 / dfactor;
 	a.facc2 = 1.0 / ifactor;
+	a.dfactor = dfactor;
+	a.ifactor = ifactor;
 	if (dp5) {
 		a.beta = x->beta == 0.0 ? 0.04 : (x->beta < 0.0 ? 0.0 : x->beta);
 		a.expo1 = 0.2 - a.beta * 0.75;

@@ -214,6 +214,7 @@ struct Params {             // kernel argument block (by value)
 	double max_step, first_step;
 	int64_t nsteps;
 	double safety, facc1, facc2, beta, expo1;
+	double dfactor, ifactor;       // = 1/facc1, 1/facc2: the limits of h_new/h (the step-size rules below multiply, never divide)
 	double *t, *Y;
 	const double *P;
 	double *state, *sstate, *work, *Yres, *Yrec, *lyap_rec, *lyap_acc;
@@ -524,7 +525,16 @@ struct Stepper : Store {
 		});
 	}
 
-	// one step attempt from (t, Y, K[0]) with step h: fills K[1..], Z = y_new; returns the error norm
+	// What attempt() returns: the error norm err of the 8th-order pair, but err² of the pairs whose norm is a plain root
+	// mean square — the controllers only need log(err) = ½·log(err²) and the comparison with 1, and a double-precision
+	// square root is some twenty instructions per attempt.  sqrt(x) <= 1 ⇔ x <= 1 + 2⁻⁵² and sqrt(x) < 1 ⇔ x < 1 in
+	// round-to-nearest, so the decisions are exactly those of the reference's err <= 1 (Hairer) and err < 1 (SciPy).
+	static constexpr bool ERR_SQUARED = Tab::ERR_NEEDS_FSAL;
+	static __device__ __forceinline__ bool accepted_hairer(double e) { return ERR_SQUARED ? e <= 1.0000000000000002 : e <= 1.0; }
+	static __device__ __forceinline__ bool accepted_scipy(double e) { return e < 1.0; }
+	static __device__ __forceinline__ double log_error(double e) { return ERR_SQUARED ? 0.5 * log(e) : log(e); }
+
+	// one step attempt from (t, Y, K[0]) with step h: fills K[1..], Z = y_new; returns the error measure (see above)
 	__device__ __forceinline__ double attempt(double t, double h)
 	{
 		static_for<1, S>([&](auto s) {
@@ -545,7 +555,7 @@ struct Stepper : Store {
 				const double q = h * e / sk;
 				return q * q;
 			});
-			return sqrt(sum / N);
+			return sum * (1.0 / N);
 		} else {
 			double s5, s3;
 			this->sum2([&](int i, auto r, double &a5, double &a3) {
@@ -956,8 +966,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					++nstep;
 					const double err = st.attempt(t, h);
 					// fac11 = err^expo1 and facold^beta through one logarithm per attempt (facold is the previous error)
-					const double log_err = log(err);
-					if (err <= 1.0) {
+					const double log_err = ST::log_error(err);
+					if (ST::accepted_hairer(err)) {
 						++n_acc;
 						st.finish_accepted(t, h);
 #ifndef JB_NO_STIFFNESS
@@ -967,9 +977,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 							if (stiff.judge(h, stnum, stden, Tab::STIFF_LIMIT)) { status = JB_STIFF; break; }
 						}
 #endif
-						double fac = exp(a.expo1 * log_err - a.beta * log_facold);
-						fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
-						double hnew = h / fac;
+						// h_new = h / clamp(fac11 / facold^β / safety, 1/ifactor, 1/dfactor), written without a division
+						double hnew = h * fmin(a.ifactor, fmax(a.dfactor, a.safety * exp(a.beta * log_facold - a.expo1 * log_err)));
 						log_facold = fmax(log_err, -9.210340371976182);     // facold = max(err, 1e-4)
 						st.accept_y();
 						st.template fsal<0, S>();
@@ -981,9 +990,9 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 						h = hnew;
 					} else {
 						if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
-							h = h / fmin(a.facc1, exp(a.expo1 * log_err) / a.safety);
+							h = h * fmax(a.dfactor, a.safety * exp(-a.expo1 * log_err));      // h / min(1/dfactor, fac11/safety)
 						else
-							h = h / a.facc1;
+							h = h * a.dfactor;
 						reject = true;
 						last = false;
 						++n_rej;
@@ -1042,8 +1051,8 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 					const double h = t_new - t;
 					h_abs = fabs(h);
 					const double err = st.attempt(t, h);
-					if (err < 1.0) {
-						double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * exp(log(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
+					if (ST::accepted_scipy(err)) {
+						double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * exp(ST::log_error(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
 						if (rejected) factor = fmin(1.0, factor);
 						h_abs *= factor;
 						++n_acc;
@@ -1057,7 +1066,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 						interpolant = false;
 						break;
 					}
-					h_abs *= fmax(0.2, 0.9 * exp(log(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
+					h_abs *= fmax(0.2, 0.9 * exp(ST::log_error(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
 					rejected = true;
 					++n_rej;
 				}
@@ -1365,8 +1374,8 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 				if (t + 1.01 * h - T > 0.0) { h = T - t; last = true; }
 				++nstep;
 				const double err = st.attempt(t, h);
-				const double log_err = log(err);
-				if (err <= 1.0) {
+				const double log_err = ST::log_error(err);
+				if (ST::accepted_hairer(err)) {
 					++n_acc;
 					st.finish_accepted(t, h);
 					bool gave_up = false;
@@ -1379,9 +1388,7 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 						status = JB_STIFF;
 						finished = true;
 					} else {
-						double fac = exp(a.expo1 * log_err - a.beta * log_facold);
-						fac = fmax(a.facc2, fmin(a.facc1, fac / a.safety));
-						double hnew = h / fac;
+						double hnew = h * fmin(a.ifactor, fmax(a.dfactor, a.safety * exp(a.beta * log_facold - a.expo1 * log_err)));
 						log_facold = fmax(log_err, -9.210340371976182);
 						st.accept_y();
 						st.template fsal<0, S>();
@@ -1394,9 +1401,9 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 					}
 				} else {
 					if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
-						h = h / fmin(a.facc1, exp(a.expo1 * log_err) / a.safety);
+						h = h * fmax(a.dfactor, a.safety * exp(-a.expo1 * log_err));
 					else
-						h = h / a.facc1;
+						h = h * a.dfactor;
 					reject = true;
 					last = false;
 					++n_rej;

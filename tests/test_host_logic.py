@@ -258,8 +258,17 @@ def test_warp_module_builds():
 	assert module.info.threads_per_block % 32 == 0 and 0 < module.info.shared_bytes <= 227 * 1024
 	thread_module = ODE.compile_cuda(storage="global")
 	assert thread_module.info.storage == _codegen.JB_STORE_GLOBAL and thread_module.info.work_vectors == 8
-	lyap = jitcode_lyap(fhn_list(), n_lyap=4, verbose=False).compile_cuda()
-	assert lyap.info.storage == _codegen.JB_STORE_SHARED and lyap.info.work_vectors == 0 and lyap.info.shared_bytes == 9 * 20 * 160 * 8
+	# small Lyapunov systems: a group of lanes per trajectory, lane j with the state and tangent vector j in registers
+	lyap_ode = jitcode_lyap(fhn_list(), n_lyap=4, verbose=False)
+	lyap = lyap_ode.compile_cuda()
+	assert lyap.info.storage == _codegen.JB_STORE_QUAD and lyap.info.work_vectors == 0 and lyap.info.n == 20 and lyap.info.n_lyap == 4
+	assert lyap_ode._quad_group(_codegen.JB_DP5, _codegen.JB_DRV_ODE) == 4
+	assert jitcode_lyap(fhn_list(), n_lyap=3, verbose=False)._quad_group(_codegen.JB_DP5, _codegen.JB_DRV_ODE) == 4      # padded to a power of two
+	assert jitcode_lyap(fhn_list(), n_lyap=1, verbose=False)._quad_group(_codegen.JB_DP5, _codegen.JB_DRV_ODE) == 0      # one vector: plain registers
+	assert lyap_ode._quad_group(_codegen.JB_DOP853, _codegen.JB_DRV_ODE) == 0                                           # 16 rows x 8 do not fit
+	# … and with the whole system per thread in shared memory when asked for
+	shared = lyap_ode.compile_cuda(storage="shared")
+	assert shared.info.storage == _codegen.JB_STORE_SHARED and shared.info.work_vectors == 0 and shared.info.shared_bytes == 9 * 20 * 160 * 8
 
 
 def test_module_builds_loads_and_exports_every_symbol():
@@ -271,7 +280,7 @@ def test_module_builds_loads_and_exports_every_symbol():
 	dense = _dense.dense_library()                    # the dense sine-coupling library: built once, loaded without a GPU
 	for name in _dense.DENSE_EXPORTS:
 		assert hasattr(dense, name), name
-	assert dense.jb_dense_work_vectors() == 18 and dense.jb_dense_control_scalars() == 10
+	assert dense.jb_dense_work_vectors() == 18 and dense.jb_dense_control_scalars() == 14
 	declared -= set(_dense.DENSE_EXPORTS)
 	ODE = jitcode(W.lotka_volterra(gamma_as_parameter=True)["f_sym"], n=2, control_pars=W.lotka_volterra(gamma_as_parameter=True)["control_pars"], verbose=False)
 	module = ODE.compile_cuda()
