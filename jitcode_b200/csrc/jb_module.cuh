@@ -109,12 +109,12 @@ jb_integrate_kernel(const __grid_constant__ Params a)
 }
 
 // lane refill for the register kernels (jb_rk.cuh, run_lanes): persistent warps, trajectories from the caller's queue
-constexpr bool MODULE_REFILL = MODULE_MODE == JB_STORE_REGISTERS && JB_MODULE_DRIVER == JB_DRV_ODE;
+constexpr bool MODULE_REFILL = MODULE_MODE == JB_STORE_REGISTERS;
 
 __global__ void __launch_bounds__(JB_MODULE_THREADS, JB_MODULE_MIN_BLOCKS)
 jb_integrate_refill_kernel(const __grid_constant__ Params a)
 {
-	if constexpr (MODULE_REFILL) run_lanes<Sys, Tab>(a);
+	if constexpr (MODULE_REFILL) run_lanes<Sys, Tab, JB_MODULE_DRIVER>(a);
 }
 
 // dY = f(t, Y): the batched counterpart of py_f (jitced_template.c:67-116)

@@ -820,187 +820,173 @@ __device__ __forceinline__ void team_lyap(int post, double *v, const WT *where, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Everything one trajectory does during one launch.  Thread storage: called by the trajectory's
-// thread.  Warp storage: called by all 32 lanes of the trajectory's warp with identical scalar
-// state; `smem` is the warp's private stage area, `tables` the staged tables of the right-hand side.
+// Everything one trajectory does during one launch, as an object: `load` binds the working storage and reads the
+// solver's state, `begin_sample` / `attempt_once` advance it towards a sample time one step attempt at a time,
+// `sample` delivers the state there (dense output, recording, Lyapunov post-step), `store` writes the solver back.
+// run_trajectory strings them together for one trajectory; run_lanes (register storage) keeps the lanes of a warp
+// busy by handing a lane the next trajectory as soon as its own has arrived.
+// Thread storage: one thread owns the object.  Warp storage: all threads of the trajectory's team hold identical
+// scalar state; `smem` is the team's private stage area, `tables` the staged tables of the right-hand side.
 
 template <class Sys, class Tab, int DRIVER, int MODE, int KREGS = 0>
-__device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b, double *smem = nullptr, const void *tables = nullptr)
-{
-	constexpr bool WARP = MODE == JB_STORE_WARP;
+struct Lane {
+	static constexpr bool WARP = MODE == JB_STORE_WARP;
 	using Store = typename std::conditional<WARP, WarpStore<Sys, Tab, DRIVER, KREGS>, ThreadStore<Sys, Tab, DRIVER, MODE>>::type;
 	using ST = Stepper<Sys, Tab, DRIVER, Store>;
 	using IVec = typename ST::IVec;
 	using UVec = typename ST::UVec;
-	constexpr int N = Sys::N;
-	constexpr int S = Tab::NSTAGE;
-	constexpr bool QUAD = MODE == JB_STORE_QUAD;
-	constexpr bool REG = MODE == JB_STORE_REGISTERS || QUAD;
-	constexpr int NV = Store::N;                                            // length of this thread's vectors (N unless QUAD)
-	constexpr bool DENSE = ST::DENSE;
-	constexpr bool IVP = ST::IVP;
-	constexpr int NLY = QUAD ? 1 : (Sys::NL > 0 ? Sys::NL : 1);             // exponents this thread computes
-	const int64_t ld = a.ld;
-	const int64_t vec = (int64_t) N * ld;                                   // one caller-visible vector
-	const int64_t off = WARP ? b * (int64_t) N : tile_offset(b, N);         // this trajectory inside it
-	bool leader = true;                                                     // writes the per-trajectory scalars
-	if constexpr (WARP) leader = Team<Sys::TEAM_WARPS>::rank() == 0;
-	// quad storage: this lane's place in the trajectory's group and whether it owns a tangent vector
-	const int member = QUAD ? (int) (threadIdx.x % (unsigned) Sys::GROUP) : 0;
-	const bool owner = !QUAD || member < Sys::NL;
-	if constexpr (QUAD) leader = member == 0;
+	static constexpr int N = Sys::N;
+	static constexpr int S = Tab::NSTAGE;
+	static constexpr bool QUAD = MODE == JB_STORE_QUAD;
+	static constexpr bool REG = MODE == JB_STORE_REGISTERS || QUAD;
+	static constexpr int NV = Store::N;                                     // length of this thread's vectors (N unless QUAD)
+	static constexpr bool DENSE = ST::DENSE;
+	static constexpr bool IVP = ST::IVP;
+	static constexpr int NLY = QUAD ? 1 : (Sys::NL > 0 ? Sys::NL : 1);      // exponents this thread computes
+	static constexpr double LOG_FACOLD_MIN = -9.210340371976182;           // log(1e-4)
 
+	const Params &a;
 	ST st;
-	st.rtol = a.rtol;
-	st.atol_s = a.atol;
-	st.atol_vec = a.atol_vec;
-	st.comp = nullptr;
-	st.shift = owner ? Sys::NB * member : 0;
-#pragma unroll
-	for (int k = 0; k < Sys::NP; ++k)
-		st.par.v[k] = WARP ? a.P[b * Sys::NP + k] : a.P[tile_offset(b, Sys::NP) + k * TILE];
+	int64_t b, off;             // the trajectory and its place inside a caller-visible vector
+	bool leader, owner;         // writes the per-trajectory scalars / (quad storage) owns a tangent vector
+	int member;                 // quad storage: place in the trajectory's group
+	int status;
+	double t;
+	int n_acc, n_rej;           // of this launch (one register each; the caller's totals are 64-bit)
+	// Hairer's driver: one call of the solver per sample time
+	double h, hmax, log_facold;
+	bool reject, last;
+	int nstep;
+	StiffnessWatch stiff;
+	// SciPy's stepper: persistent between sample times and launches
+	double h_abs, t_old, h_prev;
+	bool initialised;           // the persistent stepper exists (f(t, y) and h_abs are valid)
+	bool interpolant;           // DENSE: the interpolant of the last step is in the canonical state
+	bool have_f;                // K[0] holds f(t, Y) for the step to come
+	bool pending_f;             // K[S] holds f(t, Y) (fresh from an accepted step), K[0..S] are its stages
+	bool in_step, rejected;     // inside RungeKutta._step_impl: a step has begun / has seen a rejection
+	double min_step;
+	int attempts_here;
+	// Lyapunov exponents
+	double t_start;             // solver time before the current sample (Δt of the Lyapunov step for ODE/LAND)
+	double lyap_sum[NLY], lyap_sq[NLY];
 
-	int status = a.status[b];
-	double t = a.t[b];
-	int n_acc = 0, n_rej = 0;       // of this launch (one register each; the caller's totals are 64-bit)
+	__device__ __forceinline__ explicit Lane(const Params &params) : a(params) {}
 
 	// ---- canonical (caller-visible) locations
-	auto user = [&](double *base) {
+	__device__ __forceinline__ UVec user(double *base) const
+	{
 		if constexpr (WARP) return UVec{base, st.comp};
 		else if constexpr (QUAD) return UVec{base, Sys::NB * member, member == 0, owner};
 		else return UVec{base};
-	};
-	auto persistent = [&](double *base) {
+	}
+	__device__ __forceinline__ IVec persistent(double *base) const
+	{
 		if constexpr (QUAD) return IVec{base, Sys::NB * member, member == 0, owner};
 		else return IVec{base};
-	};
-	if constexpr (WARP) {
-		st.tables = tables;
-		st.comp = Sys::components(tables);
 	}
-	const UVec Yc = user(a.Y + off);
-	const IVec Fc = persistent(IVP ? a.state + SV_F * vec + off : nullptr);
-	const IVec Oc = persistent(DENSE ? a.state + SV_YOLD * vec + off : nullptr);
-	auto Qc = [&](int p) { return persistent(a.state + (SV_DENSE0 + p) * vec + off); };
+	__device__ __forceinline__ int64_t vec() const { return (int64_t) N * a.ld; }      // one caller-visible vector
+	__device__ __forceinline__ UVec Yc() const { return user(a.Y + off); }
+	__device__ __forceinline__ IVec Fc() const { return persistent(IVP ? a.state + SV_F * vec() + off : nullptr); }
+	__device__ __forceinline__ IVec Oc() const { return persistent(DENSE ? a.state + SV_YOLD * vec() + off : nullptr); }
+	__device__ __forceinline__ IVec Qc(int p) const { return persistent(a.state + (SV_DENSE0 + p) * vec() + off); }
 
-	// ---- bind working storage
-	if constexpr (REG) {
+	// ================= bind the working storage, read the solver
+	__device__ __forceinline__ void load(const int64_t trajectory, double *smem = nullptr, const void *tables = nullptr)
+	{
+		b = trajectory;
+		off = WARP ? b * (int64_t) N : tile_offset(b, N);
+		leader = true;
+		if constexpr (WARP) leader = Team<Sys::TEAM_WARPS>::rank() == 0;
+		member = QUAD ? (int) (threadIdx.x % (unsigned) Sys::GROUP) : 0;
+		owner = !QUAD || member < Sys::NL;
+		if constexpr (QUAD) leader = member == 0;
+
+		st.rtol = a.rtol;
+		st.atol_s = a.atol;
+		st.atol_vec = a.atol_vec;
+		st.comp = nullptr;
+		st.shift = owner ? Sys::NB * member : 0;
 #pragma unroll
-		for (int i = 0; i < NV; ++i) st.Y.v[i] = Yc(i);
-	} else if constexpr (WARP) {
-		st.bind(smem);
-		st.for_each([&](int i, auto r) { st.set_y(i, r, Yc(i)); });
-	} else if constexpr (MODE == JB_STORE_SHARED) {
-		// rows of N × (threads per block) doubles in the block's shared memory; this thread's column starts at `smem`
-		constexpr int ROW = N * Sys::THREADS;
-		st.Y.p = smem;
-		st.Z.p = smem + ROW;
+		for (int k = 0; k < Sys::NP; ++k)
+			st.par.v[k] = WARP ? a.P[b * Sys::NP + k] : a.P[tile_offset(b, Sys::NP) + k * TILE];
+		status = a.status[b];
+		t = a.t[b];
+		n_acc = n_rej = 0;
+		if constexpr (WARP) {
+			st.tables = tables;
+			st.comp = Sys::components(tables);
+		}
+		const UVec Y0 = Yc();
+		if constexpr (REG) {
 #pragma unroll
-		for (int j = 0; j < ST::KR; ++j) st.K[j].p = smem + (2 + j) * ROW;
-		if constexpr (DENSE) st.YO.p = smem + (2 + ST::KR) * ROW;
-		st.for_each([&](int i, auto r) { st.set_y(i, r, Yc(i)); });
-	} else {
-		st.Y.p = Yc.p;
-		st.Z.p = a.work + off;
+			for (int i = 0; i < NV; ++i) st.Y.v[i] = Y0(i);
+		} else if constexpr (WARP) {
+			st.bind(smem);
+			st.for_each([&](int i, auto r) { st.set_y(i, r, Y0(i)); });
+		} else if constexpr (MODE == JB_STORE_SHARED) {
+			// rows of N × (threads per block) doubles in the block's shared memory; this thread's column starts at `smem`
+			constexpr int ROW = N * Sys::THREADS;
+			st.Y.p = smem;
+			st.Z.p = smem + ROW;
 #pragma unroll
-		for (int j = 0; j < ST::KR; ++j) st.K[j].p = a.work + (int64_t) (1 + j) * vec + off;
-		if constexpr (DENSE) st.YO.p = a.work + (int64_t) (1 + ST::KR) * vec + off;
-	}
-
-	double h_abs = 0.0, t_old = NAN, h_prev = 0.0;
-	bool initialised = false;   // IVP: the persistent stepper exists (f(t,y) and h_abs are valid)
-	bool interpolant = false;   // DENSE: the interpolant of the last step is in the canonical state
-	bool have_f = false;        // IVP: K[0] holds f(t, Y) for the step to come
-	bool pending_f = false;     // IVP: K[S] holds f(t, Y) (fresh from an accepted step), K[0..S] are its stages
-	if constexpr (IVP) {
-		h_abs = a.sstate[SS_H_ABS * ld + b];
-		t_old = a.sstate[SS_T_OLD * ld + b];
-		h_prev = a.sstate[SS_H_PREV * ld + b];
-		const int flags = (int) a.sstate[SS_FLAGS * ld + b];
-		initialised = flags & FLAG_INITIALISED;
-		interpolant = flags & FLAG_INTERPOLANT;
-	}
-
-	double lyap_sum[NLY], lyap_sq[NLY];
-#pragma unroll
-	for (int k = 0; k < NLY; ++k) lyap_sum[k] = lyap_sq[k] = 0.0;
-
-	for (int it = 0; it < a.n_times; ++it) {
-		const double T = a.times[it];
-		const double t_start = t;        // solver time before this sample (Δt of the Lyapunov step for ODE/LAND)
-		if (status != JB_OK) continue;
-
-		if constexpr (DRIVER == JB_DRV_ODE) {
-			// ================= Hairer DOPRI5 / DOP853, fresh start (dopri5.f DOPCOR, dop853.f DP86CO)
-			if (T > t) {
-				st.template rhs_y<0>(t);
-				const double hmax = a.max_step > 0.0 ? a.max_step : fabs(T - t);
-				double h;
-				if (a.first_step > 0.0) {
-					h = a.first_step;
-				} else {
-					// HINIT
-					const double dnf = st.weighted_sq([&](int i, auto r) { return st.template k<0>(i, r); });
-					const double dny = st.weighted_sq([&](int i, auto r) { return st.y(i, r); });
-					h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
-					h = fmin(h, hmax);
-					st.euler_probe(h);
-					st.template rhs_z<1>(t + h);
-					const double der2 = sqrt(st.weighted_sq([&](int i, auto r) { return st.template k<1>(i, r) - st.template k<0>(i, r); })) / h;
-					const double der12 = fmax(fabs(der2), sqrt(dnf));
-					const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h) * 1e-3)
-							: pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
-					h = fmin(fmin(100.0 * fabs(h), h1), hmax);
-				}
-				double log_facold = -9.210340371976182;      // facold = 1e-4
-				bool reject = false, last = false;
-				int nstep = 0;
-				const int nmax = a.nsteps > 0 ? (int) (a.nsteps < 2000000000 ? a.nsteps : 2000000000) : 100000;
-				StiffnessWatch stiff;
-				stiff.reset();
-				while (true) {
-					if (nstep > nmax) { status = JB_TOO_MANY_STEPS; break; }
-					if (0.1 * fabs(h) <= fabs(t) * 2.3e-16) { status = JB_STEP_TOO_SMALL; break; }
-					if (!(h == h)) { status = JB_NONFINITE; break; }
-					if (t + 1.01 * h - T > 0.0) { h = T - t; last = true; }
-					++nstep;
-					const double err = st.attempt(t, h);
-					// fac11 = err^expo1 and facold^beta through one logarithm per attempt (facold is the previous error)
-					const double log_err = ST::log_error(err);
-					if (ST::accepted_hairer(err)) {
-						++n_acc;
-						st.finish_accepted(t, h);
-#ifndef JB_NO_STIFFNESS
-						if (stiff.due()) {      // (before the new step size is worked out: fewer values alive across the sums)
-							double stnum, stden;
-							st.stiffness_sums(h, stnum, stden);
-							if (stiff.judge(h, stnum, stden, Tab::STIFF_LIMIT)) { status = JB_STIFF; break; }
-						}
-#endif
-						// h_new = h / clamp(fac11 / facold^β / safety, 1/ifactor, 1/dfactor), written without a division
-						double hnew = h * fmin(a.ifactor, fmax(a.dfactor, a.safety * exp(a.beta * log_facold - a.expo1 * log_err)));
-						log_facold = fmax(log_err, -9.210340371976182);     // facold = max(err, 1e-4)
-						st.accept_y();
-						st.template fsal<0, S>();
-						t = last ? T : t + h;
-						if (fabs(hnew) > hmax) hnew = hmax;
-						if (reject) hnew = fmin(fabs(hnew), fabs(h));
-						reject = false;
-						if (last) break;
-						h = hnew;
-					} else {
-						if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
-							h = h * fmax(a.dfactor, a.safety * exp(-a.expo1 * log_err));      // h / min(1/dfactor, fac11/safety)
-						else
-							h = h * a.dfactor;
-						reject = true;
-						last = false;
-						++n_rej;
-					}
-				}
-			}
+			for (int j = 0; j < ST::KR; ++j) st.K[j].p = smem + (2 + j) * ROW;
+			if constexpr (DENSE) st.YO.p = smem + (2 + ST::KR) * ROW;
+			st.for_each([&](int i, auto r) { st.set_y(i, r, Y0(i)); });
 		} else {
-			// ================= scipy solve_ivp stepper (rk.py RungeKutta), persistent between launches
+			st.Y.p = Y0.p;
+			st.Z.p = a.work + off;
+#pragma unroll
+			for (int j = 0; j < ST::KR; ++j) st.K[j].p = a.work + (int64_t) (1 + j) * vec() + off;
+			if constexpr (DENSE) st.YO.p = a.work + (int64_t) (1 + ST::KR) * vec() + off;
+		}
+		h_abs = 0.0, t_old = NAN, h_prev = 0.0;
+		initialised = interpolant = have_f = pending_f = false;
+		if constexpr (IVP) {
+			h_abs = a.sstate[SS_H_ABS * a.ld + b];
+			t_old = a.sstate[SS_T_OLD * a.ld + b];
+			h_prev = a.sstate[SS_H_PREV * a.ld + b];
+			const int flags = (int) a.sstate[SS_FLAGS * a.ld + b];
+			initialised = flags & FLAG_INITIALISED;
+			interpolant = flags & FLAG_INTERPOLANT;
+		}
+#pragma unroll
+		for (int k = 0; k < NLY; ++k) lyap_sum[k] = lyap_sq[k] = 0.0;
+		t_start = t;
+	}
+
+	// ================= start towards the sample time T; false: there is nothing to integrate
+	__device__ __forceinline__ bool begin_sample(const double T)
+	{
+		t_start = t;
+		if constexpr (DRIVER == JB_DRV_ODE) {
+			// Hairer DOPRI5 / DOP853, fresh start (dopri5.f DOPCOR, dop853.f DP86CO)
+			if (!(T > t)) return false;
+			st.template rhs_y<0>(t);
+			hmax = a.max_step > 0.0 ? a.max_step : fabs(T - t);
+			if (a.first_step > 0.0) {
+				h = a.first_step;
+			} else {
+				// HINIT
+				const double dnf = st.weighted_sq([&](int i, auto r) { return st.template k<0>(i, r); });
+				const double dny = st.weighted_sq([&](int i, auto r) { return st.y(i, r); });
+				h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+				h = fmin(h, hmax);
+				st.euler_probe(h);
+				st.template rhs_z<1>(t + h);
+				const double der2 = sqrt(st.weighted_sq([&](int i, auto r) { return st.template k<1>(i, r) - st.template k<0>(i, r); })) / h;
+				const double der12 = fmax(fabs(der2), sqrt(dnf));
+				const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h) * 1e-3)
+						: pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
+				h = fmin(fmin(100.0 * fabs(h), h1), hmax);
+			}
+			log_facold = LOG_FACOLD_MIN;      // facold = 1e-4
+			reject = last = false;
+			nstep = 0;
+			stiff.reset();
+			return true;
+		} else {
+			// scipy solve_ivp stepper (rk.py RungeKutta), persistent between launches
 			if (!initialised) {
 				// RungeKutta.__init__: f = fun(t, y); select_initial_step with t_bound = ∞
 				st.template rhs_y<0>(t);
@@ -1023,62 +1009,122 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 				have_f = true;
 				pending_f = false;
 			}
+			attempts_here = 0;      // solve_ivp has no step limit; a launch must end nevertheless
+			in_step = false;
+			return more_steps(T);
+		}
+	}
+
+	// IVP_wrapper.integrate (integrator_tools.py:98-105): step until the solver has passed T (and has made a step at all)
+	__device__ __forceinline__ bool more_steps(const double T) const
+	{
+		return status == JB_OK && (t < T || (DENSE && !(t_old == t_old)));
+	}
+
+	// ================= one step attempt; true: the stepping for this sample time is over (arrived or failed)
+	__device__ __forceinline__ bool attempt_once(const double T)
+	{
+		if constexpr (DRIVER == JB_DRV_ODE) {
+			const int nmax = a.nsteps > 0 ? (int) (a.nsteps < 2000000000 ? a.nsteps : 2000000000) : 100000;
+			if (nstep > nmax) { status = JB_TOO_MANY_STEPS; return true; }
+			if (0.1 * fabs(h) <= fabs(t) * 2.3e-16) { status = JB_STEP_TOO_SMALL; return true; }
+			if (!(h == h)) { status = JB_NONFINITE; return true; }
+			if (t + 1.01 * h - T > 0.0) { h = T - t; last = true; }
+			++nstep;
+			const double err = st.attempt(t, h);
+			// fac11 = err^expo1 and facold^beta through one logarithm per attempt (facold is the previous error)
+			const double log_err = ST::log_error(err);
+			if (ST::accepted_hairer(err)) {
+				++n_acc;
+				st.finish_accepted(t, h);
+#ifndef JB_NO_STIFFNESS
+				if (stiff.due()) {      // (before the new step size is worked out: fewer values alive across the sums)
+					double stnum, stden;
+					st.stiffness_sums(h, stnum, stden);
+					if (stiff.judge(h, stnum, stden, Tab::STIFF_LIMIT)) { status = JB_STIFF; return true; }
+				}
+#endif
+				// h_new = h / clamp(fac11 / facold^β / safety, 1/ifactor, 1/dfactor), written without a division
+				double hnew = h * fmin(a.ifactor, fmax(a.dfactor, a.safety * exp(a.beta * log_facold - a.expo1 * log_err)));
+				log_facold = fmax(log_err, LOG_FACOLD_MIN);     // facold = max(err, 1e-4)
+				st.accept_y();
+				st.template fsal<0, S>();
+				t = last ? T : t + h;
+				if (fabs(hnew) > hmax) hnew = hmax;
+				if (reject) hnew = fmin(fabs(hnew), fabs(h));
+				reject = false;
+				if (last) return true;
+				h = hnew;
+			} else {
+				if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
+					h = h * fmax(a.dfactor, a.safety * exp(-a.expo1 * log_err));      // h / min(1/dfactor, fac11/safety)
+				else
+					h = h * a.dfactor;
+				reject = true;
+				last = false;
+				++n_rej;
+			}
+			return false;
+		} else {
+			constexpr int ATTEMPT_CAP = 1 << 26;
 			const double max_step = a.max_step > 0.0 ? a.max_step : INFINITY;
 			const double t_bound = DENSE ? INFINITY : T;
-			// solve_ivp has no step limit; a launch must end nevertheless
-			constexpr int ATTEMPT_CAP = 1 << 26;
-			int attempts_here = 0;
-			while (status == JB_OK && (t < T || (DENSE && !(t_old == t_old)))) {
+			if (!in_step) {
 				// ---- begin a step: K[0] = f(t, Y)
 				if (pending_f) {
 					st.template fsal<0, S>();
 					pending_f = false;
 				} else if (!have_f) {
-					st.for_each([&](int i, auto r) { st.template set_k<0>(i, r, Fc(i)); });
+					const IVec F = Fc();
+					st.for_each([&](int i, auto r) { st.template set_k<0>(i, r, F(i)); });
 				}
 				have_f = true;
 				// ---- RungeKutta._step_impl
-				const double min_step = 10.0 * ulp_above(t);
+				min_step = 10.0 * ulp_above(t);
 				if (h_abs > max_step) h_abs = max_step;
 				else if (h_abs < min_step) h_abs = min_step;
-				bool rejected = false;
-				while (true) {
-					if (!(fabs(h_abs) <= 1.79769313486231571e308)) { status = JB_NONFINITE; break; }   // NaN or ∞ (non-finite state)
-					if (h_abs < min_step) { status = JB_STEP_TOO_SMALL; break; }
-					if (++attempts_here > ATTEMPT_CAP) { status = JB_TOO_MANY_STEPS; break; }
-					double t_new = t + h_abs;
-					if (t_new - t_bound > 0.0) t_new = t_bound;
-					const double h = t_new - t;
-					h_abs = fabs(h);
-					const double err = st.attempt(t, h);
-					if (ST::accepted_scipy(err)) {
-						double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * exp(ST::log_error(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
-						if (rejected) factor = fmin(1.0, factor);
-						h_abs *= factor;
-						++n_acc;
-						st.finish_accepted(t, h);
-						if constexpr (DENSE) st.save_old();
-						st.accept_y();
-						t_old = t;
-						h_prev = h;
-						t = t_new;
-						pending_f = true;
-						interpolant = false;
-						break;
-					}
-					h_abs *= fmax(0.2, 0.9 * exp(ST::log_error(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
-					rejected = true;
-					++n_rej;
-				}
+				rejected = false;
+				in_step = true;
 			}
+			if (!(fabs(h_abs) <= 1.79769313486231571e308)) { status = JB_NONFINITE; return true; }   // NaN or ∞ (non-finite state)
+			if (h_abs < min_step) { status = JB_STEP_TOO_SMALL; return true; }
+			if (++attempts_here > ATTEMPT_CAP) { status = JB_TOO_MANY_STEPS; return true; }
+			double t_new = t + h_abs;
+			if (t_new - t_bound > 0.0) t_new = t_bound;
+			const double step = t_new - t;
+			h_abs = fabs(step);
+			const double err = st.attempt(t, step);
+			if (ST::accepted_scipy(err)) {
+				double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * exp(ST::log_error(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
+				if (rejected) factor = fmin(1.0, factor);
+				h_abs *= factor;
+				++n_acc;
+				st.finish_accepted(t, step);
+				if constexpr (DENSE) st.save_old();
+				st.accept_y();
+				t_old = t;
+				h_prev = step;
+				t = t_new;
+				pending_f = true;
+				interpolant = false;
+				in_step = false;
+				return !more_steps(T);
+			}
+			h_abs *= fmax(0.2, 0.9 * exp(ST::log_error(err) * (-1.0 / (Tab::ERR_ORDER + 1))));
+			rejected = true;
+			++n_rej;
+			return false;
 		}
+	}
 
-		// ================= the sample at T
-		if (status != JB_OK) continue;
-		const UVec rec = user(a.Yrec ? a.Yrec + (int64_t) it * vec + off : nullptr);
+	// ================= the sample at T (sample index `it` of the launch)
+	__device__ __forceinline__ void sample(const int it, const double T)
+	{
+		const UVec rec = user(a.Yrec ? a.Yrec + (int64_t) it * vec() + off : nullptr);
 		const UVec res = user(a.Yres ? a.Yres + off : nullptr);
-		double dt_lyap = T - t_start;
+		const double dt_lyap = T - t_start;
 		if constexpr (DENSE) {
+			const IVec O = Oc();
 			if (!interpolant) {
 				// ---- materialise the interpolant of the last step (rk.py:178-180, 693-712)
 				if constexpr (!std::is_same<Tab, DOP853>::value) {
@@ -1091,7 +1137,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 							});
 							Qc(p).set(i, q);
 						});
-						Oc.set(i, st.yo(i, r));
+						O.set(i, st.yo(i, r));
 					});
 				} else {
 					// three extra stages from (t_old, y_old), then F[0..6]
@@ -1121,7 +1167,7 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 							});
 							Qc(3 + row).set(i, h_prev * q);
 						});
-						Oc.set(i, st.yo(i, r));
+						O.set(i, st.yo(i, r));
 					});
 				}
 				interpolant = true;
@@ -1135,14 +1181,14 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 				if constexpr (!std::is_same<Tab, DOP853>::value) {
 					r = Qc(Tab::NDENSE - 1)(i);
 					static_for<1, Tab::NDENSE>([&](auto p) { r = fma(r, x, Qc(Tab::NDENSE - 1 - p)(i)); });
-					r = fma(hh * x, r, Oc(i));
+					r = fma(hh * x, r, O(i));
 				} else {
 					r = 0.0;
 					static_for<0, 7>([&](auto k) {
 						r += Qc(6 - k)(i);
 						r *= (k % 2 == 0) ? x : 1.0 - x;
 					});
-					r += Oc(i);
+					r += O(i);
 				}
 				if (restart) st.set_z(i, pass, r);
 				else {
@@ -1160,25 +1206,23 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 			}
 		}
 
-		if constexpr (Sys::NL > 0)      // (modules without tangent vectors: nothing of this is compiled — six registers less)
+		if constexpr (Sys::NL > 0)      // (modules without tangent vectors: nothing of this is compiled)
 		if (a.post != JB_POST_NONE) {
 			double norms[NLY];
-			{
-				if constexpr (WARP) {
-					// through the Z row: the state may live in registers, the tangent vectors are needed by every thread
-					st.for_each([&](int i, auto r) { st.set_z(i, r, st.y(i, r)); });
-					team_lyap<Sys>(a.post, st.pZ, Sys::positions(tables), a.proj, a.n_proj, norms, st.scratch);
-					st.for_each([&](int i, auto r) { st.set_y(i, r, st.z(i, r)); });
-				} else if constexpr (QUAD) {
-					norms[0] = group_orthonormalise<Sys::NB, Sys::NL, Sys::GROUP>(st.Y, member);
-				} else {
-					if (a.post == JB_POST_LYAP_QR)
-						lyap_orthonormalise<Sys::NB, Sys::NL, REG>(st.Y, norms);
-					else if (a.post == JB_POST_LYAP_RESTRICTED)
-						norms[0] = lyap_restricted<Sys::NB, REG>(st.Y, a.proj, a.n_proj);
-					else if (a.post == JB_POST_LYAP_TRANSVERSAL)
-						norms[0] = lyap_transversal<Sys, REG>(st.Y);
-				}
+			if constexpr (WARP) {
+				// through the Z row: the state may live in registers, the tangent vectors are needed by every thread
+				st.for_each([&](int i, auto r) { st.set_z(i, r, st.y(i, r)); });
+				team_lyap<Sys>(a.post, st.pZ, Sys::positions(st.tables), a.proj, a.n_proj, norms, st.scratch);
+				st.for_each([&](int i, auto r) { st.set_y(i, r, st.z(i, r)); });
+			} else if constexpr (QUAD) {
+				norms[0] = group_orthonormalise<Sys::NB, Sys::NL, Sys::GROUP>(st.Y, member);
+			} else {
+				if (a.post == JB_POST_LYAP_QR)
+					lyap_orthonormalise<Sys::NB, Sys::NL, REG>(st.Y, norms);
+				else if (a.post == JB_POST_LYAP_RESTRICTED)
+					norms[0] = lyap_restricted<Sys::NB, REG>(st.Y, a.proj, a.n_proj);
+				else if (a.post == JB_POST_LYAP_TRANSVERSAL)
+					norms[0] = lyap_transversal<Sys, REG>(st.Y);
 			}
 			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
 			if constexpr (QUAD) {
@@ -1222,211 +1266,131 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 	}
 
 	// ================= write the solver back
-	if constexpr (REG) {
+	__device__ __forceinline__ void store()
+	{
+		const UVec Y0 = Yc();
+		if constexpr (REG) {
 #pragma unroll
-		for (int i = 0; i < NV; ++i) Yc.set(i, st.Y.v[i]);
-	} else {
-		bool copy_back = WARP || MODE == JB_STORE_SHARED;
-		if constexpr (MODE == JB_STORE_GLOBAL) copy_back = st.Y.p != Yc.p;
-		if (copy_back) st.for_each([&](int i, auto r) { Yc.set(i, st.y(i, r)); });
-	}
-	if constexpr (IVP) {
-		if (pending_f || have_f) {
-			if (pending_f) st.for_each([&](int i, auto r) { Fc.set(i, st.template k<S>(i, r)); });
-			else st.for_each([&](int i, auto r) { Fc.set(i, st.template k<0>(i, r)); });
+			for (int i = 0; i < NV; ++i) Y0.set(i, st.Y.v[i]);
+		} else {
+			bool copy_back = WARP || MODE == JB_STORE_SHARED;
+			if constexpr (MODE == JB_STORE_GLOBAL) copy_back = st.Y.p != Y0.p;
+			if (copy_back) st.for_each([&](int i, auto r) { Y0.set(i, st.y(i, r)); });
+		}
+		if constexpr (IVP) {
+			if (pending_f || have_f) {
+				const IVec F = Fc();
+				if (pending_f) st.for_each([&](int i, auto r) { F.set(i, st.template k<S>(i, r)); });
+				else st.for_each([&](int i, auto r) { F.set(i, st.template k<0>(i, r)); });
+			}
+			if (leader) {
+				a.sstate[SS_H_ABS * a.ld + b] = h_abs;
+				a.sstate[SS_T_OLD * a.ld + b] = t_old;
+				a.sstate[SS_H_PREV * a.ld + b] = h_prev;
+				a.sstate[SS_FLAGS * a.ld + b] = (double) ((initialised ? FLAG_INITIALISED : 0) | (interpolant ? FLAG_INTERPOLANT : 0));
+			}
 		}
 		if (leader) {
-			a.sstate[SS_H_ABS * ld + b] = h_abs;
-			a.sstate[SS_T_OLD * ld + b] = t_old;
-			a.sstate[SS_H_PREV * ld + b] = h_prev;
-			a.sstate[SS_FLAGS * ld + b] = (double) ((initialised ? FLAG_INITIALISED : 0) | (interpolant ? FLAG_INTERPOLANT : 0));
+			a.t[b] = t;
+			a.status[b] = status;
+			if (a.n_accepted) a.n_accepted[b] += n_acc;
+			if (a.n_rejected) a.n_rejected[b] += n_rej;
 		}
-	}
-	if (leader) {
-		a.t[b] = t;
-		a.status[b] = status;
-		if (a.n_accepted) a.n_accepted[b] += n_acc;
-		if (a.n_rejected) a.n_rejected[b] += n_rej;
-	}
-	if constexpr (Sys::NL <= 0) {
-		// no tangent vectors, no exponents
-	} else if constexpr (QUAD) {
-		if (a.lyap_acc && a.post != JB_POST_NONE && owner) {
-			const int n_out = Sys::NL;
-			a.lyap_acc[tile_offset(b, n_out) + member * TILE] += lyap_sum[0];
-			a.lyap_acc[(int64_t) n_out * ld + tile_offset(b, n_out) + member * TILE] += lyap_sq[0];
-		}
-	} else
-	if (a.lyap_acc && a.post != JB_POST_NONE && leader) {
-		const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
-		for (int k = 0; k < NLY; ++k) {
-			if (k >= n_out) break;
-			if constexpr (WARP) {
-				a.lyap_acc[b * n_out + k] += lyap_sum[k];
-				a.lyap_acc[((int64_t) ld + b) * n_out + k] += lyap_sq[k];
-			} else {
-				a.lyap_acc[tile_offset(b, n_out) + k * TILE] += lyap_sum[k];
-				a.lyap_acc[(int64_t) n_out * ld + tile_offset(b, n_out) + k * TILE] += lyap_sq[k];
+		if constexpr (Sys::NL <= 0) {
+			// no tangent vectors, no exponents
+		} else if constexpr (QUAD) {
+			if (a.lyap_acc && a.post != JB_POST_NONE && owner) {
+				const int n_out = Sys::NL;
+				a.lyap_acc[tile_offset(b, n_out) + member * TILE] += lyap_sum[0];
+				a.lyap_acc[(int64_t) n_out * a.ld + tile_offset(b, n_out) + member * TILE] += lyap_sq[0];
+			}
+		} else if (a.lyap_acc && a.post != JB_POST_NONE && leader) {
+			const int n_out = a.post == JB_POST_LYAP_QR ? Sys::NL : 1;
+			for (int k = 0; k < NLY; ++k) {
+				if (k >= n_out) break;
+				if constexpr (WARP) {
+					a.lyap_acc[b * n_out + k] += lyap_sum[k];
+					a.lyap_acc[((int64_t) a.ld + b) * n_out + k] += lyap_sq[k];
+				} else {
+					a.lyap_acc[tile_offset(b, n_out) + k * TILE] += lyap_sum[k];
+					a.lyap_acc[(int64_t) n_out * a.ld + tile_offset(b, n_out) + k * TILE] += lyap_sq[k];
+				}
 			}
 		}
 	}
+};
+
+template <class Sys, class Tab, int DRIVER, int MODE, int KREGS = 0>
+__device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b, double *smem = nullptr, const void *tables = nullptr)
+{
+	Lane<Sys, Tab, DRIVER, MODE, KREGS> lane(a);
+	lane.load(b, smem, tables);
+	for (int it = 0; it < a.n_times; ++it) {
+		const double T = a.times[it];
+		if (lane.status != JB_OK) continue;       // failures are sticky: a failed trajectory is not advanced further
+		if (lane.begin_sample(T))
+			while (!lane.attempt_once(T)) {}
+		if (lane.status != JB_OK) continue;
+		lane.sample(it, T);
+	}
+	lane.store();
 }
 
 // ---------------------------------------------------------------------------------------------
 #ifndef JB_REFILL_LANES
-#define JB_REFILL_LANES 4      // idle lanes that start new trajectories together (measured: see DESIGN.md)
+#define JB_REFILL_LANES 4      // waiting lanes that change trajectories together (measured: see DESIGN.md)
 #endif
-// Lane refill (register storage, Hairer's driver, one sample time, no post-step).  With one thread per trajectory
-// the lanes of a warp wait for the trajectory that needs most steps (Lotka–Volterra ensemble: 24 % of the lane
-// slots idle).  Here the warps are persistent and a lane whose trajectory has landed on T takes the next one from a
-// queue while its neighbours keep stepping.  Starting a trajectory (f(t, y), HINIT) is code the stepping lanes cannot
-// share, so idle lanes wait until REFILL of them can start together (or nobody is stepping).  The arithmetic of
-// a trajectory is exactly that of run_trajectory: the same Stepper calls in the same order.
-template <class Sys, class Tab>
+// Lane refill (register storage, one sample time, no post-step; all three drivers).  With one thread per trajectory
+// the lanes of a warp wait for the trajectory that needs most steps (Lotka–Volterra ensemble: 24 % of the lane slots
+// idle).  Here the warps are persistent and a lane whose trajectory has arrived at T delivers it and takes the next
+// one from a queue while its neighbours keep stepping.  Delivering (dense output, write-back) and starting (f(t, y),
+// initial step size) are code the stepping lanes cannot share, so lanes that have arrived wait until REFILL of them can
+// change trajectories together (or nobody is stepping).  The arithmetic of a trajectory is exactly that of
+// run_trajectory: the same calls of the same Lane in the same order.
+template <class Sys, class Tab, int DRIVER>
 __device__ __forceinline__ void run_lanes(const Params &a)
 {
-	using Store = ThreadStore<Sys, Tab, JB_DRV_ODE, JB_STORE_REGISTERS>;
-	using ST = Stepper<Sys, Tab, JB_DRV_ODE, Store>;
-	using UVec = typename ST::UVec;
-	constexpr int N = Sys::N;
-	constexpr int S = Tab::NSTAGE;
 	constexpr unsigned FULL = 0xffffffffu;
 	constexpr int REFILL = JB_REFILL_LANES;
-	ST st;
-	st.rtol = a.rtol;
-	st.atol_s = a.atol;
-	st.atol_vec = a.atol_vec;
-	st.comp = nullptr;
+	Lane<Sys, Tab, DRIVER, JB_STORE_REGISTERS> lane(a);
 	const double T = a.times[0];
-	const int nmax = a.nsteps > 0 ? (int) (a.nsteps < 2000000000 ? a.nsteps : 2000000000) : 100000;
-	const int lane = threadIdx.x & 31;
-	int64_t b = -1;             // the trajectory this lane integrates; −1: none
+	const int index = threadIdx.x & 31;
+	bool occupied = false;      // the lane holds a trajectory
+	bool stepping = false;      // … which has not yet arrived at T
 	bool more = true;           // the queue may still hold trajectories
-	double t = 0.0, h = 0.0, hmax = 0.0, log_facold = 0.0;
-	bool reject = false, last = false;
-	int nstep = 0, n_acc = 0, n_rej = 0;
-	int status = JB_OK;
-	StiffnessWatch stiff;
-	stiff.reset();
 	while (true) {
-		const unsigned idle = __ballot_sync(FULL, b < 0);
-		const unsigned hungry = __ballot_sync(FULL, b < 0 && more);
-		if (idle == FULL && hungry == 0) break;
-		if (hungry != 0 && (__popc(hungry) >= REFILL || idle == FULL)) {
-			// ---- the idle lanes take the next trajectories of the queue (one atomic per warp) and start them
-			const int leader = __ffs(hungry) - 1;
-			unsigned long long base = 0;
-			if (lane == leader) base = atomicAdd(a.queue, (unsigned long long) __popc(hungry));
-			base = __shfl_sync(FULL, base, leader);
-			if (b < 0 && more) {
-				const int64_t mine = (int64_t) base + __popc(hungry & ((1u << lane) - 1u));
-				if (mine >= a.B) {
-					more = false;
-				} else {
-					status = a.status[mine];
-					t = a.t[mine];
-					if (status == JB_OK && T > t) {
-						b = mine;
-						const UVec Yc{a.Y + tile_offset(b, N)};
-#pragma unroll
-						for (int i = 0; i < N; ++i) st.Y.v[i] = Yc(i);
-#pragma unroll
-						for (int k = 0; k < Sys::NP; ++k) st.par.v[k] = a.P[tile_offset(b, Sys::NP) + k * TILE];
-						st.template rhs_y<0>(t);
-						hmax = a.max_step > 0.0 ? a.max_step : fabs(T - t);
-						if (a.first_step > 0.0) {
-							h = a.first_step;
-						} else {
-							// HINIT
-							const double dnf = st.weighted_sq([&](int i, auto r) { return st.template k<0>(i, r); });
-							const double dny = st.weighted_sq([&](int i, auto r) { return st.y(i, r); });
-							h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
-							h = fmin(h, hmax);
-							st.euler_probe(h);
-							st.template rhs_z<1>(t + h);
-							const double der2 = sqrt(st.weighted_sq([&](int i, auto r) { return st.template k<1>(i, r) - st.template k<0>(i, r); })) / h;
-							const double der12 = fmax(fabs(der2), sqrt(dnf));
-							const double h1 = der12 <= 1e-15 ? fmax(1e-6, fabs(h) * 1e-3)
-									: pow(0.01 / der12, 1.0 / Tab::HAIRER_ORDER);
-							h = fmin(fmin(100.0 * fabs(h), h1), hmax);
-						}
-						log_facold = -9.210340371976182;      // facold = 1e-4
-						reject = last = false;
-						nstep = n_acc = n_rej = 0;
-						stiff.reset();
-					} else if (a.Yrec) {
-						// nothing to integrate (already at T, or failed earlier): the sample is the state as it stands,
-						// as in run_trajectory; the lane asks again
-						const UVec Yc{a.Y + tile_offset(mine, N)}, rec{a.Yrec + tile_offset(mine, N)};
-#pragma unroll
-						for (int i = 0; i < N; ++i) rec.set(i, Yc(i));
-					}
-				}
+		const unsigned waiting = __ballot_sync(FULL, !stepping);
+		const unsigned able = __ballot_sync(FULL, !stepping && (occupied || more));      // lanes with something to deliver or to fetch
+		if (waiting == FULL && able == 0) break;
+		if (able != 0 && (__popc(able) >= REFILL || waiting == FULL)) {
+			if (!stepping && occupied) {
+				// ---- deliver the trajectory that has arrived (or failed)
+				if (lane.status == JB_OK) lane.sample(0, T);
+				lane.store();
+				occupied = false;
 			}
-		}
-		if (b >= 0) {
-			// ---- one step attempt (the body of the loop of run_trajectory's JB_DRV_ODE branch)
-			bool finished = false;
-			if (nstep > nmax) { status = JB_TOO_MANY_STEPS; finished = true; }
-			else if (0.1 * fabs(h) <= fabs(t) * 2.3e-16) { status = JB_STEP_TOO_SMALL; finished = true; }
-			else if (!(h == h)) { status = JB_NONFINITE; finished = true; }
-			else {
-				if (t + 1.01 * h - T > 0.0) { h = T - t; last = true; }
-				++nstep;
-				const double err = st.attempt(t, h);
-				const double log_err = ST::log_error(err);
-				if (ST::accepted_hairer(err)) {
-					++n_acc;
-					st.finish_accepted(t, h);
-					bool gave_up = false;
-					if (stiff.due()) {
-						double stnum, stden;
-						st.stiffness_sums(h, stnum, stden);
-						gave_up = stiff.judge(h, stnum, stden, Tab::STIFF_LIMIT);
-					}
-					if (gave_up) {
-						status = JB_STIFF;
-						finished = true;
+			// ---- the free lanes take the next trajectories of the queue (one atomic per warp) and start them
+			const unsigned hungry = __ballot_sync(FULL, !occupied && more);
+			if (hungry != 0) {
+				const int first = __ffs(hungry) - 1;
+				unsigned long long base = 0;
+				if (index == first) base = atomicAdd(a.queue, (unsigned long long) __popc(hungry));
+				base = __shfl_sync(FULL, base, first);
+				if (!occupied && more) {
+					const int64_t mine = (int64_t) base + __popc(hungry & ((1u << index) - 1u));
+					if (mine >= a.B) {
+						more = false;
 					} else {
-						double hnew = h * fmin(a.ifactor, fmax(a.dfactor, a.safety * exp(a.beta * log_facold - a.expo1 * log_err)));
-						log_facold = fmax(log_err, -9.210340371976182);
-						st.accept_y();
-						st.template fsal<0, S>();
-						t = last ? T : t + h;
-						if (fabs(hnew) > hmax) hnew = hmax;
-						if (reject) hnew = fmin(fabs(hnew), fabs(h));
-						reject = false;
-						if (last) finished = true;
-						else h = hnew;
+						lane.load(mine);
+						occupied = true;
+						// (a trajectory with nothing to integrate, or one that failed earlier, is delivered with the next batch)
+						stepping = lane.status == JB_OK && lane.begin_sample(T);
 					}
-				} else {
-					if (Tab::ERR_NEEDS_FSAL || !a.hairer_reject_by_dfactor)
-						h = h * fmax(a.dfactor, a.safety * exp(-a.expo1 * log_err));
-					else
-						h = h * a.dfactor;
-					reject = true;
-					last = false;
-					++n_rej;
 				}
-			}
-			if (finished) {
-				const UVec Yc{a.Y + tile_offset(b, N)};
-#pragma unroll
-				for (int i = 0; i < N; ++i) Yc.set(i, st.Y.v[i]);
-				if (a.Yrec) {
-					const UVec rec{a.Yrec + tile_offset(b, N)};
-#pragma unroll
-					for (int i = 0; i < N; ++i) rec.set(i, st.Y.v[i]);
-				}
-				a.t[b] = t;
-				a.status[b] = status;
-				if (a.n_accepted) a.n_accepted[b] += n_acc;
-				if (a.n_rejected) a.n_rejected[b] += n_rej;
-				b = -1;
 			}
 		}
+		if (stepping) stepping = !lane.attempt_once(T);
 	}
 }
-
 
 }  // namespace jb

@@ -103,14 +103,15 @@ def test_first_step_and_step_limit():
 		backend.integrate(100.0)
 
 
-@pytest.mark.parametrize("name", ["dopri5", "dop853"])
-def test_lane_refill_changes_nothing(name, monkeypatch):
-	"""large ensembles in register storage run on persistent warps whose lanes take trajectories from a queue: results,
-	times, step counts and failure reports are bit for bit those of the one-thread-per-trajectory launch, and those
-	are the oracle's within tolerance"""
+@pytest.mark.parametrize("name,interpolate", [("dopri5", True), ("dop853", True), ("RK45", True), ("RK45", False), ("DOP853", True), ("RK23", False)])
+def test_lane_refill_changes_nothing(name, interpolate, monkeypatch):
+	"""large ensembles in register storage run on persistent warps whose lanes take trajectories from a queue (all three
+	drivers): results, times, step counts and failure reports are bit for bit those of the one-thread-per-trajectory
+	launch, and those are the oracle's within tolerance"""
 	system = W.lotka_volterra(gamma_as_parameter=True)
 	B = 3001                                          # ragged: the last warps run dry at different times
 	Y0, pars = W.lotka_volterra_ensemble(B, seed=9, gamma_as_parameter=True)
+	hairer = name in ("dopri5", "dop853")
 	outcomes = {}
 	for refill in (True, False):
 		if refill:
@@ -118,21 +119,28 @@ def test_lane_refill_changes_nothing(name, monkeypatch):
 		else:
 			monkeypatch.setenv("JITCODE_B200_NO_LANE_REFILL", "1")
 		ODE = make(system)
-		ODE.set_integrator(name, rtol=RTOL, atol=ATOL)
+		ODE.set_integrator(name, interpolate=interpolate, rtol=RTOL, atol=ATOL)
 		ODE.set_parameters(pars)
 		ODE.set_initial_value(Y0, 0.0)
 		first = ODE.integrate(7.0)
-		second = ODE.integrate(20.0)                 # a second call continues from the first
-		ODE.set_integrator(name, nsteps=40, rtol=RTOL, atol=ATOL)
-		ODE.set_initial_value(Y0, 0.0)
-		with pytest.raises(UnsuccessfulIntegration) as failure:
-			ODE.integrate(60.0)
-		outcomes[refill] = (first, second, ODE.step_counts(), tuple(failure.value.indices), ODE.y)
-	assert np.array_equal(outcomes[True][0], outcomes[False][0]) and np.array_equal(outcomes[True][1], outcomes[False][1])
-	assert outcomes[True][2] == outcomes[False][2] and outcomes[True][3] == outcomes[False][3]
-	assert np.array_equal(outcomes[True][4], outcomes[False][4], equal_nan=True)
-	assert len(outcomes[True][3]) > 0                # trajectories that hit the step limit
-	expected = oracle(system, name, Y0[:64], [7.0, 20.0], pars=pars[:64], rtol=RTOL, atol=ATOL)
+		second = ODE.integrate(20.0)                 # a second call continues from the first (solve_ivp names: the same stepper)
+		third = ODE.integrate(20.0 + 1e-9) if not hairer else second      # dense output: a sample inside the last step, no stepping at all
+		counts = ODE.step_counts()
+		failed = ()
+		if hairer:
+			ODE.set_integrator(name, nsteps=40, rtol=RTOL, atol=ATOL)
+			ODE.set_initial_value(Y0, 0.0)
+			with pytest.raises(UnsuccessfulIntegration) as failure:
+				ODE.integrate(60.0)
+			failed = tuple(failure.value.indices)
+			assert len(failed) > 0                   # trajectories that hit the step limit
+		outcomes[refill] = (first, second, third, counts, failed, ODE.y)
+	for with_refill, without in zip(outcomes[True], outcomes[False]):
+		if isinstance(with_refill, np.ndarray):
+			assert np.array_equal(with_refill, without, equal_nan=True)
+		else:
+			assert with_refill == without
+	expected = oracle(system, name, Y0[:64], [7.0, 20.0], pars=pars[:64], interpolate=interpolate, rtol=RTOL, atol=ATOL)
 	within_tolerance(outcomes[True][0][:64], expected[0])
 	within_tolerance(outcomes[True][1][:64], expected[1])
 
