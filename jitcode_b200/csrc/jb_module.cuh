@@ -384,8 +384,8 @@ int jb_integrate(const jb_integrate_args *x)
 		jb::jb_integrate_kernel<jb::MODULE_MODE><<<blocks, JB_MODULE_THREADS, jb::Shared::BYTES, (cudaStream_t) x->stream>>>(a);
 		return jb::launched("jb_integrate");
 	}
-	if (jb::MODULE_REFILL && x->queue && x->n_times == 1 && x->post == JB_POST_NONE && x->B >= 4 * JB_MODULE_THREADS && !std::getenv("JITCODE_B200_NO_LANE_REFILL")) {
-		// plain integrate(T) of a large ensemble: persistent warps whose lanes take trajectories from the caller's queue
+	if (jb::MODULE_REFILL && x->queue && x->post == JB_POST_NONE && x->B >= 4 * JB_MODULE_THREADS && !std::getenv("JITCODE_B200_NO_LANE_REFILL")) {
+		// large ensemble without post-step: persistent warps whose lanes take trajectories from the caller's queue
 		jb::DeviceFacts *facts = nullptr;
 		if (const int bad = jb::current_device_facts(&facts)) return bad;
 		int resident = facts->refill_blocks.load(std::memory_order_acquire);

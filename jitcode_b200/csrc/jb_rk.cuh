@@ -1340,34 +1340,49 @@ __device__ __forceinline__ void run_trajectory(const Params &a, const int64_t b,
 #ifndef JB_REFILL_LANES
 #define JB_REFILL_LANES 4      // waiting lanes that change trajectories together (measured: see DESIGN.md)
 #endif
-// Lane refill (register storage, one sample time, no post-step; all three drivers).  With one thread per trajectory
-// the lanes of a warp wait for the trajectory that needs most steps (Lotka–Volterra ensemble: 24 % of the lane slots
-// idle).  Here the warps are persistent and a lane whose trajectory has arrived at T delivers it and takes the next
-// one from a queue while its neighbours keep stepping.  Delivering (dense output, write-back) and starting (f(t, y),
-// initial step size) are code the stepping lanes cannot share, so lanes that have arrived wait until REFILL of them can
-// change trajectories together (or nobody is stepping).  The arithmetic of a trajectory is exactly that of
-// run_trajectory: the same calls of the same Lane in the same order.
+// Lane refill (register storage, no post-step; all three drivers, any number of sample times).  With one thread per
+// trajectory the lanes of a warp wait for the trajectory that needs most steps (Lotka–Volterra ensemble: 24 % of the
+// lane slots idle).  Here the warps are persistent and a lane whose trajectory has arrived at its last sample time
+// delivers it and takes the next one from a queue while its neighbours keep stepping.  Delivering a sample (dense
+// output, recording), writing the solver back and starting anew (f(t, y), initial step size) are code the stepping
+// lanes cannot share, so lanes that have arrived at a sample time wait until REFILL of them can do that together (or
+// nobody is stepping).  The arithmetic of a trajectory is exactly that of run_trajectory: the same calls of the same
+// Lane in the same order.
 template <class Sys, class Tab, int DRIVER>
 __device__ __forceinline__ void run_lanes(const Params &a)
 {
 	constexpr unsigned FULL = 0xffffffffu;
 	constexpr int REFILL = JB_REFILL_LANES;
 	Lane<Sys, Tab, DRIVER, JB_STORE_REGISTERS> lane(a);
-	const double T = a.times[0];
 	const int index = threadIdx.x & 31;
 	bool occupied = false;      // the lane holds a trajectory
-	bool stepping = false;      // … which has not yet arrived at T
+	bool stepping = false;      // … which is on its way to sample time `it`
 	bool more = true;           // the queue may still hold trajectories
+	int it = 0;
+	// from sample index `it` on: deliver what needs no integration, start towards the first sample time that does;
+	// false: the trajectory is through with all its sample times (or has failed: failures are sticky)
+	auto advance = [&]() {
+		while (it < a.n_times && lane.status == JB_OK) {
+			if (lane.begin_sample(a.times[it])) return true;
+			if (lane.status == JB_OK) lane.sample(it, a.times[it]);
+			++it;
+		}
+		return false;
+	};
 	while (true) {
 		const unsigned waiting = __ballot_sync(FULL, !stepping);
 		const unsigned able = __ballot_sync(FULL, !stepping && (occupied || more));      // lanes with something to deliver or to fetch
 		if (waiting == FULL && able == 0) break;
 		if (able != 0 && (__popc(able) >= REFILL || waiting == FULL)) {
 			if (!stepping && occupied) {
-				// ---- deliver the trajectory that has arrived (or failed)
-				if (lane.status == JB_OK) lane.sample(0, T);
-				lane.store();
-				occupied = false;
+				// ---- the trajectory has arrived at sample time `it` (or failed): deliver, go on or write the solver back
+				if (lane.status == JB_OK) lane.sample(it, a.times[it]);
+				++it;
+				stepping = advance();
+				if (!stepping) {
+					lane.store();
+					occupied = false;
+				}
 			}
 			// ---- the free lanes take the next trajectories of the queue (one atomic per warp) and start them
 			const unsigned hungry = __ballot_sync(FULL, !occupied && more);
@@ -1382,14 +1397,15 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 						more = false;
 					} else {
 						lane.load(mine);
-						occupied = true;
-						// (a trajectory with nothing to integrate, or one that failed earlier, is delivered with the next batch)
-						stepping = lane.status == JB_OK && lane.begin_sample(T);
+						it = 0;
+						stepping = advance();
+						if (stepping) occupied = true;
+						else lane.store();       // nothing to integrate at all (or failed earlier): done at once
 					}
 				}
 			}
 		}
-		if (stepping) stepping = !lane.attempt_once(T);
+		if (stepping) stepping = !lane.attempt_once(a.times[it]);
 	}
 }
 
