@@ -453,13 +453,16 @@ class Bench:
 		del result
 
 		# ---- end-to-end arm: pinned host buffers in and out through the public API
-		for _ in range(min(warmup, 2)):
+		for _ in range(warmup):      # (also lets torch's caching allocator for page-locked memory settle: results rotate through three blocks)
 			host_step()
 		self.barrier()
 		solver.reset_step_counts()
 		t0 = time.perf_counter()
 		for _ in range(steps):
+			t_step = time.perf_counter()
 			returned = host_step()
+			if os.environ.get("JITCODE_B200_BENCH_DEBUG"):
+				print(f"[{name}] end-to-end step: {1e3 * (time.perf_counter() - t_step):.2f} ms", file=sys.stderr)
 		self.barrier()
 		e2e_seconds = time.perf_counter() - t0
 		e2e_attempts = sum(solver.step_counts())

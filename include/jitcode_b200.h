@@ -155,7 +155,7 @@ int64_t jb_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense sine-coupled phase oscillators (csrc/jb_dense.cu; one library, not generated per system):
- *     dy_i/dt = omega_i + sum_j W_ij sin(y_j - y_i)
+ *     dy_i/dt = omega_i + c * sum_j W_ij sin(y_j - y_i)          (c: optional per-trajectory control parameter)
  * — what the reference writes out as n*deg sine terms (examples/kuramoto_network.py:19-26) — as one FP64
  * tensor-core GEMM per right-hand-side evaluation for the whole ensemble.  Replaces, for such systems, the same
  * reference entry points as jb_eval_f / jb_integrate with driver JB_DRV_ODE ("dopri5" / "dop853",
@@ -167,6 +167,8 @@ typedef struct jb_dense_args {
 	int64_t  B, ld;            /* trajectories, padded (multiple of 64) */
 	const double *W;           /* [n][n] row-major coupling matrix (device) */
 	const double *omega;       /* [n] natural frequencies (device) */
+	const double *coupling;    /* [ld] per-trajectory factor c_b of the coupling sum (a control parameter: dy_i/dt = omega_i + c_b * sum_j …), or NULL for 1 */
+	const double *atol_vec;    /* [n] per-component atol (device), or NULL: `atol` for all */
 	double   T;                /* target time */
 	double   rtol, atol, max_step, first_step;
 	int64_t  nsteps;           /* step-attempt limit per call; 0 = Hairer's default */

@@ -25,13 +25,18 @@ from ._integrator import STATUS_TEXT, UnsuccessfulIntegration, require_cuda
 from ._symbolic import is_dynvar
 
 
-def detect_sine_coupling(f):
-	"""(W, omega) if every equation is  constant + Σ_j number · sin(±(y(j) − y(i))),  else None."""
+def detect_sine_coupling(f, control_pars=()):
+	"""(W, omega) if every equation is  constant + Σ_j number · sin(±(y(j) − y(i))),  else None.
+	With control parameters: (W, omega, c) if ONE of them multiplies every coupling term (and nothing else contains any) —
+	dy_i/dt = ω_i + c · Σ_j W_ij sin(y_j − y_i), the coupling strength as a per-trajectory parameter."""
 	n = len(f)
 	W = np.zeros((n, n))
 	omega = np.zeros(n)
+	control_pars = list(control_pars)
+	factor = None
 	found = False
 	for i, expr in enumerate(f):
+		expr = sympy.expand(expr) if control_pars else expr
 		for term in sympy.Add.make_args(expr):
 			coefficient, rest = term.as_coeff_Mul()
 			if not coefficient.is_Number:
@@ -39,6 +44,15 @@ def detect_sine_coupling(f):
 			if rest is sympy.S.One:
 				omega[i] += float(coefficient)
 				continue
+			if control_pars and rest.is_Mul:
+				# c · sin(…): split off the control parameter
+				symbols = [a for a in rest.args if a in control_pars]
+				others = [a for a in rest.args if a not in control_pars]
+				if len(symbols) != 1 or len(others) != 1 or (factor is not None and symbols[0] != factor):
+					return None
+				factor, rest = symbols[0], others[0]
+			elif control_pars:
+				return None           # a coupling term without the parameter, next to terms with it: not this form
 			if rest.func is not sympy.sin:
 				return None
 			parts = sympy.Add.make_args(rest.args[0])
@@ -56,14 +70,16 @@ def detect_sine_coupling(f):
 			else:
 				return None
 			found = True
-	return (W, omega) if found else None
+	if not found or (control_pars and (factor is None or len(control_pars) != 1)):
+		return None
+	return (W, omega, factor) if control_pars else (W, omega)
 
 
 class DenseArgs(ctypes.Structure):
 	_fields_ = [
 		("struct_size", ctypes.c_uint32), ("n", ctypes.c_int32),
 		("B", ctypes.c_int64), ("ld", ctypes.c_int64),
-		("W", ctypes.c_void_p), ("omega", ctypes.c_void_p),
+		("W", ctypes.c_void_p), ("omega", ctypes.c_void_p), ("coupling", ctypes.c_void_p), ("atol_vec", ctypes.c_void_p),
 		("T", ctypes.c_double),
 		("rtol", ctypes.c_double), ("atol", ctypes.c_double), ("max_step", ctypes.c_double), ("first_step", ctypes.c_double),
 		("nsteps", ctypes.c_int64),
@@ -129,16 +145,24 @@ class CudaDenseSineIntegrator:
 	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5") or DOP853 ("dop853")."""
 
 	def __init__(self, W, omega, *, method=0, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
-			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=0):
+			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=0, coupling_parameter=False):
 		self.device = require_cuda(device)
 		self.n = len(omega)
 		self.module = DenseModule(self.n)
 		self.lib = self.module.lib
 		self.W = torch.as_tensor(np.ascontiguousarray(W, dtype=float)).to(self.device)
 		self.omega = torch.as_tensor(np.ascontiguousarray(omega, dtype=float)).to(self.device)
-		if np.ndim(atol) != 0:
-			raise NotImplementedError("The dense engine takes a scalar atol.")
-		self.rtol, self.atol = float(rtol), float(atol)
+		if np.ndim(atol) == 0:
+			self.atol, self.atol_vec = float(atol), None
+		else:
+			atol = np.asarray(atol, dtype=float)
+			if atol.shape != (self.n,):
+				raise ValueError("atol must be a scalar or have one entry per component.")
+			self.atol, self.atol_vec = 0.0, torch.as_tensor(atol, device=self.device)
+		self.rtol = float(rtol)
+		# dy_i/dt = ω_i + c·Σ_j W_ij sin(y_j − y_i) with c a control parameter (one value per trajectory)
+		self.n_params = 1 if coupling_parameter else 0
+		self._pars = None
 		self.max_step = float(max_step) if max_step and np.isfinite(max_step) else 0.0
 		self.first_step = float(first_step) if first_step else 0.0
 		self.nsteps = int(nsteps)
@@ -151,7 +175,6 @@ class CudaDenseSineIntegrator:
 		self._out_kind, self._single = "numpy", False
 		self.kernel_events = None
 		self.rounds = 0
-		self.n_params = 0
 
 	@property
 	def stream(self):
@@ -171,12 +194,16 @@ class CudaDenseSineIntegrator:
 		self.scratch = torch.zeros(ld // 32 + 2, dtype=torch.int32, device=dev)
 		self.host_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
 		self.rounds_host = np.zeros(1, dtype=np.int64)
+		self.coupling = torch.ones(ld, **f64) if self.n_params else None
+		self._pars_on_device = False
 
 	def _args(self, T):
 		a = DenseArgs()
 		a.struct_size = ctypes.sizeof(DenseArgs)
 		a.n, a.B, a.ld = self.n, self.B, self.ld
 		a.W, a.omega = self.W.data_ptr(), self.omega.data_ptr()
+		a.coupling = None if self.coupling is None else self.coupling.data_ptr()
+		a.atol_vec = None if self.atol_vec is None else self.atol_vec.data_ptr()
 		a.T = T
 		a.rtol, a.atol, a.max_step, a.first_step = self.rtol, self.atol, self.max_step, self.first_step
 		a.nsteps = self.nsteps
@@ -234,7 +261,27 @@ class CudaDenseSineIntegrator:
 	# ---- protocol of integrator_tools
 
 	def set_parameters(self, pars):
-		pass
+		"""the coupling strength: one value for all trajectories or one per trajectory ((B,), (B, 1), (1,) …)"""
+		if not self.n_params:
+			return
+		pars = pars.detach().to(torch.float64) if isinstance(pars, torch.Tensor) else torch.as_tensor(np.asarray(pars, dtype=float))
+		self._pars = pars.reshape(-1)
+		self._pars_on_device = False
+		if self.B is not None:
+			self._upload_parameters()
+
+	def _upload_parameters(self):
+		if not self.n_params or self._pars_on_device:
+			return
+		if self._pars is None:
+			raise RuntimeError("Something needs parameters to be set. Try calling `set_parameters` earlier.")
+		values = self._pars.to(self.device)
+		if values.numel() == 1:
+			values = values.expand(self.B)
+		if values.numel() != self.B:
+			raise ValueError(f"Got parameters for {values.numel()} trajectories, but initial values for {self.B}.")
+		self.coupling[:self.B].copy_(values)
+		self._pars_on_device = True
 
 	def set_initial_value(self, initial_value, time=0.0):
 		rows, kind, single = self._to_device_rows(initial_value)
@@ -246,6 +293,8 @@ class CudaDenseSineIntegrator:
 		self.time = float(time)
 		self.status.zero_()
 		self._rows = rows
+		if self._pars is not None:
+			self._upload_parameters()
 
 	@property
 	def t(self):
@@ -268,6 +317,7 @@ class CudaDenseSineIntegrator:
 
 	def _advance(self, T, rows=None):
 		"""one call of jb_dense_integrate: every trajectory to T; the state there as (B, n) device rows (`rows`: where to)"""
+		self._upload_parameters()
 		args = self._args(T)
 		if self.kernel_events is not None:
 			start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -328,6 +378,9 @@ class CudaDenseSineIntegrator:
 		self._out_kind, self._single = kind, single
 		_check(self.lib, self.lib.jb_dense_transpose(rows.data_ptr(), self.Y.data_ptr(), self.B, self.n, self.n, self.ld, self.stream), "jb_dense_transpose")
 		self.status.zero_()
+		self._pars_on_device = False
+		if self.n_params:
+			self._upload_parameters()
 		out = torch.empty_like(self.Y)
 		args = self._args(0.0)
 		_check(self.lib, self.lib.jb_dense_eval_f(ctypes.byref(args), out.data_ptr()), "jb_dense_eval_f")

@@ -176,12 +176,14 @@ class jitcode:
 		self._tangent_indices_module = []
 
 	@classmethod
-	def from_sine_coupling(cls, W, omega, verbose=False):
+	def from_sine_coupling(cls, W, omega, coupling_parameter=None, verbose=False):
 		"""
-		The system  dy_i/dt = omega[i] + Σ_j W[i, j]·sin(y_j − y_i)  given by its data instead of by n·deg symbolic
+		The system  dy_i/dt = omega[i] + c·Σ_j W[i, j]·sin(y_j − y_i)  given by its data instead of by n·deg symbolic
 		sine terms (which SymPy needs minutes to build for a dense network of 1000 oscillators).  Equivalent to
 		`jitcode(f_sym)` with that f_sym — the symbolic input is recognised and ends up in the same kernels — and
 		only available with `set_integrator("dopri5")` and `set_integrator("dop853")`.
+		coupling_parameter : a symbol to make c a control parameter (`set_parameters`: one value or one per trajectory);
+			None: c = 1.
 		"""
 		W, omega = np.asarray(W, dtype=float), np.asarray(omega, dtype=float)
 		if W.shape != (len(omega), len(omega)):
@@ -190,15 +192,17 @@ class jitcode:
 		jitcode.__init__(self, [y(0)], n=1, verbose=verbose)        # placeholder system; replaced by the coupling data
 		self._f_list, self.n = [], len(omega)
 		self._n_basic_module = self.n
-		self._sine_coupling = (W, omega)
+		self.control_pars = [coupling_parameter] if coupling_parameter is not None else []
+		self._sine_coupling = (W, omega, coupling_parameter) if coupling_parameter is not None else (W, omega)
 		return self
 
 	def _dense_coupling(self):
-		"""(W, omega) if the system is a network of sine-coupled phase oscillators, else None (cached)."""
+		"""(W, omega[, c]) if the system is a network of sine-coupled phase oscillators (optionally with the coupling
+		strength c as its one control parameter), else None (cached)."""
 		if not hasattr(self, "_sine_coupling"):
 			self._sine_coupling = None
-			if self._f_list and not self.helpers and not self.control_pars and self._post == JB_POST_NONE:
-				self._sine_coupling = _dense.detect_sine_coupling(self._f_list)
+			if self._f_list and not self.helpers and len(self.control_pars) <= 1 and self._post == JB_POST_NONE:
+				self._sine_coupling = _dense.detect_sine_coupling(self._f_list, self.control_pars)
 		return self._sine_coupling
 
 	# ------------------------------------------------------------------ input handling and checks
@@ -439,7 +443,10 @@ class jitcode:
 	def f(self, time, state):
 		"""Evaluates the compiled derivative on the GPU: state (n,) → (n,), or (B, n) → (B, n)."""
 		if isinstance(self.integrator, _dense.CudaDenseSineIntegrator) or not self._f_list:
-			helper = _dense.CudaDenseSineIntegrator(*self._dense_coupling())
+			coupling = self._dense_coupling()
+			helper = _dense.CudaDenseSineIntegrator(*coupling[:2], coupling_parameter=len(coupling) == 3)
+			if len(coupling) == 3:
+				helper.set_parameters(self._parameter_rows())
 			return helper.eval_f(state)
 		module = self._f_module or (next(iter(self._modules.values())) if self._modules else self._module(_codegen.JB_DP5, _codegen.JB_DRV_ODE))
 		self._f_module = module
@@ -543,7 +550,7 @@ class jitcode:
 		if count != len(self.control_pars):
 			raise ValueError("Number of values does not match number of control parameters.")
 		self.control_par_values = values
-		if isinstance(self.integrator, CudaEnsembleIntegrator) and count:
+		if isinstance(self.integrator, (CudaEnsembleIntegrator, _dense.CudaDenseSineIntegrator)) and count:
 			self.integrator.set_parameters(self._parameter_rows())
 
 	def set_f_params(self, *args):
@@ -593,7 +600,11 @@ class jitcode:
 			require_cuda(device)                                         # … running does
 			integrator_params.pop("verbosity", None)
 			self._integrator_config = None
-			self.integrator = _dense.CudaDenseSineIntegrator(*self._dense_coupling(), method=method, device=device, nsteps=nsteps, **integrator_params)
+			coupling = self._dense_coupling()
+			self.integrator = _dense.CudaDenseSineIntegrator(*coupling[:2], method=method, device=device, nsteps=nsteps,
+					coupling_parameter=len(coupling) == 3, **integrator_params)
+			if len(coupling) == 3 and self.control_par_values is not None:
+				self.integrator.set_parameters(self._parameter_rows())
 			self._restore_state(old_integrator)
 			return
 		module = self._module(method, driver, storage, threads, kregs, min_blocks, team_warps)   # compiling needs no GPU …

@@ -271,6 +271,8 @@ struct Dense {
 	int64_t B, ld;
 	int n;
 	const double *W, *omega;
+	const double *coupling;     // [ld] per-trajectory factor of the coupling sum, or null
+	const double *atol_vec;     // [n] per-component atol, or null
 	double T, rtol, atol, max_step, first_step;
 	int64_t nmax;
 	double safety, facc1, facc2, beta, expo1;
@@ -306,6 +308,7 @@ __device__ __forceinline__ void for_rows(const Dense &d, F &&body)
 }
 
 __device__ __forceinline__ int flags_of(const Dense &d, int64_t b) { return (int) d.ctrl[C_FLAGS * d.ld + b]; }
+__device__ __forceinline__ double atol_of(const Dense &d, int i) { return d.atol_vec ? d.atol_vec[i] : d.atol; }
 
 // adds `value` (a per-thread partial sum over this thread's rows) to slot[b]: shared-memory reduction over the
 // 8 row lanes of the block, then one atomic per (block, trajectory)
@@ -338,7 +341,8 @@ __global__ void __launch_bounds__(256) sincos_kernel(const Dense d, int need_fla
 template <int J>
 __device__ __forceinline__ double finish_rhs(const Dense &d, int i, int64_t b, int64_t at)
 {
-	const double value = d.omega[i] + xs_cos(d, i, b) * g_sin(d, i, b) - xs_sin(d, i, b) * g_cos(d, i, b);
+	const double sum = xs_cos(d, i, b) * g_sin(d, i, b) - xs_sin(d, i, b) * g_cos(d, i, b);
+	const double value = d.coupling ? fma(d.coupling[b], sum, d.omega[i]) : d.omega[i] + sum;
 	vec(d, W_K0 + J)[at] = value;
 	return value;
 }
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(256) start_kernel(const Dense d)
 	if (active)
 		for_rows(d, [&](int i, int64_t, int64_t at) {
 			const double f0 = finish_rhs<0>(d, i, b, at);
-			const double sk = fma(d.rtol, fabs(d.Y[at]), d.atol);
+			const double sk = fma(d.rtol, fabs(d.Y[at]), atol_of(d, i));
 			const double qf = f0 / sk, qy = d.Y[at] / sk;
 			dnf = fma(qf, qf, dnf);
 			dny = fma(qy, qy, dny);
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(256) probe_finish_kernel(const Dense d)
 	if (active)
 		for_rows(d, [&](int i, int64_t, int64_t at) {
 			const double f1 = finish_rhs<1>(d, i, b, at);
-			const double q = (f1 - vec(d, W_K0)[at]) / fma(d.rtol, fabs(d.Y[at]), d.atol);
+			const double q = (f1 - vec(d, W_K0)[at]) / fma(d.rtol, fabs(d.Y[at]), atol_of(d, i));
 			der2 = fma(q, q, der2);
 		});
 	reduce_to(d.ctrl + C_DER2 * d.ld, b, active, der2);
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const Dense d)
 				if constexpr (w5 != 0.0) e5 = fma(w5, k[j], e5);
 				if constexpr (w3 != 0.0) e3 = fma(w3, k[j], e3);
 			});
-			const double sk = fma(d.rtol, fmax(fabs(y), fabs(z)), d.atol);
+			const double sk = fma(d.rtol, fmax(fabs(y), fabs(z)), atol_of(d, i));
 			e5 /= sk;
 			e3 /= sk;
 			s5 = fma(e5, e5, s5);
@@ -549,7 +553,7 @@ __global__ void __launch_bounds__(256) error_kernel(const Dense d)
 					constexpr double w = DP5::E[j];
 					if constexpr (w != 0.0) e = fma(w, vec(d, W_K0 + j)[at], e);
 				});
-				const double sk = fma(d.rtol, fmax(fabs(d.Y[at]), fabs(vec(d, W_Z)[at])), d.atol);
+				const double sk = fma(d.rtol, fmax(fabs(d.Y[at]), fabs(vec(d, W_Z)[at])), atol_of(d, i));
 				const double q = h * e / sk;
 				sum = fma(q, q, sum);
 			}
@@ -771,7 +775,7 @@ int jb_dense_eval_f(const jb_dense_args *x, double *dY)
 {
 	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_eval_f: argument block has the wrong size");
 	jbd::Dense d{};
-	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega;
+	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega; d.coupling = x->coupling; d.atol_vec = x->atol_vec;
 	d.Y = x->Y; d.work = x->work; d.ctrl = x->ctrl; d.status = x->status;
 	d.tile_skip = x->scratch; d.active_count = x->scratch + x->ld / 32 + 1;
 	d.t = x->t; d.T = INFINITY;
@@ -810,7 +814,7 @@ static int integrate(const jb_dense_args *x)
 			|| !x->status || !x->n_accepted || !x->n_rejected || !x->scratch || !x->host_flag)
 		return jbd::fail(JB_E_BAD_ARGUMENT, "jb_dense_integrate: missing or inconsistent buffers");
 	jbd::Dense d{};
-	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega;
+	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega; d.coupling = x->coupling; d.atol_vec = x->atol_vec;
 	d.T = x->T; d.rtol = x->rtol; d.atol = x->atol; d.max_step = x->max_step; d.first_step = x->first_step;
 	d.nmax = x->nsteps > 0 ? x->nsteps : 100000;
 	d.safety = x->safety > 0.0 ? x->safety : 0.9;

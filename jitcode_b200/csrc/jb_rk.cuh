@@ -649,8 +649,12 @@ struct StiffnessWatch {
 	}
 };
 
+// spacing of the doubles just above t: |nextafter(t, ∞) − t| (RungeKutta._step_impl: min_step = 10·that)
 __device__ __forceinline__ double ulp_above(double t)
 {
+	// positive normal t whose spacing is normal too: 2^(exponent − 52), straight from the bits
+	const unsigned biased = ((unsigned) __double2hiint(t) >> 20) & 0x7ffu;
+	if (t > 0.0 && biased > 52u && biased < 0x7feu) return __hiloint2double((int) ((biased - 52u) << 20), 0);
 	return fabs(::nextafter(t, (double) INFINITY) - t);
 }
 

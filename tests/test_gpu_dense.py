@@ -203,3 +203,49 @@ def test_dense_stiffness_detection():
 		# which the test gives up agrees to a few per cent there, and to rounding where the problem is not stiff
 		assert_allclose(ODE.integrator.tt[:B].cpu().numpy(), ref["t"], rtol=0.05 if stiff else 1e-12)
 		assert_allclose(ODE.integrator.y_device.cpu().numpy(), ref["y"], rtol=1e-6, atol=0.05 if stiff else 1e-9)
+
+
+@pytest.mark.parametrize("name", ["dopri5", "dop853"])
+def test_dense_coupling_parameter_and_vector_atol(name):
+	"""the coupling strength as a per-trajectory control parameter (dy_i/dt = ω_i + c·Σ_j W_ij sin(y_j − y_i), recognised
+	in the symbolic input) and one atol per component: dense engine against the generic kernels, which compile the
+	written-out form with `c` as an ordinary control parameter, and against the oracle"""
+	import sympy
+	from jitcode_b200 import y
+	from oracle import c_rhs, ensemble
+	n, B = 40, 70
+	data = W.kuramoto_data(n)
+	A, omega = data["A"], data["omega"]
+	c = sympy.Symbol("c")
+	f = [omega[i] + c / (n - 1) * sympy.Add(*[sympy.sin(y(j) - y(i)) for j in range(n) if A[j, i]]) for i in range(n)]
+	Y0 = W.kuramoto_ensemble(B, n, seed=8)
+	strengths = np.random.default_rng(9).uniform(0.5, 4.0, B)
+	atol = 10.0 ** np.random.default_rng(10).uniform(-11, -8, n)
+	times = [1.0, 2.5, 6.0]
+	results = {}
+	for storage in ("dense", None):
+		ODE = jitcode(f, n=n, control_pars=[c], verbose=False)
+		ODE.set_integrator(name, rtol=1e-7, atol=atol, **({"storage": storage} if storage else {"storage": "global"}))
+		assert (ODE.integrator.module.info.storage == 4) == (storage == "dense")
+		ODE.set_parameters(strengths)
+		ODE.set_initial_value(Y0, 0.0)
+		results[storage] = ODE.integrate_many(times)
+	bound = 10 * (atol + 1e-7 * np.abs(results[None]))
+	assert np.all(np.abs(results["dense"] - results[None]) <= bound)
+	# the default choice for such a system is the dense engine, and one value serves all trajectories
+	ODE = jitcode(f, n=n, control_pars=[c], verbose=False)
+	ODE.set_integrator(name, rtol=1e-7, atol=atol)
+	assert ODE.integrator.module.info.storage == 4
+	ODE.set_parameters(2.0)
+	ODE.set_initial_value(Y0[:16], 0.0)
+	single = ODE.integrate(2.0)
+	handle = c_rhs.build_rhs(f, control_pars=[c], n=n)
+	# (SciPy's compiled dopri5/dop853 take a scalar atol: the oracle runs with the smallest one)
+	ref = ensemble.run_ensemble(handle, name, Y0[:16], [2.0], pars=np.full((16, 1), 2.0), rtol=1e-7, atol=float(atol.min()))["y"][0]
+	assert np.all(np.abs(single - ref) <= 30 * (atol + 1e-7 * np.abs(ref)))
+	assert_allclose(ODE.f(0.3, Y0[:9]), handle_f_many(handle, 2.0, Y0[:9]), rtol=1e-11, atol=1e-12)
+
+
+def handle_f_many(handle, strength, states):
+	handle.initialise(strength)
+	return np.stack([handle.f(0.3, state) for state in states])
