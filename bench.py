@@ -24,6 +24,7 @@ the lattice-specific paths of the code generator do not apply):
     kuramoto_dopri5  the same under dopri5
     roessler_random  config 3's network rewired with probability 1 (no lattice left), 256 Ki trajectories
     roessler_er      Erdős–Rényi network of the same mean degree, 256 Ki trajectories
+    roessler_t50     config 3 sampled every 10 time units up to t = 50 (the example's loop) in one launch, 256 Ki trajectories
 `strong` (N > 1): 1 Mi trajectories IN TOTAL sharded over the ranks, every rank's result written by its integrate kernel's
 unpack straight into its slot of the all-gather buffer, one in-place ncclAllGather inside the timed region.
 
@@ -60,23 +61,28 @@ METRIC = "ensemble RK45 trajectory-steps/s"
 UNIT = "trajectory-steps/s"
 RTOL, ATOL = 1e-6, 1e-12
 HEADLINE = "roessler"
-CONFIGS = ("lv", "lv_RK45", "fhn_lyap", "kuramoto", "kuramoto_dopri5", "roessler_random", "roessler_er")
+CONFIGS = ("lv", "lv_RK45", "fhn_lyap", "kuramoto", "kuramoto_dopri5", "roessler_random", "roessler_er", "roessler_t50")
 STRONG = ("roessler", "lv")
 DEFAULT_TRAJECTORIES = {"roessler": 1 << 20, "lv": 1 << 20, "lv_RK45": 1 << 20, "fhn_lyap": 100_000, "kuramoto": 4096,
-		"kuramoto_dopri5": 4096, "roessler_random": 1 << 18, "roessler_er": 1 << 18}
+		"kuramoto_dopri5": 4096, "roessler_random": 1 << 18, "roessler_er": 1 << 18, "roessler_t50": 1 << 18}
 CPU_SAMPLE_PER_CORE = {"roessler": 2048, "lv": 1024, "lv_RK45": 48, "fhn_lyap": 2048, "kuramoto": 2, "kuramoto_dopri5": 2,
-		"roessler_random": 1024, "roessler_er": 1024}
+		"roessler_random": 1024, "roessler_er": 1024, "roessler_t50": 256}
 
 
 def workload(name, B, seed_offset=0):
 	"""the synthetic input of one config: system, seeded ensemble, sample times, integrator, tolerances"""
 	if name.startswith("roessler"):
-		topology = {"roessler": "small_world", "roessler_random": "random", "roessler_er": "erdos_renyi"}[name]
+		topology = {"roessler": "small_world", "roessler_random": "random", "roessler_er": "erdos_renyi", "roessler_t50": "small_world"}[name]
 		system = W.roessler_network(100, topology=topology)
 		Y0, pars = W.roessler_ensemble(B, seed=43 + seed_offset)
 		label = {"small_world": "SW_of_Roesslers N=100 (n=300), per-trajectory k and Y0",
 				"random": "Roessler network N=100 (n=300), ring rewired with p=1 (random graph, degree 20)",
 				"erdos_renyi": "Roessler network N=100 (n=300), Erdos-Renyi graph of mean degree 20"}[topology]
+		if name == "roessler_t50":
+			# the example's sampling (outputs every 10 time units) as ONE launch; chaotic (λ ≈ 0.08): two implementations
+			# of the same method agree to 1e-3 of the state's scale up to t = 50 (SURVEY.md §8d)
+			return {"kind": "generic", "system": system, "Y0": Y0, "pars": pars, "T": 50.0, "times": [10.0, 20.0, 30.0, 40.0, 50.0], "integrator": "dopri5",
+					"rtol": RTOL, "atol": ATOL, "label": label + ", samples t=10..50 in one launch", "parity": {"n": 256, "rule": "scale", "bound": 1e-3}}
 		# chaotic: agreement to 1e-6 of the state's scale at the horizon T = 10 (SURVEY.md §8d)
 		return {"kind": "generic", "system": system, "Y0": Y0, "pars": pars, "T": 10.0, "times": [10.0], "integrator": "dopri5",
 				"rtol": RTOL, "atol": ATOL, "label": label, "parity": {"n": 256, "rule": "scale", "bound": 1e-6}}
@@ -401,7 +407,7 @@ class Bench:
 				states, exponents = ODE.integrate_many(times, record_states=False)     # the calls of the example's loop as one launch
 				keep["lyaps"] = exponents
 				return states
-			if kind == "dense":
+			if kind == "dense" or len(times) > 1:
 				return ODE.integrate_many(times)
 			return ODE.integrate(wl["T"])
 
@@ -416,6 +422,9 @@ class Bench:
 				return ODE.integrate_many(times)                                       # every sample, as the example stores them
 			if pars_host is not None:
 				ODE.set_parameters(pars_host)
+			if len(times) > 1:
+				ODE.set_initial_value(Y0_host, 0.0)
+				return ODE.integrate_many(times)                                       # every sample back to the host
 			if hasattr(solver, "integrate_streamed") and B >= 65536:
 				# the public call for host-resident ensembles: uploads and downloads overlap the kernels chunk by chunk
 				return ODE.integrate_streamed(Y0_host, wl["T"], out_host, 0.0, chunks=args.chunks)

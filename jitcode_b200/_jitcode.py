@@ -405,6 +405,12 @@ class jitcode:
 					raise ValueError("Shared storage: the stages of that many trajectories do not fit one block's shared memory.")
 				if min_blocks is None and storage == _codegen.JB_STORE_GLOBAL:
 					min_blocks = 8      # 16 warps/SM at ≤ 128 registers: measured +60 % over 8 warps at 255 (latency-bound streaming)
+				if min_blocks is None and storage == _codegen.JB_STORE_REGISTERS:
+					# small systems: cap the registers so that 16 (12) warps stay resident — the delivery code of the
+					# persistent kernel (dense output, write-back) otherwise inflates the allocation of the step loop
+					# (Lotka–Volterra under RK45: 142 registers uncapped = 12 warps, measured 10 % slower than 16)
+					doubles = (_stage_rows(method, driver) + 3) * self.n
+					min_blocks = max(1, (4 if doubles <= 40 else 3 if doubles <= 64 else 2) * 128 // threads)
 			source = _codegen.module_source(
 				statements, self.n, len(self.control_pars),
 				self._n_basic_module, self._n_lyap_module, self._tangent_indices_module,

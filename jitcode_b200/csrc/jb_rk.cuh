@@ -653,8 +653,10 @@ struct StiffnessWatch {
 __device__ __forceinline__ double ulp_above(double t)
 {
 	// positive normal t whose spacing is normal too: 2^(exponent − 52), straight from the bits
+#ifndef JB_SLOW_ULP
 	const unsigned biased = ((unsigned) __double2hiint(t) >> 20) & 0x7ffu;
 	if (t > 0.0 && biased > 52u && biased < 0x7feu) return __hiloint2double((int) ((biased - 52u) << 20), 0);
+#endif
 	return fabs(::nextafter(t, (double) INFINITY) - t);
 }
 
@@ -1363,53 +1365,61 @@ __device__ __forceinline__ void run_lanes(const Params &a)
 	bool stepping = false;      // … which is on its way to sample time `it`
 	bool more = true;           // the queue may still hold trajectories
 	int it = 0;
-	// from sample index `it` on: deliver what needs no integration, start towards the first sample time that does;
-	// false: the trajectory is through with all its sample times (or has failed: failures are sticky)
-	auto advance = [&]() {
-		while (it < a.n_times && lane.status == JB_OK) {
-			if (lane.begin_sample(a.times[it])) return true;
-			if (lane.status == JB_OK) lane.sample(it, a.times[it]);
-			++it;
-		}
-		return false;
-	};
+	double T = 0.0;             // a.times[it], in a register (the step loop compares with it in every attempt)
 	while (true) {
 		const unsigned waiting = __ballot_sync(FULL, !stepping);
 		const unsigned able = __ballot_sync(FULL, !stepping && (occupied || more));      // lanes with something to deliver or to fetch
 		if (waiting == FULL && able == 0) break;
 		if (able != 0 && (__popc(able) >= REFILL || waiting == FULL)) {
-			if (!stepping && occupied) {
-				// ---- the trajectory has arrived at sample time `it` (or failed): deliver, go on or write the solver back
-				if (lane.status == JB_OK) lane.sample(it, a.times[it]);
-				++it;
-				stepping = advance();
-				if (!stepping) {
-					lane.store();
-					occupied = false;
+			// ---- change of trajectories.  Pass 0: the lanes that have arrived at sample time `it` (or failed) deliver
+			// the sample and go on to their next sample time, or write the solver back and become free.  Then the free
+			// lanes take the next trajectories of the queue (one atomic per warp).  Pass 1: those start.  (One loop, not
+			// two copies of its body: delivering and starting are the bulky parts of the kernel.)
+			bool arrived = !stepping && occupied, fresh = false;
+#pragma unroll 1
+			for (int pass = 0; pass < 2; ++pass) {
+				if (pass == 0 ? arrived : fresh) {
+					bool deliver = arrived;
+					while (true) {
+						if (deliver) {
+							if (lane.status == JB_OK) lane.sample(it, T);
+							++it;
+						}
+						if (it >= a.n_times || lane.status != JB_OK) {      // through with all sample times, or failed (failures are sticky)
+							lane.store();
+							occupied = false;
+							break;
+						}
+						T = a.times[it];
+						if (lane.begin_sample(T)) {
+							stepping = true;
+							break;
+						}
+						deliver = true;       // nothing to integrate for this sample time: it is delivered at once
+					}
 				}
-			}
-			// ---- the free lanes take the next trajectories of the queue (one atomic per warp) and start them
-			const unsigned hungry = __ballot_sync(FULL, !occupied && more);
-			if (hungry != 0) {
-				const int first = __ffs(hungry) - 1;
-				unsigned long long base = 0;
-				if (index == first) base = atomicAdd(a.queue, (unsigned long long) __popc(hungry));
-				base = __shfl_sync(FULL, base, first);
-				if (!occupied && more) {
-					const int64_t mine = (int64_t) base + __popc(hungry & ((1u << index) - 1u));
-					if (mine >= a.B) {
-						more = false;
-					} else {
-						lane.load(mine);
-						it = 0;
-						stepping = advance();
-						if (stepping) occupied = true;
-						else lane.store();       // nothing to integrate at all (or failed earlier): done at once
+				if (pass == 0) {
+					arrived = false;
+					const unsigned hungry = __ballot_sync(FULL, !occupied && more);
+					if (hungry == 0) break;
+					const int first = __ffs(hungry) - 1;
+					unsigned long long base = 0;
+					if (index == first) base = atomicAdd(a.queue, (unsigned long long) __popc(hungry));
+					base = __shfl_sync(FULL, base, first);
+					if (!occupied && more) {
+						const int64_t mine = (int64_t) base + __popc(hungry & ((1u << index) - 1u));
+						if (mine >= a.B) {
+							more = false;
+						} else {
+							lane.load(mine);
+							it = 0;
+							occupied = fresh = true;
+						}
 					}
 				}
 			}
 		}
-		if (stepping) stepping = !lane.attempt_once(a.times[it]);
+		if (stepping) stepping = !lane.attempt_once(T);
 	}
 }
 
