@@ -179,10 +179,10 @@ typedef struct jb_dense_args {
 	double  *ctrl;             /* [jb_dense_control_scalars()][ld] */
 	int32_t *status;           /* [ld] enum jb_status, sticky */
 	int64_t *n_accepted, *n_rejected;   /* [ld] += */
-	int32_t *scratch;          /* [ld/32 + 2] device scratch */
-	int32_t *host_flag;        /* one int32 in (pinned) host memory: the host polls the number of unfinished trajectories */
+	int32_t *scratch;          /* [ld/32 + 8] device scratch */
+	int32_t *host_flag;        /* four int32 in (pinned) host memory: the host polls the number of unfinished trajectories (of each of the interleaved sub-ensembles) */
 	int32_t  rounds_per_check; /* lock-step rounds between two polls; 0 = default (1: a round takes milliseconds, a poll microseconds) */
-	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1) */
+	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1); bits 9-11: number of interleaved sub-ensembles (0: default, up to four of >= 1024 trajectories each; 1: none) */
 	int64_t *rounds_out;       /* host: number of lock-step rounds of this call, or NULL */
 	void    *stream;
 } jb_dense_args;

@@ -145,7 +145,8 @@ class CudaDenseSineIntegrator:
 	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5") or DOP853 ("dop853")."""
 
 	def __init__(self, W, omega, *, method=0, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
-			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=0, coupling_parameter=False):
+			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=0, coupling_parameter=False,
+			interleave=0):
 		self.device = require_cuda(device)
 		self.n = len(omega)
 		self.module = DenseModule(self.n)
@@ -168,7 +169,9 @@ class CudaDenseSineIntegrator:
 		self.nsteps = int(nsteps)
 		self.controller = (float(safety), float(ifactor), float(dfactor), float(beta))
 		self.rounds_per_check = int(rounds_per_check)
-		self.method_flags = int(method) | (256 if verbatim_dop853_reject else 0)
+		# interleave: number of sub-ensembles whose launch sequences overlap on separate streams (0: default — up to
+		# four of ≥ 1024 trajectories each; 1: none; csrc/jb_dense.cu, integrate)
+		self.method_flags = int(method) | (256 if verbatim_dop853_reject else 0) | ((int(interleave) & 7) << 9)
 		self.B = None
 		self.time = None
 		self._rows = None
@@ -191,8 +194,8 @@ class CudaDenseSineIntegrator:
 		self.status = torch.zeros(ld, dtype=torch.int32, device=dev)
 		self.n_accepted = torch.zeros(ld, dtype=torch.int64, device=dev)
 		self.n_rejected = torch.zeros(ld, dtype=torch.int64, device=dev)
-		self.scratch = torch.zeros(ld // 32 + 2, dtype=torch.int32, device=dev)
-		self.host_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+		self.scratch = torch.zeros(ld // 32 + 8, dtype=torch.int32, device=dev)
+		self.host_flag = torch.zeros(4, dtype=torch.int32).pin_memory()
 		self.rounds_host = np.zeros(1, dtype=np.int64)
 		self.coupling = torch.ones(ld, **f64) if self.n_params else None
 		self._pars_on_device = False

@@ -43,6 +43,18 @@ constexpr int LDA = BK + 4;     // shared-memory row lengths chosen so that a ha
 constexpr int LDB = BN + 4;     // (4 rows × 4 consecutive doubles) hit 32 distinct banks
 constexpr size_t GEMM_SHARED_BYTES = sizeof(double) * 2 * (BM * LDA + BK * LDB);     // double-buffered tiles
 
+// Which column tiles a launch computes.  A whole matrix: tile t starts at column t·width.  The right-hand side of a
+// SUB-ENSEMBLE (trajectories b0 … b1−1 of an ensemble with ld columns per half): its sine columns b0 … b1−1 and its
+// cosine columns ld+b0 … ld+b1−1 — tiles_half tiles each.
+struct Columns {
+	int tile0, tiles_half, half_tiles;      // tiles_half == 0: the whole matrix
+	__host__ __device__ int64_t first_column(int tile, int width) const
+	{
+		if (tiles_half == 0) return (int64_t) tile * width;
+		return (int64_t) (tile < tiles_half ? tile0 + tile : half_tiles + tile0 + tile - tiles_half) * width;
+	}
+};
+
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 {
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -51,11 +63,12 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 
 __global__ void __launch_bounds__(256)
 dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
-		int M, int N, int K, const int *__restrict__ tile_skip, int64_t ld)
+		int M, int N, int K, const int *__restrict__ tile_skip, int64_t ld, Columns columns)
 {
+	const int64_t n0 = columns.first_column((int) blockIdx.x, BN);
 	if (tile_skip) {
 		// columns n0 … n0+63 are trajectories (n0 mod ld) … of the sin or of the cos half; skip_flags are per 32 trajectories
-		const int64_t first = (((int64_t) blockIdx.x * BN) % ld) / 32;
+		const int64_t first = (n0 % ld) / 32;
 		if (tile_skip[first] && tile_skip[first + 1]) return;
 	}
 	extern __shared__ __align__(16) double gemm_shared[];
@@ -63,7 +76,7 @@ dgemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, do
 	double (*sB)[BK * LDB] = reinterpret_cast<double (*)[BK * LDB]>(gemm_shared + 2 * BM * LDA);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int wm = warp >> 1, wn = warp & 1;                 // warp position in the block tile
-	const int64_t m0 = (int64_t) blockIdx.y * BM, n0 = (int64_t) blockIdx.x * BN;
+	const int64_t m0 = (int64_t) blockIdx.y * BM;
 
 	double acc[4][4][2];
 #pragma unroll
@@ -161,12 +174,13 @@ __device__ __forceinline__ void cp_async_16(double *smem, const double *global, 
 template <class S>
 __global__ void __launch_bounds__(S::THREADS)
 dgemm_dmma_pipelined_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
-		int M, int N, int K, const int *__restrict__ tile_skip, int64_t ld)
+		int M, int N, int K, const int *__restrict__ tile_skip, int64_t ld, Columns columns)
 {
 	constexpr int TM = S::TM, TN = S::TN, SA = S::SA, SB = S::SB, MI = S::MI, NI = S::NI, THREADS = S::THREADS;
+	const int64_t n0 = columns.first_column((int) blockIdx.x, TN);
 	if (tile_skip) {
 		// columns n0 … n0+TN−1 are trajectories (n0 mod ld) … of the sin or of the cos half; flags are per 32 trajectories
-		const int64_t first = (((int64_t) blockIdx.x * TN) % ld) / 32;
+		const int64_t first = (n0 % ld) / 32;
 		bool all = true;
 #pragma unroll
 		for (int g = 0; g < TN / 32; ++g) all = all && tile_skip[first + g];
@@ -177,7 +191,7 @@ dgemm_dmma_pipelined_kernel(const double *__restrict__ A, const double *__restri
 	double *const sB = gemm_shared + STAGES * TM * SA;                // [STAGES][BK * SB]
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int wm = warp / S::WN, wn = warp % S::WN;
-	const int64_t m0 = (int64_t) blockIdx.y * TM, n0 = (int64_t) blockIdx.x * TN;
+	const int64_t m0 = (int64_t) blockIdx.y * TM;
 
 	double acc[MI][NI][2];
 #pragma unroll
@@ -268,7 +282,8 @@ template <> struct Coef<DOP853> {
 };
 
 struct Dense {
-	int64_t B, ld;
+	int64_t B, ld;          // trajectories b0 … B−1 of an ensemble whose arrays have ld columns
+	int64_t b0, b1;         // the sub-ensemble this launch sequence works on: columns b0 … b1−1 (multiples of 64)
 	int n;
 	const double *W, *omega;
 	const double *coupling;     // [ld] per-trajectory factor of the coupling sum, or null
@@ -297,7 +312,7 @@ constexpr int ROWS_PER_BLOCK = 64;
 template <class F>
 __device__ __forceinline__ void for_rows(const Dense &d, F &&body)
 {
-	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * 32 + threadIdx.x;
 	const int i0 = blockIdx.y * ROWS_PER_BLOCK + threadIdx.y;
 	if (b >= d.B) return;
 #pragma unroll
@@ -350,7 +365,7 @@ __device__ __forceinline__ double finish_rhs(const Dense &d, int i, int64_t b, i
 // after the GEMM of f(t, Y): K[0] = f; HINIT sums dnf = Σ(f/sk)², dny = Σ(y/sk)²
 __global__ void __launch_bounds__(256) start_kernel(const Dense d)
 {
-	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * 32 + threadIdx.x;
 	double dnf = 0.0, dny = 0.0;
 	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
 	if (active)
@@ -382,7 +397,7 @@ __global__ void __launch_bounds__(256) probe_kernel(const Dense d)
 // HINIT: der2 = Σ((f1 − f0)/sk)²
 __global__ void __launch_bounds__(256) probe_finish_kernel(const Dense d)
 {
-	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * 32 + threadIdx.x;
 	double der2 = 0.0;
 	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
 	if (active)
@@ -413,7 +428,7 @@ __device__ __forceinline__ void publish_activity(const Dense &d, int64_t b, bool
 {
 	// one flag per 32-trajectory tile for the GEMM, one counter for the host
 	const unsigned any = __ballot_sync(0xffffffffu, active);
-	if ((threadIdx.x & 31) == 0 && b < d.ld) {
+	if ((threadIdx.x & 31) == 0 && b < d.b1) {       // (the grid may overshoot the sub-ensemble: the next one's tiles are not ours)
 		d.tile_skip[b / 32] = any == 0;
 		if (any) atomicAdd(d.active_count, __popc(any));
 	}
@@ -422,7 +437,7 @@ __device__ __forceinline__ void publish_activity(const Dense &d, int64_t b, bool
 // one thread per trajectory: decide which trajectories integrate at all, reset their controllers
 __global__ void __launch_bounds__(256) setup_kernel(const Dense d)
 {
-	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	bool active = false;
 	if (b < d.B) {
 		active = d.status[b] == JB_OK && d.T > d.t[b];
@@ -440,7 +455,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const Dense d)
 template <class Tab>
 __global__ void __launch_bounds__(256) first_step_kernel(const Dense d, int have_probe)
 {
-	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	bool active = false;
 	if (b < d.B) {
 		int flags = flags_of(d, b);
@@ -478,7 +493,7 @@ __global__ void __launch_bounds__(256) stage_kernel(const Dense d)
 {
 	constexpr int S = Tab::NSTAGE;
 	constexpr bool SUMS_ERROR = !Tab::ERR_NEEDS_FSAL && ROW == S;
-	const int64_t bb = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	const int64_t bb = d.b0 + (int64_t) blockIdx.x * 32 + threadIdx.x;
 	double s5 = 0.0, s3 = 0.0;
 	for_rows(d, [&](int i, int64_t b, int64_t at) {
 		const int flags = flags_of(d, b);
@@ -538,7 +553,7 @@ template <class Tab>
 __global__ void __launch_bounds__(256) error_kernel(const Dense d)
 {
 	constexpr int S = Tab::NSTAGE;
-	const int64_t b = (int64_t) blockIdx.x * 32 + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * 32 + threadIdx.x;
 	const int flags = b < d.B ? flags_of(d, b) : 0;
 	const bool active = flags & F_ACTIVE;
 	const bool stiff_due = active && (flags & F_STIFF);
@@ -582,7 +597,7 @@ __global__ void __launch_bounds__(256) error_kernel(const Dense d)
 template <class Tab>
 __global__ void __launch_bounds__(256) control_kernel(const Dense d)
 {
-	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	bool active = false;
 	if (b < d.B) {
 		int flags = flags_of(d, b);
@@ -666,7 +681,7 @@ __global__ void __launch_bounds__(256) commit_kernel(const Dense d)
 
 __global__ void clear_accepted_kernel(const Dense d)
 {
-	const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (b < d.B) d.ctrl[C_FLAGS * d.ld + b] = (double) (flags_of(d, b) & ~F_ACCEPTED);
 }
 
@@ -703,37 +718,42 @@ using Shape64 = Shape<4, 2, 2, 4>;       //  64 × 64, 256 threads
 constexpr int N_SHAPES = 4;
 
 template <class S>
-static void launch_shape(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream)
+static void launch_shape(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream, Columns columns)
 {
 	// (the attribute is a per-device property of the function; setting it costs a microsecond and keeps this re-entrant)
 	cudaFuncSetAttribute(dgemm_dmma_pipelined_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) S::SHARED_BYTES);
-	const dim3 grid((N + S::TN - 1) / S::TN, (M + S::TM - 1) / S::TM);
-	dgemm_dmma_pipelined_kernel<S><<<grid, S::THREADS, S::SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
+	const unsigned tiles = columns.tiles_half ? 2u * columns.tiles_half : (unsigned) ((N + S::TN - 1) / S::TN);
+	const dim3 grid(tiles, (M + S::TM - 1) / S::TM);
+	dgemm_dmma_pipelined_kernel<S><<<grid, S::THREADS, S::SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld, columns);
 }
 
-static void launch_gemm(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream, int shape = -1)
+static void launch_gemm(const double *A, const double *B, double *C, int M, int N, int K, const int *tile_skip, int64_t ld, cudaStream_t stream,
+		int shape = -1, Columns columns = Columns{0, 0, 0})
 {
 	const bool aligned = K % 2 == 0 && N % 2 == 0 && (((uintptr_t) A | (uintptr_t) B) & 15) == 0;
 	if (!aligned) {
 		cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GEMM_SHARED_BYTES);
-		const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-		dgemm_dmma_kernel<<<grid, 256, GEMM_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld);
+		const unsigned tiles = columns.tiles_half ? 2u * columns.tiles_half : (unsigned) ((N + BN - 1) / BN);
+		const dim3 grid(tiles, (M + BM - 1) / BM);
+		dgemm_dmma_kernel<<<grid, 256, GEMM_SHARED_BYTES, stream>>>(A, B, C, M, N, K, tile_skip, ld, columns);
 		launch_counter.fetch_add(1, std::memory_order_relaxed);
 		return;
 	}
 	if (shape < 0) shape = M <= 64 ? 3 : (M <= 96 ? 2 : 0);
 	switch (shape) {
-	case 1: launch_shape<Shape112>(A, B, C, M, N, K, tile_skip, ld, stream); break;
-	case 2: launch_shape<Shape96>(A, B, C, M, N, K, tile_skip, ld, stream); break;
-	case 3: launch_shape<Shape64>(A, B, C, M, N, K, tile_skip, ld, stream); break;
-	default: launch_shape<Shape128>(A, B, C, M, N, K, tile_skip, ld, stream); break;
+	case 1: launch_shape<Shape112>(A, B, C, M, N, K, tile_skip, ld, stream, columns); break;
+	case 2: launch_shape<Shape96>(A, B, C, M, N, K, tile_skip, ld, stream, columns); break;
+	case 3: launch_shape<Shape64>(A, B, C, M, N, K, tile_skip, ld, stream, columns); break;
+	default: launch_shape<Shape128>(A, B, C, M, N, K, tile_skip, ld, stream, columns); break;
 	}
 	launch_counter.fetch_add(1, std::memory_order_relaxed);
 }
 
 static void gemm(const Dense &d, cudaStream_t stream)
 {
-	launch_gemm(d.W, vec(d, W_XS), vec(d, W_G), d.n, (int) (2 * d.ld), d.n, d.tile_skip, d.ld, stream);
+	// (all tile shapes are 64 columns wide, like the padding of ld)
+	const Columns columns{(int) (d.b0 / 64), (int) ((d.b1 - d.b0) / 64), (int) (d.ld / 64)};
+	launch_gemm(d.W, vec(d, W_XS), vec(d, W_G), d.n, (int) (2 * d.ld), d.n, d.tile_skip, d.ld, stream, -1, columns);
 }
 
 }  // namespace jbd
@@ -776,6 +796,7 @@ int jb_dense_eval_f(const jb_dense_args *x, double *dY)
 	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_eval_f: argument block has the wrong size");
 	jbd::Dense d{};
 	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega; d.coupling = x->coupling; d.atol_vec = x->atol_vec;
+	d.b0 = 0; d.b1 = x->ld;
 	d.Y = x->Y; d.work = x->work; d.ctrl = x->ctrl; d.status = x->status;
 	d.tile_skip = x->scratch; d.active_count = x->scratch + x->ld / 32 + 1;
 	d.t = x->t; d.T = INFINITY;
@@ -804,7 +825,31 @@ static void launch_stages(const Dense &d, dim3 egrid, dim3 eblock, cudaStream_t 
 	}
 }
 
-// advance every trajectory to x->T (Hairer's DOPRI5 / DOP853, fresh start, lands exactly on T)
+// extra streams per device for the interleaved sub-ensembles (created once; read-only afterwards)
+constexpr int MAX_CHAINS = 4;
+static cudaStream_t side_stream(int which)
+{
+	static std::atomic<cudaStream_t> streams[64][MAX_CHAINS];
+	int device = 0;
+	if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64 || which < 0 || which >= MAX_CHAINS) return nullptr;
+	cudaStream_t stream = streams[device][which].load(std::memory_order_acquire);
+	if (!stream) {
+		if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+		cudaStream_t expected = nullptr;
+		if (!streams[device][which].compare_exchange_strong(expected, stream)) {      // another thread was faster
+			cudaStreamDestroy(stream);
+			stream = expected;
+		}
+	}
+	return stream;
+}
+
+// advance every trajectory to x->T (Hairer's DOPRI5 / DOP853, fresh start, lands exactly on T).
+// Large ensembles are integrated as SEVERAL sub-ensembles whose launch sequences are interleaved on as many streams: the
+// step of one is a chain of dependent kernels — element-wise stage kernel (memory-bound), GEMM (tensor-bound), stage
+// kernel, … — so with a second, independent chain in flight the stage kernels of one run under the GEMM of the other
+// and the partly filled last wave of a GEMM's blocks is topped up.  The host polls one chain while the other has a
+// round queued.
 template <class Tab>
 static int integrate(const jb_dense_args *x)
 {
@@ -832,58 +877,132 @@ static int integrate(const jb_dense_args *x)
 	d.reject_by_dfactor = (x->method_flags >> 8) & 1;
 	d.t = x->t; d.Y = x->Y; d.work = x->work; d.ctrl = x->ctrl; d.status = x->status;
 	d.n_accepted = x->n_accepted; d.n_rejected = x->n_rejected;
-	d.tile_skip = x->scratch; d.active_count = x->scratch + x->ld / 32 + 1;
-	cudaStream_t stream = (cudaStream_t) x->stream;
-	const dim3 eblock(32, 8), egrid((unsigned) (d.ld / 32), (unsigned) ((d.n + jbd::ROWS_PER_BLOCK - 1) / jbd::ROWS_PER_BLOCK));
-	const unsigned tgrid = (unsigned) ((d.ld + 255) / 256);
-
-	auto active_trajectories = [&](int *count) -> cudaError_t {
-		cudaError_t err = cudaMemcpyAsync(x->host_flag, d.active_count, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
-		if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
-		*count = *x->host_flag;
-		return err;
-	};
-	auto reset_count = [&]() { return cudaMemsetAsync(d.active_count, 0, sizeof(int32_t), stream); };
-
-	// ---- fresh start: f(t, Y), HINIT
-	cudaError_t err = reset_count();
-	JBD_LAUNCH(jbd::setup_kernel, tgrid, 256, d);
-	int active = 0;
-	if (err == cudaSuccess) err = active_trajectories(&active);
-	if (err != cudaSuccess) return jbd::fail((int) err, "jb_dense_integrate");
-	if (active == 0) return 0;
-	JBD_LAUNCH(jbd::sincos_kernel<0>, egrid, eblock, d, jbd::F_ACTIVE);
-	jbd::gemm(d, stream);
-	JBD_LAUNCH(jbd::start_kernel, egrid, eblock, d);
+	d.tile_skip = x->scratch;
 	const int have_probe = !(d.first_step > 0.0);
-	if (have_probe) {
-		JBD_LAUNCH(jbd::probe_kernel, egrid, eblock, d);
-		jbd::gemm(d, stream);
-		JBD_LAUNCH(jbd::probe_finish_kernel, egrid, eblock, d);
-	}
-	reset_count();
-	JBD_LAUNCH(jbd::first_step_kernel<Tab>, tgrid, 256, d, have_probe);
 
-	// ---- rounds: one step attempt of every unfinished trajectory; the host looks at the counter every few rounds
-	const int check_every = x->rounds_per_check > 0 ? x->rounds_per_check : 1;
-	int64_t rounds = 0;
-	while (true) {
-		for (int r = 0; r < check_every; ++r) {
-			launch_stages<Tab>(d, egrid, eblock, stream);
-			JBD_LAUNCH(jbd::error_kernel<Tab>, egrid, eblock, d);
-			reset_count();
-			JBD_LAUNCH(jbd::control_kernel<Tab>, tgrid, 256, d);
-			++rounds;
-		}
-		err = active_trajectories(&active);
-		if (err != cudaSuccess) return jbd::fail((int) err, "jb_dense_integrate");
-		if (active == 0) break;
-		if (rounds > d.nmax + 8) return jbd::fail(JB_E_UNSUPPORTED, "jb_dense_integrate: round limit exceeded");
+	// ---- the sub-ensembles: equal parts of ≥ 1024 trajectories each (bits 9-11 of method_flags: that many chains; 0: as many as fit, at most four — measured on config 5: 1: 234.7 ms, 2: 224.1, 3: 212.3, 4: 215.9 per ten samples)
+	struct Chain {
+		Dense d;
+		cudaStream_t stream;
+		cudaEvent_t polled;
+		int32_t *host_flag;
+		bool alive;
+		int64_t rounds;
+	} chains[MAX_CHAINS];
+	cudaStream_t main_stream = (cudaStream_t) x->stream;
+	const int wanted = (x->method_flags >> 9) & 7;
+	int n_chains = wanted ? wanted : MAX_CHAINS;
+	if (n_chains > MAX_CHAINS) n_chains = MAX_CHAINS;
+	while (n_chains > 1 && d.B < 1024 * (int64_t) n_chains) --n_chains;
+	for (int c = 1; c < n_chains; ++c)
+		if (!side_stream(c)) n_chains = 1;
+	const int64_t part = n_chains > 1 ? (d.B / n_chains + 63) / 64 * 64 : d.ld;
+	for (int c = 0; c < n_chains; ++c) {
+		Chain &chain = chains[c];
+		chain.d = d;
+		chain.d.b0 = c * part;
+		chain.d.b1 = c == n_chains - 1 ? d.ld : (c + 1) * part;
+		if (chain.d.B > chain.d.b1) chain.d.B = chain.d.b1;       // its kernels must not touch the next chain's trajectories
+		chain.d.active_count = x->scratch + x->ld / 32 + 1 + c;
+		chain.stream = c == 0 ? main_stream : side_stream(c);
+		chain.host_flag = x->host_flag + c;
+		chain.alive = true;
+		chain.rounds = 0;
+		if (cudaEventCreateWithFlags(&chain.polled, cudaEventDisableTiming) != cudaSuccess)
+			return jbd::fail((int) cudaGetLastError(), "jb_dense_integrate: creating an event");
 	}
-	JBD_LAUNCH(jbd::commit_kernel, egrid, eblock, d);
-	JBD_LAUNCH(jbd::clear_accepted_kernel, tgrid, 256, d);
+	cudaError_t err = cudaSuccess;
+	for (int c = 1; c < n_chains && err == cudaSuccess; ++c) {
+		// the extra streams join the caller's: they start after what the caller has queued so far
+		err = cudaEventRecord(chains[c].polled, main_stream);
+		if (err == cudaSuccess) err = cudaStreamWaitEvent(chains[c].stream, chains[c].polled, 0);
+	}
+
+	const dim3 eblock(32, 8);
+	auto grids = [&](const Dense &sub, dim3 &egrid, unsigned &tgrid) {
+		const int64_t width = sub.b1 - sub.b0;
+		egrid = dim3((unsigned) (width / 32), (unsigned) ((sub.n + jbd::ROWS_PER_BLOCK - 1) / jbd::ROWS_PER_BLOCK));
+		tgrid = (unsigned) ((width + 255) / 256);
+	};
+	// queue the copy of the chain's counter of unfinished trajectories and mark the point to wait for
+	auto queue_poll = [&](Chain &chain) {
+		cudaMemcpyAsync(chain.host_flag, chain.d.active_count, sizeof(int32_t), cudaMemcpyDeviceToHost, chain.stream);
+		cudaEventRecord(chain.polled, chain.stream);
+	};
+	auto reset_count = [&](Chain &chain) { cudaMemsetAsync(chain.d.active_count, 0, sizeof(int32_t), chain.stream); };
+	// ---- fresh start: f(t, Y), HINIT
+	auto launch_start = [&](Chain &chain) {
+		const Dense &sub = chain.d;
+		cudaStream_t stream = chain.stream;
+		dim3 egrid; unsigned tgrid;
+		grids(sub, egrid, tgrid);
+		reset_count(chain);
+		JBD_LAUNCH(jbd::setup_kernel, tgrid, 256, sub);
+		JBD_LAUNCH(jbd::sincos_kernel<0>, egrid, eblock, sub, jbd::F_ACTIVE);
+		jbd::gemm(sub, stream);
+		JBD_LAUNCH(jbd::start_kernel, egrid, eblock, sub);
+		if (have_probe) {
+			JBD_LAUNCH(jbd::probe_kernel, egrid, eblock, sub);
+			jbd::gemm(sub, stream);
+			JBD_LAUNCH(jbd::probe_finish_kernel, egrid, eblock, sub);
+		}
+		reset_count(chain);
+		JBD_LAUNCH(jbd::first_step_kernel<Tab>, tgrid, 256, sub, have_probe);
+		queue_poll(chain);
+	};
+	// ---- a round: one step attempt of every unfinished trajectory of the chain
+	auto launch_round = [&](Chain &chain) {
+		const Dense &sub = chain.d;
+		cudaStream_t stream = chain.stream;
+		dim3 egrid; unsigned tgrid;
+		grids(sub, egrid, tgrid);
+		launch_stages<Tab>(sub, egrid, eblock, stream);
+		JBD_LAUNCH(jbd::error_kernel<Tab>, egrid, eblock, sub);
+		reset_count(chain);
+		JBD_LAUNCH(jbd::control_kernel<Tab>, tgrid, 256, sub);
+		++chain.rounds;
+		queue_poll(chain);
+	};
+	auto launch_finish = [&](Chain &chain) {
+		const Dense &sub = chain.d;
+		cudaStream_t stream = chain.stream;
+		dim3 egrid; unsigned tgrid;
+		grids(sub, egrid, tgrid);
+		JBD_LAUNCH(jbd::commit_kernel, egrid, eblock, sub);
+		JBD_LAUNCH(jbd::clear_accepted_kernel, tgrid, 256, sub);
+	};
+
+	for (int c = 0; c < n_chains; ++c) launch_start(chains[c]);
+	int alive = n_chains;
+	while (alive > 0 && err == cudaSuccess) {
+		for (int c = 0; c < n_chains && err == cudaSuccess; ++c) {
+			Chain &chain = chains[c];
+			if (!chain.alive) continue;
+			err = cudaEventSynchronize(chain.polled);       // (the other chain has its round queued meanwhile)
+			if (err != cudaSuccess) break;
+			if (*chain.host_flag == 0) {
+				if (chain.rounds > 0) launch_finish(chain);
+				chain.alive = false;
+				--alive;
+			} else if (chain.rounds > d.nmax + 8) {
+				err = cudaErrorUnknown;
+			} else {
+				launch_round(chain);
+			}
+		}
+	}
+	for (int c = 1; c < n_chains && err == cudaSuccess; ++c) {
+		// the caller's stream continues after the other chains have finished
+		err = cudaEventRecord(chains[c].polled, chains[c].stream);
+		if (err == cudaSuccess) err = cudaStreamWaitEvent(main_stream, chains[c].polled, 0);
+	}
+	int64_t rounds = 0;
+	for (int c = 0; c < n_chains; ++c) {
+		rounds = chains[c].rounds > rounds ? chains[c].rounds : rounds;
+		cudaEventDestroy(chains[c].polled);
+	}
 	if (x->rounds_out) *x->rounds_out = rounds;
-	err = cudaGetLastError();
+	if (err == cudaSuccess) err = cudaGetLastError();
 	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_integrate");
 }
 

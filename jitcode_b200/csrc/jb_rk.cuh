@@ -688,10 +688,8 @@ struct StiffnessWatch {
 __device__ __forceinline__ double ulp_above(double t)
 {
 	// positive normal t whose spacing is normal too: 2^(exponent − 52), straight from the bits
-#ifndef JB_SLOW_ULP
 	const unsigned biased = ((unsigned) __double2hiint(t) >> 20) & 0x7ffu;
 	if (t > 0.0 && biased > 52u && biased < 0x7feu) return __hiloint2double((int) ((biased - 52u) << 20), 0);
-#endif
 	return fabs(::nextafter(t, (double) INFINITY) - t);
 }
 

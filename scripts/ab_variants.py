@@ -1,7 +1,9 @@
 """A/B of compile-time variants of one workload's integrate kernel (development aid):
     python scripts/ab_variants.py roessler 262144 -- "" "-DJB_NO_STIFFNESS" …
     python scripts/ab_variants.py fhn_lyap 100000 threads=64,min_blocks=4 threads=128,min_blocks=3 …
-every argument after the batch size is one variant: extra nvcc flags, or key=value pairs handed to set_integrator."""
+every argument after the batch size is one variant: extra nvcc flags, or key=value pairs handed to set_integrator.
+Switches the kernels understand: -DJB_NO_STIFFNESS (Hairer's stiffness test compiled out), -DJB_LITERAL_COEF (Runge–Kutta
+coefficients as 64-bit literals instead of constant-bank operands), -DJB_REFILL_LANES=k (lanes that change trajectories together)."""
 import sys
 import time
 import torch

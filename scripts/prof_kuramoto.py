@@ -10,7 +10,8 @@ B = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 wl = bench.workload("kuramoto" if name == "dop853" else "kuramoto_dopri5", B)
 from jitcode_b200 import jitcode
 ODE = jitcode.from_sine_coupling(*wl["system"]["sine_coupling"])
-ODE.set_integrator(wl["integrator"], rtol=wl["rtol"], atol=wl["atol"])
+import os
+ODE.set_integrator(wl["integrator"], rtol=wl["rtol"], atol=wl["atol"], interleave=int(os.environ.get("INTERLEAVE", "0")))
 Y0 = torch.as_tensor(wl["Y0"]).cuda()
 for rep in range(2):
 	ODE.set_initial_value(Y0, 0.0)

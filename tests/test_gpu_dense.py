@@ -249,3 +249,25 @@ def test_dense_coupling_parameter_and_vector_atol(name):
 def handle_f_many(handle, strength, states):
 	handle.initialise(strength)
 	return np.stack([handle.f(0.3, state) for state in states])
+
+
+@pytest.mark.parametrize("chains", [1, 2, 3, 4])
+def test_dense_interleaved_sub_ensembles(chains):
+	"""large ensembles run as several sub-ensembles whose launch sequences overlap on separate streams; every
+	trajectory is integrated exactly once by exactly one of them: results and step counts do not depend on the number
+	of sub-ensembles (ragged ensemble size: the last one is shorter, and its tiles are partly empty)"""
+	n, B = 48, 4096 + 1000 + 37
+	system = W.kuramoto(n)
+	Wm = system["c"] / (n - 1) * system["A"].T.astype(float)
+	np.fill_diagonal(Wm, 0.0)
+	Y0 = torch.as_tensor(W.kuramoto_ensemble(B, n, seed=3)).cuda()
+	outcome = []
+	for k in (chains, 1):
+		ODE = jitcode.from_sine_coupling(Wm, system["omega"])
+		ODE.set_integrator("dopri5", rtol=1e-6, atol=1e-9, interleave=k)
+		ODE.set_initial_value(Y0, 0.0)
+		first = ODE.integrate(1.5)
+		second = ODE.integrate(4.0)
+		outcome.append((first.cpu().numpy(), second.cpu().numpy(), ODE.step_counts()))
+	assert np.array_equal(outcome[0][0], outcome[1][0]) and np.array_equal(outcome[0][1], outcome[1][1])
+	assert outcome[0][2] == outcome[1][2]
