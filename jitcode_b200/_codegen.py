@@ -126,6 +126,11 @@ def rhs_statements(f, helpers, control_pars, do_cse=False):
 	return lines
 
 
+def _vectorise_row_length(n):
+	from ._vectorise import row_length
+	return row_length(n)
+
+
 def _c_array(values, per_line=16):
 	values = list(values) or ["0"]
 	return ",\n\t".join(", ".join(values[k:k+per_line]) for k in range(0, len(values), per_line))
@@ -155,7 +160,7 @@ def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, met
 	tu = [str(int(v)) for v in tables.u] if warp else []
 	tu_type = "unsigned short" if (not tu or max(max(int(v) for v in tu), n) < 65536) else "unsigned int"
 	components = [str(int(c)) for c in (component_of if warp else range(n))]
-	n_row = (n + 2) // 2 * 2 if warp else n
+	n_row = _vectorise_row_length(n) if warp else n
 	if warp:
 		function = f"""	template <class VI, class VO>
 	static __device__ __forceinline__ void rhs_warp(const double t, const VI &y, VO &dy, const Par &par, const int lane, const void *jb_tables, double *jb_scratch)
@@ -196,7 +201,7 @@ struct Sys {{
 	static constexpr int NL = {n_lyap};     // tangent vectors
 	static constexpr int NT = {len(tangent_indices)};     // transversal tangent coordinates
 	static constexpr int TF_COUNT = {len(tf)}, TU_COUNT = {len(tu)};
-	static constexpr int NROW = {n_row};   // shared-memory row length (warp storage): position N holds 0
+	static constexpr int NROW = {n_row};   // shared-memory row length (warp storage): positions N … NROW-1 hold 0
 	static constexpr int TEAM_WARPS = {int(team_warps)};   // warps that share one trajectory (warp storage)
 	static constexpr int GROUP = {int(group)};   // lanes that share one trajectory (quad storage)
 	static constexpr int THREADS = {int(threads)};   // threads per block (= row stride of shared storage)

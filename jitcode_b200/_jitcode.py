@@ -91,7 +91,7 @@ def _warp_configuration(n, method, driver, table_bytes, kregs=None, threads=None
 	threads : threads per block (one persistent block per SM) = 32 · team_warps · trajectories per block."""
 	stages = _stage_rows(method, driver)
 	dense = 1 if driver == _codegen.JB_DRV_IVP_DENSE else 0
-	row_bytes = (n + 2) // 2 * 2 * 8
+	row_bytes = _vectorise.row_length(n) * 8
 	available = SHARED_MEMORY_PER_BLOCK - table_bytes - 8 * n - 64
 	last_stage = {_codegen.JB_DP5: 6, _codegen.JB_DOP853: 12, _codegen.JB_RK23: 3}[method]      # K[S]: its row doubles as the staging row while k <= S
 

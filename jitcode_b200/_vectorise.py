@@ -500,23 +500,51 @@ def _ell(values, start, size, width, pad):
 	return out
 
 
-def _spread_over_banks(entries, width):
+# Positions N … N + ZERO_WORDS − 1 of every shared-memory row hold 0.0: where a padded gather table has no entry, the
+# lane reads one of them.  One such word per bank, because the padding reads take part in the bank arithmetic like any
+# other: with a single zero word every real gather that fell into ITS bank cost an extra wavefront (ncu on the Rössler
+# network: 18 of the 32 gathers per evaluation, 6 % of all shared-memory wavefronts of the kernel).
+ZERO_WORDS = 16
+
+
+def row_length(n):
+	"""doubles per shared-memory row of warp storage: the n components and the zero words, even (16-byte rows)"""
+	return (n + ZERO_WORDS + 1) // 2 * 2
+
+
+def _spread_over_banks(entries, width, zero_slot=None, physical=lambda lane: lane):
 	"""The terms of a sum may run in any order, and padding may sit anywhere: every statement's gathers are dealt
 	to the `width` slots of its pass so that the lanes which execute a slot together (half a warp per 64-bit
-	shared-memory wavefront) hit as few equal banks with different words as possible.  entries[lane]: positions."""
+	shared-memory wavefront) hit as few equal banks with different words as possible.  entries[lane]: positions.
+	With zero_slot (the first of ZERO_WORDS zero words, one per bank) the padding entries are resolved as well: to the
+	zero word of a bank that no other word of the same slot and half-warp occupies.  physical: the lane of the warp
+	that executes entry `lane` (the blocked ring order rotates the lanes, see _print_loop)."""
 	load = {}       # (slot, half-warp, bank) → words already read there
 	placed = []
 	for lane, wanted in enumerate(entries):
 		row, free = [None] * width, list(range(width))
 		for where in wanted:
 			def cost(k):
-				others = load.get((k, (lane % 32) // 16, where % 16), ())
+				others = load.get((k, (physical(lane) % 32) // 16, where % 16), ())
 				return 0 if where in others else len(others)
 			best = min(free, key=lambda k: (cost(k), k))
 			free.remove(best)
 			row[best] = where
-			load.setdefault((best, (lane % 32) // 16, where % 16), set()).add(where)
+			load.setdefault((best, (physical(lane) % 32) // 16, where % 16), set()).add(where)
 		placed.append(row)
+	if zero_slot is not None:
+		for lane, row in enumerate(placed):
+			half = (physical(lane) % 32) // 16
+			for k, where in enumerate(row):
+				if where is None:
+					# the emptiest bank of this slot and half-warp (a zero word already read there is the same word: no cost)
+					def crowd(bank):
+						zero = zero_slot + (bank - zero_slot) % 16
+						return len(load.get((k, half, bank), set()) - {zero})
+					bank = min(range(16), key=lambda b: (crowd(b), b))
+					zero = zero_slot + (bank - zero_slot) % 16
+					row[k] = zero
+					load.setdefault((k, half, bank), set()).add(zero)
 	return placed
 
 
@@ -607,6 +635,22 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 
 		# one table for both kinds where the offsets leave a bit for the sign: padded to the longest statement of a pass
 		# once, not once per kind
+		# Rotated lanes (blocked order): lane p of the warp does the work of ring block (p + R) mod team.  A window word
+		# at relative block c is then read by lanes 0 … 15 — one 64-bit wavefront — at blocks R+c … R+15+c: consecutive
+		# words, no wrap-around inside the wavefront, as long as −c ≤ R ≤ team − 16 − c for every c.  Unrotated, the
+		# wrap put words 16 apart (= the same bank) into one wavefront for every negative c (ncu: 10 of the 26 window
+		# loads of the Rössler network took 3 wavefronts instead of 2).
+		rotation = 0
+		if diagonals and blocked:
+			window_carries = [divmod(q + (d if d <= ring // 2 else d - ring), blocked)[0] for q in range(blocked) for d in diagonals]
+			rotation = max(0, min(-min(window_carries), team - 16 - max(window_carries)))
+			if rotation < -min(window_carries):
+				rotation = 0        # the ring is too short for a wavefront without wrap-around either way
+		who = "jb_lane" if blocked else "lane"
+		physical = (lambda lane: (lane - rotation) % team) if blocked else (lambda lane: lane)
+		if blocked and prologue is not None and not any("const int jb_lane" in line for line in prologue):
+			shifted = f"lane + {rotation}"
+			prologue.insert(0, f"\tconst int jb_lane = {f'{shifted} >= {team} ? {shifted} - {team} : {shifted}' if rotation else 'lane'};")
 		signed_pairs = bool(missing) and 8 * zero_slot < 32768 and SIGNED_PAIRS
 		negative = [set(terms) for terms in missing] if signed_pairs else [set()] * size
 		if signed_pairs:
@@ -622,7 +666,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 				pass_width += pass_width % 2
 				bases.append(len(words) // 2)      # in 32-bit words
 				widths.append(pass_width // 2)
-				placed = _spread_over_banks([lists[m] for m in members], pass_width) if SPREAD_OVER_BANKS else [list(lists[m]) + [None] * (pass_width - len(lists[m])) for m in members]
+				placed = _spread_over_banks([lists[m] for m in members], pass_width, zero_slot, physical) if SPREAD_OVER_BANKS else [list(lists[m]) + [None] * (pass_width - len(lists[m])) for m in members]
 				for kp in range(pass_width // 2):
 					for lane in range(team):
 						for k in (2*kp, 2*kp + 1):
@@ -634,7 +678,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 			offset, bases, widths = table
 			lines.append("\t{")
 			lines.append(f"\t\tconstexpr int pass_base[{n_pass}] = {{ {', '.join(map(str, bases))} }}, pass_pairs[{n_pass}] = {{ {', '.join(map(str, widths))} }};")
-			lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
+			lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + {who};")
 			lines.append("#pragma unroll")
 			lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
 			lines.append(f"\t\t\tconst unsigned pair = pairs[k * {team}];")
@@ -677,13 +721,13 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 					for k, d in enumerate(signed):
 						users.setdefault(divmod(q + d, blocked), []).append((q, k))
 				for carry in sorted({carry for carry, _ in users}):
-					shifted = f"lane {'-' if carry < 0 else '+'} {abs(carry)}"
+					shifted = f"jb_lane {'-' if carry < 0 else '+'} {abs(carry)}"
 					wrapped = f"{shifted} < 0 ? {shifted} + {team} : {shifted}" if carry < 0 else f"{shifted} >= {team} ? {shifted} - {team} : {shifted}"
-					prologue.append(f"\tconst int {name}_l{tag(carry)} = {wrapped if carry else 'lane'};")
+					prologue.append(f"\tconst int {name}_l{tag(carry)} = {wrapped if carry else 'jb_lane'};")
 				for q in range(blocked):
 					prologue.append(f"\tdouble {name}_s{q}a = 0.0, {name}_s{q}b = 0.0, {name}_s{q}c = 0.0, {name}_s{q}d = 0.0;")
 					if not all_present:
-						prologue.append(f"\tconst unsigned {name}_present{q} = JB_TU[{low} + lane + {q * team}] | ((unsigned) JB_TU[{high} + lane + {q * team}] << 16);")
+						prologue.append(f"\tconst unsigned {name}_present{q} = JB_TU[{low} + jb_lane + {q * team}] | ((unsigned) JB_TU[{high} + jb_lane + {q * team}] << 16);")
 				shared_by_all = [key for key, wanted in users.items() if all_present and blocked > 1 and len(wanted) == blocked]
 				if shared_by_all:
 					prologue.append(f"\tdouble {name}_core_a = 0.0, {name}_core_b = 0.0, {name}_core_c = 0.0, {name}_core_d = 0.0;")
@@ -843,11 +887,11 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 			# passes unrolled: every pass knows its own trip counts at compile time
 			header.append("#pragma unroll")
 			header.append(f"for (int pass = 0; pass < {n_pass}; ++pass) {{")
-			header.append(f"\tconst int m = lane + {lanes} * pass;")
+			header.append(f"\tconst int m = {'jb_lane' if blocked else 'lane'} + {lanes} * pass;")
 			if not blocked:
 				header.append(f"\tif (m >= {size}) break;")
 		else:
-			header.append(f"for (int m = lane, pass = 0; m < {size}; m += {lanes}, ++pass) {{")
+			header.append(f"for (int m = {'jb_lane' if blocked else 'lane'}, pass = 0; m < {size}; m += {lanes}, ++pass) {{")
 			header.append("\t(void) pass;")
 		body, lines = lines, []
 		for g, group in members:
@@ -863,6 +907,8 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 		lines.append("}")
 		if blocked:
 			lines.append("}")
+		if blocked and not any("const int jb_lane" in line for line in prologue):
+			prologue.insert(0, "\tconst int jb_lane = lane;")
 		lines = body + (header[:1] + prologue + header[1:] if blocked else header) + lines
 	helper_declarations = [f"double {symbol.name};" for symbol, _ in plan.helpers]
 	component_of = [None] * plan.n

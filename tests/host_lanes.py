@@ -10,6 +10,8 @@ import subprocess
 
 import numpy as np
 
+from jitcode_b200 import _vectorise
+
 SOURCE = r"""
 #include <math.h>
 #include <vector>
@@ -77,7 +79,7 @@ def evaluate_printed(lines, tables, component_of, n_par, t, state, pars, lanes, 
 	library = workdir / f"lanes_{tag}.so"
 	subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-o", str(library), str(path)], check=True, capture_output=True)
 	lib = ctypes.CDLL(str(library))
-	row = np.zeros((n + 2) // 2 * 2)
+	row = np.zeros(_vectorise.row_length(n))
 	row[:n] = np.asarray(state, dtype=float)[component_of]
 	out = np.full_like(row, np.nan)
 	parameters = np.asarray(list(pars) + [0.0], dtype=float)
