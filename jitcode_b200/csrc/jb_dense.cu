@@ -292,6 +292,7 @@ struct Dense {
 	int64_t nmax;
 	double safety, facc1, facc2, beta, expo1;
 	int reject_by_dfactor;      // dop853: shrink by exactly dfactor on a rejection, like SciPy 1.18.1's compiled code
+	int driver;                 // enum jb_driver
 	double *t, *Y, *work, *ctrl;
 	int32_t *status;
 	int64_t *n_accepted, *n_rejected;
@@ -363,11 +364,11 @@ __device__ __forceinline__ double finish_rhs(const Dense &d, int i, int64_t b, i
 }
 
 // after the GEMM of f(t, Y): K[0] = f; HINIT sums dnf = Σ(f/sk)², dny = Σ(y/sk)²
-__global__ void __launch_bounds__(256) start_kernel(const Dense d)
+__global__ void __launch_bounds__(256) start_kernel(const Dense d, int need_flag)
 {
 	const int64_t b = d.b0 + (int64_t) blockIdx.x * 32 + threadIdx.x;
 	double dnf = 0.0, dny = 0.0;
-	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
+	const bool active = b < d.B && (flags_of(d, b) & need_flag);
 	if (active)
 		for_rows(d, [&](int i, int64_t, int64_t at) {
 			const double f0 = finish_rhs<0>(d, i, b, at);
@@ -381,13 +382,25 @@ __global__ void __launch_bounds__(256) start_kernel(const Dense d)
 }
 
 // HINIT: first guess h0 and the Euler probe Z = Y + h0 K[0], XS = sincos(Z)
-__global__ void __launch_bounds__(256) probe_kernel(const Dense d)
+// (solve_ivp drivers: select_initial_step's h0 from the root-mean-square norms, scipy _ivp/common.py:108-117)
+__device__ __forceinline__ double scipy_h0(const Dense &d, int64_t b)
+{
+	const double d0 = sqrt(d.ctrl[C_DNY * d.ld + b] / d.n), d1 = sqrt(d.ctrl[C_DNF * d.ld + b] / d.n);
+	return (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+}
+
+__global__ void __launch_bounds__(256) probe_kernel(const Dense d, int need_flag)
 {
 	for_rows(d, [&](int i, int64_t b, int64_t at) {
-		if (!(flags_of(d, b) & F_ACTIVE)) return;
+		if (!(flags_of(d, b) & need_flag)) return;
 		const double dnf = d.ctrl[C_DNF * d.ld + b], dny = d.ctrl[C_DNY * d.ld + b];
-		double h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
-		h = fmin(h, d.ctrl[C_HMAX * d.ld + b]);
+		double h;
+		if (d.driver == JB_DRV_ODE) {
+			h = (dnf <= 1e-10 || dny <= 1e-10) ? 1e-6 : sqrt(dny / dnf) * 0.01;
+			h = fmin(h, d.ctrl[C_HMAX * d.ld + b]);
+		} else {
+			h = scipy_h0(d, b);
+		}
 		const double z = fma(h, vec(d, W_K0)[at], d.Y[at]);
 		vec(d, W_Z)[at] = z;
 		sincos(z, &xs_sin(d, i, b), &xs_cos(d, i, b));
@@ -395,11 +408,11 @@ __global__ void __launch_bounds__(256) probe_kernel(const Dense d)
 }
 
 // HINIT: der2 = Σ((f1 − f0)/sk)²
-__global__ void __launch_bounds__(256) probe_finish_kernel(const Dense d)
+__global__ void __launch_bounds__(256) probe_finish_kernel(const Dense d, int need_flag)
 {
 	const int64_t b = d.b0 + (int64_t) blockIdx.x * 32 + threadIdx.x;
 	double der2 = 0.0;
-	const bool active = b < d.B && (flags_of(d, b) & F_ACTIVE);
+	const bool active = b < d.B && (flags_of(d, b) & need_flag);
 	if (active)
 		for_rows(d, [&](int i, int64_t, int64_t at) {
 			const double f1 = finish_rhs<1>(d, i, b, at);
@@ -500,7 +513,9 @@ __global__ void __launch_bounds__(256) stage_kernel(const Dense d)
 		double k[S + 1];
 		double y = d.Y[at];
 		if constexpr (ROW == 1) {
-			if (flags & F_ACCEPTED) {
+			// (solve_ivp with dense output: a trajectory that has arrived keeps y_old, y_new and all stages of its last
+			// step until commit_ivp_kernel has turned them into the interpolant)
+			if ((flags & F_ACCEPTED) && (d.driver != JB_DRV_IVP_DENSE || (flags & F_ACTIVE))) {
 				y = vec(d, W_Z)[at];
 				d.Y[at] = y;
 				k[0] = vec(d, W_K0 + S)[at];
@@ -805,7 +820,7 @@ int jb_dense_eval_f(const jb_dense_args *x, double *dY)
 	JBD_LAUNCH(jbd::setup_kernel, (unsigned) ((d.B + 255) / 256), 256, d);
 	JBD_LAUNCH(jbd::sincos_kernel<0>, egrid, eblock, d, jbd::F_ACTIVE);
 	jbd::gemm(d, stream);
-	JBD_LAUNCH(jbd::start_kernel, egrid, eblock, d);
+	JBD_LAUNCH(jbd::start_kernel, egrid, eblock, d, (int) jbd::F_ACTIVE);
 	cudaError_t err = cudaMemcpyAsync(dY, jbd::vec(d, jbd::W_K0), sizeof(double) * d.n * d.ld, cudaMemcpyDeviceToDevice, stream);
 	if (err == cudaSuccess) err = cudaGetLastError();
 	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_eval_f");
@@ -844,12 +859,108 @@ static cudaStream_t side_stream(int which)
 	return stream;
 }
 
-// advance every trajectory to x->T (Hairer's DOPRI5 / DOP853, fresh start, lands exactly on T).
+// One of the interleaved sub-ensembles: its column range, stream, grids, and the host's view of its progress.
+struct Chain {
+	Dense d;
+	cudaStream_t stream;
+	cudaEvent_t polled;
+	int32_t *host_flag;
+	bool alive;
+	int64_t rounds;
+	dim3 egrid;             // element-wise kernels: 32 trajectories × 64 components per block
+	unsigned tgrid;         // per-trajectory kernels: 256 trajectories per block
+	void reset_count() const { cudaMemsetAsync(d.active_count, 0, sizeof(int32_t), stream); }
+};
+static const dim3 eblock(32, 8);
+
 // Large ensembles are integrated as SEVERAL sub-ensembles whose launch sequences are interleaved on as many streams: the
 // step of one is a chain of dependent kernels — element-wise stage kernel (memory-bound), GEMM (tensor-bound), stage
 // kernel, … — so with a second, independent chain in flight the stage kernels of one run under the GEMM of the other
 // and the partly filled last wave of a GEMM's blocks is topped up.  The host polls one chain while the other has a
-// round queued.
+// round queued.  start / round / finish queue the kernels of one chain (they end with the chain's counter of unfinished
+// trajectories up to date); this function does the polling, the forking and joining of the streams.
+template <class Start, class Round, class Finish>
+static int run_chains(const jb_dense_args *x, const Dense &d, Start &&launch_start, Round &&launch_round, Finish &&launch_finish)
+{
+	// ---- the sub-ensembles: equal parts of ≥ 1024 trajectories each (bits 9-11 of method_flags: that many chains; 0: as
+	// many as fit, at most four — measured on config 5: 1: 234.7 ms, 2: 224.1, 3: 216.9, 4: 215.9 per ten samples)
+	Chain chains[MAX_CHAINS];
+	cudaStream_t main_stream = (cudaStream_t) x->stream;
+	const int wanted = (x->method_flags >> 9) & 7;
+	int n_chains = wanted ? wanted : MAX_CHAINS;
+	if (n_chains > MAX_CHAINS) n_chains = MAX_CHAINS;
+	while (n_chains > 1 && d.B < 1024 * (int64_t) n_chains) --n_chains;
+	for (int c = 1; c < n_chains; ++c)
+		if (!side_stream(c)) n_chains = 1;
+	const int64_t part = n_chains > 1 ? (d.B / n_chains + 63) / 64 * 64 : d.ld;
+	for (int c = 0; c < n_chains; ++c) {
+		Chain &chain = chains[c];
+		chain.d = d;
+		chain.d.b0 = c * part;
+		chain.d.b1 = c == n_chains - 1 ? d.ld : (c + 1) * part;
+		if (chain.d.B > chain.d.b1) chain.d.B = chain.d.b1;       // its kernels must not touch the next chain's trajectories
+		chain.d.active_count = x->scratch + x->ld / 32 + 1 + c;
+		chain.stream = c == 0 ? main_stream : side_stream(c);
+		chain.host_flag = x->host_flag + c;
+		chain.alive = true;
+		chain.rounds = 0;
+		const int64_t width = chain.d.b1 - chain.d.b0;
+		chain.egrid = dim3((unsigned) (width / 32), (unsigned) ((d.n + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK));
+		chain.tgrid = (unsigned) ((width + 255) / 256);
+		if (cudaEventCreateWithFlags(&chain.polled, cudaEventDisableTiming) != cudaSuccess)
+			return fail((int) cudaGetLastError(), "jb_dense_integrate: creating an event");
+	}
+	cudaError_t err = cudaSuccess;
+	for (int c = 1; c < n_chains && err == cudaSuccess; ++c) {
+		// the extra streams join the caller's: they start after what the caller has queued so far
+		err = cudaEventRecord(chains[c].polled, main_stream);
+		if (err == cudaSuccess) err = cudaStreamWaitEvent(chains[c].stream, chains[c].polled, 0);
+	}
+	// queue the copy of the chain's counter of unfinished trajectories and mark the point to wait for
+	auto queue_poll = [&](Chain &chain) {
+		cudaMemcpyAsync(chain.host_flag, chain.d.active_count, sizeof(int32_t), cudaMemcpyDeviceToHost, chain.stream);
+		cudaEventRecord(chain.polled, chain.stream);
+	};
+	for (int c = 0; c < n_chains; ++c) {
+		launch_start(chains[c]);
+		queue_poll(chains[c]);
+	}
+	int alive = n_chains;
+	while (alive > 0 && err == cudaSuccess) {
+		for (int c = 0; c < n_chains && err == cudaSuccess; ++c) {
+			Chain &chain = chains[c];
+			if (!chain.alive) continue;
+			err = cudaEventSynchronize(chain.polled);       // (the other chains have their rounds queued meanwhile)
+			if (err != cudaSuccess) break;
+			if (*chain.host_flag == 0) {
+				launch_finish(chain);
+				chain.alive = false;
+				--alive;
+			} else if (chain.rounds > d.nmax + 8) {
+				err = cudaErrorUnknown;
+			} else {
+				launch_round(chain);
+				++chain.rounds;
+				queue_poll(chain);
+			}
+		}
+	}
+	for (int c = 1; c < n_chains && err == cudaSuccess; ++c) {
+		// the caller's stream continues after the other chains have finished
+		err = cudaEventRecord(chains[c].polled, chains[c].stream);
+		if (err == cudaSuccess) err = cudaStreamWaitEvent(main_stream, chains[c].polled, 0);
+	}
+	int64_t rounds = 0;
+	for (int c = 0; c < n_chains; ++c) {
+		rounds = chains[c].rounds > rounds ? chains[c].rounds : rounds;
+		cudaEventDestroy(chains[c].polled);
+	}
+	if (x->rounds_out) *x->rounds_out = rounds;
+	if (err == cudaSuccess) err = cudaGetLastError();
+	return err == cudaSuccess ? 0 : fail((int) err, "jb_dense_integrate");
+}
+
+// advance every trajectory to x->T (Hairer's DOPRI5 / DOP853, fresh start, lands exactly on T)
 template <class Tab>
 static int integrate(const jb_dense_args *x)
 {
@@ -880,130 +991,41 @@ static int integrate(const jb_dense_args *x)
 	d.tile_skip = x->scratch;
 	const int have_probe = !(d.first_step > 0.0);
 
-	// ---- the sub-ensembles: equal parts of ≥ 1024 trajectories each (bits 9-11 of method_flags: that many chains; 0: as many as fit, at most four — measured on config 5: 1: 234.7 ms, 2: 224.1, 3: 212.3, 4: 215.9 per ten samples)
-	struct Chain {
-		Dense d;
-		cudaStream_t stream;
-		cudaEvent_t polled;
-		int32_t *host_flag;
-		bool alive;
-		int64_t rounds;
-	} chains[MAX_CHAINS];
-	cudaStream_t main_stream = (cudaStream_t) x->stream;
-	const int wanted = (x->method_flags >> 9) & 7;
-	int n_chains = wanted ? wanted : MAX_CHAINS;
-	if (n_chains > MAX_CHAINS) n_chains = MAX_CHAINS;
-	while (n_chains > 1 && d.B < 1024 * (int64_t) n_chains) --n_chains;
-	for (int c = 1; c < n_chains; ++c)
-		if (!side_stream(c)) n_chains = 1;
-	const int64_t part = n_chains > 1 ? (d.B / n_chains + 63) / 64 * 64 : d.ld;
-	for (int c = 0; c < n_chains; ++c) {
-		Chain &chain = chains[c];
-		chain.d = d;
-		chain.d.b0 = c * part;
-		chain.d.b1 = c == n_chains - 1 ? d.ld : (c + 1) * part;
-		if (chain.d.B > chain.d.b1) chain.d.B = chain.d.b1;       // its kernels must not touch the next chain's trajectories
-		chain.d.active_count = x->scratch + x->ld / 32 + 1 + c;
-		chain.stream = c == 0 ? main_stream : side_stream(c);
-		chain.host_flag = x->host_flag + c;
-		chain.alive = true;
-		chain.rounds = 0;
-		if (cudaEventCreateWithFlags(&chain.polled, cudaEventDisableTiming) != cudaSuccess)
-			return jbd::fail((int) cudaGetLastError(), "jb_dense_integrate: creating an event");
-	}
-	cudaError_t err = cudaSuccess;
-	for (int c = 1; c < n_chains && err == cudaSuccess; ++c) {
-		// the extra streams join the caller's: they start after what the caller has queued so far
-		err = cudaEventRecord(chains[c].polled, main_stream);
-		if (err == cudaSuccess) err = cudaStreamWaitEvent(chains[c].stream, chains[c].polled, 0);
-	}
-
-	const dim3 eblock(32, 8);
-	auto grids = [&](const Dense &sub, dim3 &egrid, unsigned &tgrid) {
-		const int64_t width = sub.b1 - sub.b0;
-		egrid = dim3((unsigned) (width / 32), (unsigned) ((sub.n + jbd::ROWS_PER_BLOCK - 1) / jbd::ROWS_PER_BLOCK));
-		tgrid = (unsigned) ((width + 255) / 256);
-	};
-	// queue the copy of the chain's counter of unfinished trajectories and mark the point to wait for
-	auto queue_poll = [&](Chain &chain) {
-		cudaMemcpyAsync(chain.host_flag, chain.d.active_count, sizeof(int32_t), cudaMemcpyDeviceToHost, chain.stream);
-		cudaEventRecord(chain.polled, chain.stream);
-	};
-	auto reset_count = [&](Chain &chain) { cudaMemsetAsync(chain.d.active_count, 0, sizeof(int32_t), chain.stream); };
-	// ---- fresh start: f(t, Y), HINIT
-	auto launch_start = [&](Chain &chain) {
-		const Dense &sub = chain.d;
-		cudaStream_t stream = chain.stream;
-		dim3 egrid; unsigned tgrid;
-		grids(sub, egrid, tgrid);
-		reset_count(chain);
-		JBD_LAUNCH(jbd::setup_kernel, tgrid, 256, sub);
-		JBD_LAUNCH(jbd::sincos_kernel<0>, egrid, eblock, sub, jbd::F_ACTIVE);
-		jbd::gemm(sub, stream);
-		JBD_LAUNCH(jbd::start_kernel, egrid, eblock, sub);
-		if (have_probe) {
-			JBD_LAUNCH(jbd::probe_kernel, egrid, eblock, sub);
+	return run_chains(x, d,
+		// ---- fresh start: f(t, Y), HINIT
+		[&](Chain &chain) {
+			const Dense &sub = chain.d;
+			cudaStream_t stream = chain.stream;
+			chain.reset_count();
+			JBD_LAUNCH(jbd::setup_kernel, chain.tgrid, 256, sub);
+			JBD_LAUNCH(jbd::sincos_kernel<0>, chain.egrid, eblock, sub, (int) jbd::F_ACTIVE);
 			jbd::gemm(sub, stream);
-			JBD_LAUNCH(jbd::probe_finish_kernel, egrid, eblock, sub);
-		}
-		reset_count(chain);
-		JBD_LAUNCH(jbd::first_step_kernel<Tab>, tgrid, 256, sub, have_probe);
-		queue_poll(chain);
-	};
-	// ---- a round: one step attempt of every unfinished trajectory of the chain
-	auto launch_round = [&](Chain &chain) {
-		const Dense &sub = chain.d;
-		cudaStream_t stream = chain.stream;
-		dim3 egrid; unsigned tgrid;
-		grids(sub, egrid, tgrid);
-		launch_stages<Tab>(sub, egrid, eblock, stream);
-		JBD_LAUNCH(jbd::error_kernel<Tab>, egrid, eblock, sub);
-		reset_count(chain);
-		JBD_LAUNCH(jbd::control_kernel<Tab>, tgrid, 256, sub);
-		++chain.rounds;
-		queue_poll(chain);
-	};
-	auto launch_finish = [&](Chain &chain) {
-		const Dense &sub = chain.d;
-		cudaStream_t stream = chain.stream;
-		dim3 egrid; unsigned tgrid;
-		grids(sub, egrid, tgrid);
-		JBD_LAUNCH(jbd::commit_kernel, egrid, eblock, sub);
-		JBD_LAUNCH(jbd::clear_accepted_kernel, tgrid, 256, sub);
-	};
-
-	for (int c = 0; c < n_chains; ++c) launch_start(chains[c]);
-	int alive = n_chains;
-	while (alive > 0 && err == cudaSuccess) {
-		for (int c = 0; c < n_chains && err == cudaSuccess; ++c) {
-			Chain &chain = chains[c];
-			if (!chain.alive) continue;
-			err = cudaEventSynchronize(chain.polled);       // (the other chain has its round queued meanwhile)
-			if (err != cudaSuccess) break;
-			if (*chain.host_flag == 0) {
-				if (chain.rounds > 0) launch_finish(chain);
-				chain.alive = false;
-				--alive;
-			} else if (chain.rounds > d.nmax + 8) {
-				err = cudaErrorUnknown;
-			} else {
-				launch_round(chain);
+			JBD_LAUNCH(jbd::start_kernel, chain.egrid, eblock, sub, (int) jbd::F_ACTIVE);
+			if (have_probe) {
+				JBD_LAUNCH(jbd::probe_kernel, chain.egrid, eblock, sub, (int) jbd::F_ACTIVE);
+				jbd::gemm(sub, stream);
+				JBD_LAUNCH(jbd::probe_finish_kernel, chain.egrid, eblock, sub, (int) jbd::F_ACTIVE);
 			}
-		}
-	}
-	for (int c = 1; c < n_chains && err == cudaSuccess; ++c) {
-		// the caller's stream continues after the other chains have finished
-		err = cudaEventRecord(chains[c].polled, chains[c].stream);
-		if (err == cudaSuccess) err = cudaStreamWaitEvent(main_stream, chains[c].polled, 0);
-	}
-	int64_t rounds = 0;
-	for (int c = 0; c < n_chains; ++c) {
-		rounds = chains[c].rounds > rounds ? chains[c].rounds : rounds;
-		cudaEventDestroy(chains[c].polled);
-	}
-	if (x->rounds_out) *x->rounds_out = rounds;
-	if (err == cudaSuccess) err = cudaGetLastError();
-	return err == cudaSuccess ? 0 : jbd::fail((int) err, "jb_dense_integrate");
+			chain.reset_count();
+			JBD_LAUNCH(jbd::first_step_kernel<Tab>, chain.tgrid, 256, sub, have_probe);
+		},
+		// ---- a round: one step attempt of every unfinished trajectory of the chain
+		[&](Chain &chain) {
+			const Dense &sub = chain.d;
+			cudaStream_t stream = chain.stream;
+			launch_stages<Tab>(sub, chain.egrid, eblock, stream);
+			JBD_LAUNCH(jbd::error_kernel<Tab>, chain.egrid, eblock, sub);
+			chain.reset_count();
+			JBD_LAUNCH(jbd::control_kernel<Tab>, chain.tgrid, 256, sub);
+		},
+		// ---- the accepted trajectories of the last round still have y_new in Z
+		[&](Chain &chain) {
+			const Dense &sub = chain.d;
+			cudaStream_t stream = chain.stream;
+			if (chain.rounds == 0) return;
+			JBD_LAUNCH(jbd::commit_kernel, chain.egrid, eblock, sub);
+			JBD_LAUNCH(jbd::clear_accepted_kernel, chain.tgrid, 256, sub);
+		});
 }
 
 }  // namespace jbd
