@@ -158,8 +158,10 @@ int64_t jb_launch_count(void);
  *     dy_i/dt = omega_i + c * sum_j W_ij sin(y_j - y_i)          (c: optional per-trajectory control parameter)
  * — what the reference writes out as n*deg sine terms (examples/kuramoto_network.py:19-26) — as one FP64
  * tensor-core GEMM per right-hand-side evaluation for the whole ensemble.  Replaces, for such systems, the same
- * reference entry points as jb_eval_f / jb_integrate with driver JB_DRV_ODE ("dopri5" / "dop853",
- * ODE_wrapper.integrate, integrator_tools.py:134-144).  Layout: plain structure of arrays, X[i*ld + b], ld a multiple of 64.
+ * reference entry points as jb_eval_f / jb_integrate: driver JB_DRV_ODE ("dopri5" / "dop853", ODE_wrapper.integrate,
+ * integrator_tools.py:134-144) and SciPy's solve_ivp stepper with the same pairs — JB_DRV_IVP_LAND ("RK45" / "DOP853"
+ * without interpolation, IVP_wrapper_no_interpolation.integrate :110-128) and JB_DRV_IVP_DENSE ("RK45" with dense
+ * output, IVP_wrapper.integrate :98-105).  Layout: plain structure of arrays, X[i*ld + b], ld a multiple of 64.
  */
 typedef struct jb_dense_args {
 	uint32_t struct_size;      /* sizeof(jb_dense_args), checked */
@@ -182,13 +184,14 @@ typedef struct jb_dense_args {
 	int32_t *scratch;          /* [ld/32 + 8] device scratch */
 	int32_t *host_flag;        /* four int32 in (pinned) host memory: the host polls the number of unfinished trajectories (of each of the interleaved sub-ensembles) */
 	int32_t  rounds_per_check; /* lock-step rounds between two polls; 0 = default (1: a round takes milliseconds, a poll microseconds) */
-	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1); bits 9-11: number of interleaved sub-ensembles (0: default, up to four of >= 1024 trajectories each; 1: none) */
+	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1); bits 9-11: number of interleaved sub-ensembles (0: default, up to four of >= 1024 trajectories each; 1: none); bits 12-13: the driver, enum jb_driver — with the solve_ivp drivers work and ctrl persist between calls, and JB_DRV_IVP_DENSE exists for JB_DP5 only; bit 14: a new state was set, steppers have to be created */
 	int64_t *rounds_out;       /* host: number of lock-step rounds of this call, or NULL */
 	void    *stream;
 } jb_dense_args;
 
 int         jb_dense_work_vectors(void);
 int         jb_dense_control_scalars(void);
+int         jb_dense_result_vector(void);   /* solve_ivp with dense output: the work vector that holds the sample at T ([n][ld], like Y) */
 const char *jb_dense_last_error(void);
 int64_t     jb_dense_launch_count(void);
 int jb_dense_integrate(const jb_dense_args *args);

@@ -92,7 +92,7 @@ class DenseArgs(ctypes.Structure):
 		("stream", ctypes.c_void_p),
 	]
 
-DENSE_EXPORTS = ("jb_dense_work_vectors", "jb_dense_control_scalars", "jb_dense_last_error", "jb_dense_launch_count",
+DENSE_EXPORTS = ("jb_dense_work_vectors", "jb_dense_control_scalars", "jb_dense_result_vector", "jb_dense_last_error", "jb_dense_launch_count",
 		"jb_dense_integrate", "jb_dense_eval_f", "jb_dense_gemm", "jb_dense_gemm_shape", "jb_dense_transpose")
 
 _library = None
@@ -142,9 +142,13 @@ class DenseModule:
 
 
 class CudaDenseSineIntegrator:
-	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5") or DOP853 ("dop853")."""
+	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5") or DOP853 ("dop853")
+	(driver 0: every `integrate` call is a fresh start that lands on the target time, ODE_wrapper), or SciPy's solve_ivp
+	stepper with the same pairs ("RK45", "DOP853"): persistent between calls, driver 1 = the sample is the dense output
+	of the step that passed the target time (IVP_wrapper; the 5(4) pair only), driver 2 = the last step is clipped to the
+	target time (IVP_wrapper_no_interpolation)."""
 
-	def __init__(self, W, omega, *, method=0, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
+	def __init__(self, W, omega, *, method=0, driver=0, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
 			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=0, coupling_parameter=False,
 			interleave=0):
 		self.device = require_cuda(device)
@@ -171,7 +175,11 @@ class CudaDenseSineIntegrator:
 		self.rounds_per_check = int(rounds_per_check)
 		# interleave: number of sub-ensembles whose launch sequences overlap on separate streams (0: default — up to
 		# four of ≥ 1024 trajectories each; 1: none; csrc/jb_dense.cu, integrate)
-		self.method_flags = int(method) | (256 if verbatim_dop853_reject else 0) | ((int(interleave) & 7) << 9)
+		self.driver = int(driver)
+		if self.driver == 1 and int(method) != 0:
+			raise NotImplementedError("The dense engine has dense output for RK45 only; use DOP853 with interpolate=False.")
+		self.method_flags = int(method) | (256 if verbatim_dop853_reject else 0) | ((int(interleave) & 7) << 9) | (self.driver << 12)
+		self._fresh = True      # the solve_ivp stepper has to be created by the next call (a new state was set)
 		self.B = None
 		self.time = None
 		self._rows = None
@@ -215,7 +223,7 @@ class CudaDenseSineIntegrator:
 		a.status, a.n_accepted, a.n_rejected = self.status.data_ptr(), self.n_accepted.data_ptr(), self.n_rejected.data_ptr()
 		a.scratch, a.host_flag = self.scratch.data_ptr(), self.host_flag.data_ptr()
 		a.rounds_per_check = self.rounds_per_check
-		a.method_flags = self.method_flags
+		a.method_flags = self.method_flags | ((1 << 14) if (self.driver and self._fresh) else 0)
 		a.rounds_out = self.rounds_host.ctypes.data
 		a.stream = self.stream
 		return a
@@ -295,6 +303,8 @@ class CudaDenseSineIntegrator:
 		self.tt.fill_(float(time))
 		self.time = float(time)
 		self.status.zero_()
+		self.ctrl.zero_()       # (the persistent stepper of the solve_ivp drivers lives there)
+		self._fresh = True
 		self._rows = rows
 		if self._pars is not None:
 			self._upload_parameters()
@@ -331,7 +341,13 @@ class CudaDenseSineIntegrator:
 			self.kernel_events.append((start, end))
 		self.rounds += int(self.rounds_host[0])
 		self.time = T
-		self._rows = self._rows_from(self.Y, rows)
+		self._fresh = False
+		if self.driver == 1:      # dense output: the sample is not the solver's state
+			width = self.n * self.ld
+			result = self.lib.jb_dense_result_vector()
+			self._rows = self._rows_from(self.work[result * width:(result + 1) * width], rows)
+		else:
+			self._rows = self._rows_from(self.Y, rows)
 
 	def _check_failures(self):
 		failed = (self.status[:self.B] != 0).nonzero().flatten()
@@ -345,9 +361,10 @@ class CudaDenseSineIntegrator:
 		T = float(T)
 		if self.B is None:
 			raise RuntimeError("You must call set_initial_value first.")
-		if T < self.time:
+		# (IVP_wrapper.integrate has no such check: an earlier time is read off the last step's interpolant, integrator_tools.py:98-105)
+		if T < self.time and self.driver != 1:
 			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
-		if T == self.time:
+		if T == self.time and (self.driver != 1 or not self._fresh):
 			return self._export(self._rows, out)
 		self._advance(T)
 		self._check_failures()
@@ -359,12 +376,12 @@ class CudaDenseSineIntegrator:
 		times = [float(T) for T in times]
 		if self.B is None:
 			raise RuntimeError("You must call set_initial_value first.")
-		if any(later < earlier for earlier, later in zip([self.time] + times, times)):
+		if any(later < earlier for earlier, later in zip(([] if self.driver == 1 else [self.time]) + times, times)):
 			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
 		out = torch.empty((len(times) if record_states else 1, self.B, self.n), dtype=torch.float64, device=self.device)
 		for i, T in enumerate(times):
 			slot = out[i if record_states else 0]
-			if T == self.time:
+			if T == self.time and (self.driver != 1 or not self._fresh):
 				slot.copy_(self._rows)
 			else:
 				self._advance(T, slot)

@@ -597,17 +597,18 @@ class jitcode:
 			storage = STORAGE_BY_NAME[storage]
 		old_integrator = self.integrator
 		dense = storage == "dense"
-		if storage is None and backend == "ode" and self.n >= DENSE_MINIMUM_N and self._dense_coupling() is not None:
+		dense_capable = method in (_codegen.JB_DP5, _codegen.JB_DOP853) and not (method == _codegen.JB_DOP853 and driver == _codegen.JB_DRV_IVP_DENSE)
+		if storage is None and dense_capable and self.n >= DENSE_MINIMUM_N and self._dense_coupling() is not None:
 			dense = np.count_nonzero(self._dense_coupling()[0]) >= DENSE_MINIMUM_DENSITY * self.n**2
 		if dense:
-			if backend != "ode" or self._dense_coupling() is None:
-				raise NotImplementedError("The dense engine integrates sine-coupled phase oscillators with \"dopri5\" or \"dop853\" only.")
+			if not dense_capable or self._dense_coupling() is None:
+				raise NotImplementedError("The dense engine integrates sine-coupled phase oscillators with \"dopri5\", \"dop853\", \"RK45\", or \"DOP853\" without interpolation only.")
 			_dense.dense_library()                                       # compiling needs no GPU …
 			require_cuda(device)                                         # … running does
 			integrator_params.pop("verbosity", None)
 			self._integrator_config = None
 			coupling = self._dense_coupling()
-			self.integrator = _dense.CudaDenseSineIntegrator(*coupling[:2], method=method, device=device, nsteps=nsteps,
+			self.integrator = _dense.CudaDenseSineIntegrator(*coupling[:2], method=method, driver=driver, device=device, nsteps=nsteps,
 					coupling_parameter=len(coupling) == 3, **integrator_params)
 			if len(coupling) == 3 and self.control_par_values is not None:
 				self.integrator.set_parameters(self._parameter_rows())

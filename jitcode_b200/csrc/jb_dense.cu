@@ -266,11 +266,18 @@ dgemm_dmma_pipelined_kernel(const double *__restrict__ A, const double *__restri
 
 enum { C_H = 0, C_HMAX, C_FACOLD, C_ERR2, C_DNF, C_DNY, C_DER2, C_FLAGS, C_NSTEP, C_ERR3,
 		C_NACC /* accepted steps of this call */, C_STIFF /* IASTI + 16·NONSTI + 128·(last estimate above the limit) */,
-		C_STNUM, C_STDEN /* sums of Hairer's stiffness estimate */, C_COUNT };
-enum { F_ACTIVE = 1, F_LAST = 2, F_REJECT = 4, F_ACCEPTED = 8, F_STIFF = 16 /* this attempt, if accepted, is looked at by the stiffness test */ };
+		C_STNUM, C_STDEN /* sums of Hairer's stiffness estimate */,
+		// SciPy's persistent stepper (solve_ivp drivers; these survive from call to call): |h| for the next step, start and
+		// length of the last step, end of the attempt in flight, and IVP_* bits
+		C_HABS, C_TOLD, C_HPREV, C_TNEW, C_IVP, C_COUNT };
+enum { F_ACTIVE = 1, F_LAST = 2, F_REJECT = 4, F_ACCEPTED = 8, F_STIFF = 16 /* this attempt, if accepted, is looked at by the stiffness test */,
+		F_INIT = 32 /* solve_ivp drivers: the stepper is being created (f(t, y), select_initial_step) */ };
+enum { IVP_EXISTS = 1 /* the stepper exists: K[0] = f(t, Y), C_HABS valid */, IVP_STEPPED = 2 /* it has made a step: W_YOLD, W_Q0 … hold its interpolant */ };
 // C_FLAGS is stored as a double holding a small int
 // work vectors, work[k*n*ld + i*ld + b]
-enum { W_Z = 0, W_K0 = 1 /* … W_K0+12 */, W_XS = 14 /* sin | cos: 2 vectors */, W_G = 16 /* G_s | G_c: 2 vectors */, W_COUNT = 18 };
+enum { W_Z = 0, W_K0 = 1 /* … W_K0+12 */, W_XS = 14 /* sin | cos: 2 vectors */, W_G = 16 /* G_s | G_c: 2 vectors */,
+		W_YOLD = 18 /* solve_ivp with dense output: start of the last step */, W_Q0 = 19 /* … W_Q0+3: its quartic interpolant */,
+		W_RES = 23 /* … and the sample at the target time */, W_COUNT = 24 };
 
 // coefficient access as constant expressions (both pairs; jb_tableaux.cuh)
 template <class Tab> struct Coef;
@@ -686,6 +693,193 @@ __global__ void __launch_bounds__(256) control_kernel(const Dense d)
 	publish_activity(d, b, active);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// SciPy's solve_ivp stepper (scipy _ivp/rk.py RungeKutta, common.py select_initial_step) as IVP_wrapper and
+// IVP_wrapper_no_interpolation drive it (integrator_tools.py:98-128); the same arithmetic as the IVP branches of
+// jb_rk.cuh's Lane, one trajectory per thread of these control kernels, the vectors in the element-wise kernels above.
+
+// IVP_wrapper.integrate: `while t < T: step()` — and at least one step before the first dense output
+__device__ __forceinline__ bool ivp_more_steps(const Dense &d, int64_t b, double t, int ivp)
+{
+	return t < d.T || (d.driver == JB_DRV_IVP_DENSE && !(ivp & IVP_STEPPED));
+}
+
+// the top of RungeKutta._step_impl (rk.py:111-124): limits of h_abs for a new step
+__device__ __forceinline__ double ivp_begin_step(const Dense &d, double t, double h_abs)
+{
+	const double min_step = 10.0 * fabs(::nextafter(t, (double) INFINITY) - t);
+	const double max_step = d.max_step > 0.0 ? d.max_step : INFINITY;
+	if (h_abs > max_step) h_abs = max_step;
+	else if (h_abs < min_step) h_abs = min_step;
+	return h_abs;
+}
+
+// one pass of its `while not step_accepted` loop up to rk_step (rk.py:126-141): the step to attempt
+__device__ __forceinline__ void ivp_begin_attempt(const Dense &d, int64_t b, double t, double &h_abs, int &flags)
+{
+	const double min_step = 10.0 * fabs(::nextafter(t, (double) INFINITY) - t);
+	if (!(fabs(h_abs) <= 1.79769313486231571e308)) { d.status[b] = JB_NONFINITE; flags &= ~F_ACTIVE; return; }
+	if (h_abs < min_step) { d.status[b] = JB_STEP_TOO_SMALL; flags &= ~F_ACTIVE; return; }
+	const double t_bound = d.driver == JB_DRV_IVP_DENSE ? INFINITY : d.T;
+	double t_new = t + h_abs;
+	if (t_new - t_bound > 0.0) t_new = t_bound;
+	const double h = t_new - t;
+	h_abs = fabs(h);
+	d.ctrl[C_H * d.ld + b] = h;
+	d.ctrl[C_TNEW * d.ld + b] = t_new;
+}
+
+// who integrates in this call, and whose stepper has to be created first
+__global__ void __launch_bounds__(256) setup_ivp_kernel(const Dense d)
+{
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	bool active = false;
+	if (b < d.B) {
+		const int ivp = (int) d.ctrl[C_IVP * d.ld + b];
+		active = d.status[b] == JB_OK && ivp_more_steps(d, b, d.t[b], ivp);
+		d.ctrl[C_FLAGS * d.ld + b] = active ? (F_ACTIVE | ((ivp & IVP_EXISTS) ? 0 : F_INIT)) : 0;
+		d.ctrl[C_DNF * d.ld + b] = d.ctrl[C_DNY * d.ld + b] = d.ctrl[C_DER2 * d.ld + b] = d.ctrl[C_ERR2 * d.ld + b] = d.ctrl[C_ERR3 * d.ld + b] = 0.0;
+	}
+	publish_activity(d, b, active);
+}
+
+// select_initial_step's result for the new steppers; the first attempt of everybody
+template <class Tab>
+__global__ void __launch_bounds__(256) first_step_ivp_kernel(const Dense d, int have_probe)
+{
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	bool active = false;
+	if (b < d.B) {
+		int flags = flags_of(d, b);
+		if (flags & F_ACTIVE) {
+			double h_abs = d.ctrl[C_HABS * d.ld + b];
+			if (flags & F_INIT) {
+				if (!have_probe) {
+					h_abs = d.first_step;
+				} else {
+					const double h0 = scipy_h0(d, b);
+					const double d1 = sqrt(d.ctrl[C_DNF * d.ld + b] / d.n);
+					const double d2 = sqrt(d.ctrl[C_DER2 * d.ld + b] / d.n) / h0;
+					const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / (Tab::ERR_ORDER + 1));
+					h_abs = fmin(fmin(100.0 * h0, h1), d.max_step > 0.0 ? d.max_step : INFINITY);
+				}
+				d.ctrl[C_IVP * d.ld + b] = IVP_EXISTS;
+				d.ctrl[C_TOLD * d.ld + b] = NAN;
+				d.ctrl[C_HPREV * d.ld + b] = 0.0;
+				flags &= ~F_INIT;
+			}
+			h_abs = ivp_begin_step(d, d.t[b], h_abs);
+			ivp_begin_attempt(d, b, d.t[b], h_abs, flags);
+			d.ctrl[C_HABS * d.ld + b] = h_abs;
+			d.ctrl[C_FLAGS * d.ld + b] = flags;
+			d.ctrl[C_ERR2 * d.ld + b] = d.ctrl[C_ERR3 * d.ld + b] = 0.0;
+			active = flags & F_ACTIVE;
+		}
+	}
+	publish_activity(d, b, active);
+}
+
+// the rest of the loop (rk.py:143-176): accept or reject, new h_abs, and the next attempt (of this step or the next)
+template <class Tab>
+__global__ void __launch_bounds__(256) control_ivp_kernel(const Dense d)
+{
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	bool active = false;
+	if (b < d.B) {
+		int flags = flags_of(d, b);
+		// (dense output: a trajectory that has arrived stays "accepted" until commit_ivp_kernel has formed its interpolant;
+		// without dense output stage 1 of this round has already taken Y ← Z for it)
+		if ((flags & F_ACTIVE) || d.driver != JB_DRV_IVP_DENSE) flags &= ~F_ACCEPTED;
+		if (flags & F_ACTIVE) {
+			double t = d.t[b], h_abs = d.ctrl[C_HABS * d.ld + b];
+			const double h = d.ctrl[C_H * d.ld + b];
+			double err;
+			if constexpr (Tab::ERR_NEEDS_FSAL) {
+				err = sqrt(d.ctrl[C_ERR2 * d.ld + b] / d.n);
+			} else {
+				const double s5 = d.ctrl[C_ERR2 * d.ld + b], s3 = d.ctrl[C_ERR3 * d.ld + b];
+				double deno = fma(0.01, s3, s5);
+				if (deno <= 0.0) deno = 1.0;
+				err = (s5 == 0.0 && s3 == 0.0) ? 0.0 : fabs(h) * s5 * sqrt(1.0 / (deno * d.n));
+			}
+			constexpr double exponent = -1.0 / (Tab::ERR_ORDER + 1);
+			if (err < 1.0) {
+				double factor = err == 0.0 ? 10.0 : fmin(10.0, 0.9 * pow(err, exponent));
+				if (flags & F_REJECT) factor = fmin(1.0, factor);
+				h_abs *= factor;
+				d.n_accepted[b] += 1;
+				d.ctrl[C_TOLD * d.ld + b] = t;
+				d.ctrl[C_HPREV * d.ld + b] = h;
+				t = d.ctrl[C_TNEW * d.ld + b];
+				const int ivp = IVP_EXISTS | IVP_STEPPED;
+				d.ctrl[C_IVP * d.ld + b] = ivp;
+				flags |= F_ACCEPTED;
+				flags &= ~F_REJECT;
+				if (ivp_more_steps(d, b, t, ivp)) {
+					h_abs = ivp_begin_step(d, t, h_abs);
+					ivp_begin_attempt(d, b, t, h_abs, flags);
+				} else {
+					flags &= ~F_ACTIVE;
+				}
+			} else {
+				// (a NaN error lands here, as in SciPy: the step shrinks until it is too small)
+				h_abs *= fmax(0.2, 0.9 * pow(err, exponent));
+				flags |= F_REJECT;
+				d.n_rejected[b] += 1;
+				ivp_begin_attempt(d, b, t, h_abs, flags);
+			}
+			d.t[b] = t;
+			d.ctrl[C_HABS * d.ld + b] = h_abs;
+			d.ctrl[C_ERR2 * d.ld + b] = d.ctrl[C_ERR3 * d.ld + b] = 0.0;
+			active = flags & F_ACTIVE;
+		}
+		d.ctrl[C_FLAGS * d.ld + b] = flags;
+	}
+	publish_activity(d, b, active);
+}
+
+// End of a call of the solve_ivp drivers.  Trajectories whose last attempt was accepted still have y_old in Y, y_new in
+// Z and the stages of that step in K: with dense output the step's interpolant is formed first (Q = Kᵀ·P, rk.py:178-180
+// for the 5(4) pair), then Y ← Z and K[0] ← K[S] = f(t, Y) for the next call.  With dense output every trajectory then
+// delivers its sample from the interpolant of its last step (RkDenseOutput._call_impl), made in this call or an earlier one.
+template <class Tab>
+__global__ void __launch_bounds__(256) commit_ivp_kernel(const Dense d)
+{
+	constexpr int S = Tab::NSTAGE;
+	for_rows(d, [&](int, int64_t b, int64_t at) {
+		if (flags_of(d, b) & F_ACCEPTED) {
+			if constexpr (Tab::ERR_NEEDS_FSAL) {
+				if (d.driver == JB_DRV_IVP_DENSE) {
+					double k[S + 1];
+					static_for<0, S + 1>([&](auto j) { k[j] = vec(d, W_K0 + j)[at]; });
+					static_for<0, 4>([&](auto p) {
+						double q = 0.0;
+						static_for<0, S + 1>([&](auto j) {
+							constexpr double w = DP5::P[j][p];
+							if constexpr (w != 0.0) q = fma(w, k[j], q);
+						});
+						vec(d, W_Q0 + p)[at] = q;
+					});
+					vec(d, W_YOLD)[at] = d.Y[at];
+				}
+			}
+			d.Y[at] = vec(d, W_Z)[at];
+			vec(d, W_K0)[at] = vec(d, W_K0 + S)[at];
+		}
+		if (d.driver == JB_DRV_IVP_DENSE && ((int) d.ctrl[C_IVP * d.ld + b] & IVP_STEPPED)) {
+			const double t_old = d.ctrl[C_TOLD * d.ld + b];
+			const double hh = d.t[b] - t_old;
+			const double x = (d.T - t_old) / hh;
+			double r = vec(d, W_Q0 + 3)[at];
+			r = fma(r, x, vec(d, W_Q0 + 2)[at]);
+			r = fma(r, x, vec(d, W_Q0 + 1)[at]);
+			r = fma(r, x, vec(d, W_Q0)[at]);
+			vec(d, W_RES)[at] = fma(hh * x, r, vec(d, W_YOLD)[at]);
+		}
+	});
+}
+
 // the accepted trajectories of the very last round still have y_new in Z: Y ← Z
 __global__ void __launch_bounds__(256) commit_kernel(const Dense d)
 {
@@ -779,6 +973,7 @@ const char *jb_dense_last_error(void) { return jbd::error_text; }
 int64_t jb_dense_launch_count(void) { return jbd::launch_counter.load(std::memory_order_relaxed); }
 int jb_dense_work_vectors(void) { return jbd::W_COUNT; }
 int jb_dense_control_scalars(void) { return jbd::C_COUNT; }
+int jb_dense_result_vector(void) { return jbd::W_RES; }
 
 int jb_dense_gemm(const double *A, const double *B, double *C, int M, int N, int K, void *stream_)
 {
@@ -960,16 +1155,15 @@ static int run_chains(const jb_dense_args *x, const Dense &d, Start &&launch_sta
 	return err == cudaSuccess ? 0 : fail((int) err, "jb_dense_integrate");
 }
 
-// advance every trajectory to x->T (Hairer's DOPRI5 / DOP853, fresh start, lands exactly on T)
+// checks the argument block and fills the kernels' view of it; 0 or an error code
 template <class Tab>
-static int integrate(const jb_dense_args *x)
+static int describe(const jb_dense_args *x, Dense &d)
 {
 	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_integrate: argument block has the wrong size");
 	if (x->B <= 0) return 0;
 	if (x->ld < x->B || x->ld % 64 || x->n <= 0 || !x->W || !x->omega || !x->t || !x->Y || !x->work || !x->ctrl
 			|| !x->status || !x->n_accepted || !x->n_rejected || !x->scratch || !x->host_flag)
 		return jbd::fail(JB_E_BAD_ARGUMENT, "jb_dense_integrate: missing or inconsistent buffers");
-	jbd::Dense d{};
 	d.B = x->B; d.ld = x->ld; d.n = x->n; d.W = x->W; d.omega = x->omega; d.coupling = x->coupling; d.atol_vec = x->atol_vec;
 	d.T = x->T; d.rtol = x->rtol; d.atol = x->atol; d.max_step = x->max_step; d.first_step = x->first_step;
 	d.nmax = x->nsteps > 0 ? x->nsteps : 100000;
@@ -986,9 +1180,20 @@ static int integrate(const jb_dense_args *x)
 		d.expo1 = 1.0 / 8.0 - d.beta * 0.2;
 	}
 	d.reject_by_dfactor = (x->method_flags >> 8) & 1;
+	d.driver = (x->method_flags >> 12) & 3;
 	d.t = x->t; d.Y = x->Y; d.work = x->work; d.ctrl = x->ctrl; d.status = x->status;
 	d.n_accepted = x->n_accepted; d.n_rejected = x->n_rejected;
 	d.tile_skip = x->scratch;
+	return 0;
+}
+
+// advance every trajectory to x->T (Hairer's DOPRI5 / DOP853, fresh start, lands exactly on T)
+template <class Tab>
+static int integrate(const jb_dense_args *x)
+{
+	jbd::Dense d{};
+	if (const int code = describe<Tab>(x, d)) return code;
+	if (x->B <= 0) return 0;
 	const int have_probe = !(d.first_step > 0.0);
 
 	return run_chains(x, d,
@@ -1028,6 +1233,56 @@ static int integrate(const jb_dense_args *x)
 		});
 }
 
+// the same for SciPy's solve_ivp stepper (RK45 / DOP853): persistent between calls; with dense output (JB_DRV_IVP_DENSE,
+// the 5(4) pair only) the sample at T goes to work vector jb_dense_result_vector() and Y stays the solver's state
+template <class Tab>
+static int integrate_ivp(const jb_dense_args *x)
+{
+	jbd::Dense d{};
+	if (const int code = describe<Tab>(x, d)) return code;
+	if (x->B <= 0) return 0;
+	if (d.driver == JB_DRV_IVP_DENSE && !Tab::ERR_NEEDS_FSAL)
+		return jbd::fail(JB_E_BAD_ARGUMENT, "jb_dense_integrate: dense output exists for the 5(4) pair only (DOP853: interpolate=False)");
+	d.nmax = (int64_t) 1 << 26;       // solve_ivp has no step limit; a call must end nevertheless
+	const int have_probe = !(d.first_step > 0.0);
+	const int fresh = (x->method_flags >> 14) & 1;      // some stepper may have to be created (the caller set a new state)
+
+	return run_chains(x, d,
+		[&](Chain &chain) {
+			const Dense &sub = chain.d;
+			cudaStream_t stream = chain.stream;
+			chain.reset_count();
+			JBD_LAUNCH(jbd::setup_ivp_kernel, chain.tgrid, 256, sub);
+			if (fresh) {
+				// RungeKutta.__init__: f = fun(t, y), select_initial_step (the Euler probe of common.py:119-122)
+				JBD_LAUNCH(jbd::sincos_kernel<0>, chain.egrid, eblock, sub, (int) jbd::F_INIT);
+				jbd::gemm(sub, stream);
+				JBD_LAUNCH(jbd::start_kernel, chain.egrid, eblock, sub, (int) jbd::F_INIT);
+				if (have_probe) {
+					JBD_LAUNCH(jbd::probe_kernel, chain.egrid, eblock, sub, (int) jbd::F_INIT);
+					jbd::gemm(sub, stream);
+					JBD_LAUNCH(jbd::probe_finish_kernel, chain.egrid, eblock, sub, (int) jbd::F_INIT);
+				}
+			}
+			chain.reset_count();
+			JBD_LAUNCH(jbd::first_step_ivp_kernel<Tab>, chain.tgrid, 256, sub, have_probe);
+		},
+		[&](Chain &chain) {
+			const Dense &sub = chain.d;
+			cudaStream_t stream = chain.stream;
+			launch_stages<Tab>(sub, chain.egrid, eblock, stream);
+			JBD_LAUNCH(jbd::error_kernel<Tab>, chain.egrid, eblock, sub);
+			chain.reset_count();
+			JBD_LAUNCH(jbd::control_ivp_kernel<Tab>, chain.tgrid, 256, sub);
+		},
+		[&](Chain &chain) {
+			const Dense &sub = chain.d;
+			cudaStream_t stream = chain.stream;
+			JBD_LAUNCH(jbd::commit_ivp_kernel<Tab>, chain.egrid, eblock, sub);
+			JBD_LAUNCH(jbd::clear_accepted_kernel, chain.tgrid, 256, sub);
+		});
+}
+
 }  // namespace jbd
 
 extern "C" {
@@ -1035,7 +1290,9 @@ extern "C" {
 int jb_dense_integrate(const jb_dense_args *x)
 {
 	if (!x || x->struct_size != sizeof(jb_dense_args)) return jbd::fail(JB_E_ABI, "jb_dense_integrate: argument block has the wrong size");
-	return (x->method_flags & 0xff) == JB_DOP853 ? jbd::integrate<jbd::DOP853>(x) : jbd::integrate<jbd::DP5>(x);
+	const bool dop853 = (x->method_flags & 0xff) == JB_DOP853;
+	if (((x->method_flags >> 12) & 3) != JB_DRV_ODE) return dop853 ? jbd::integrate_ivp<jbd::DOP853>(x) : jbd::integrate_ivp<jbd::DP5>(x);
+	return dop853 ? jbd::integrate<jbd::DOP853>(x) : jbd::integrate<jbd::DP5>(x);
 }
 
 }  // extern "C"

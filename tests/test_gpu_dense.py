@@ -126,6 +126,59 @@ def test_dense_integration_matches_generic_kernels_and_oracle(name):
 	within_tolerance(results["dense"][:, :24], ref["y"])
 
 
+@pytest.mark.parametrize("name,interpolate", [("RK45", True), ("RK45", False), ("DOP853", False)])
+def test_dense_solve_ivp_drivers(name, interpolate):
+	"""SciPy's solve_ivp stepper inside the dense engine (IVP_wrapper / IVP_wrapper_no_interpolation,
+	integrator_tools.py:98-128): persistent between calls, dense output of the step that passed the target time or last
+	step clipped to it — against the generic kernels (the same drivers, golden-pinned in test_gpu_parity.py), against the
+	CPU oracle (SciPy's own stepper under the reference's wrappers) and step for step in the number of attempts.
+	Sample times closer than a step (several samples from one interpolant), one call per time and all in one call."""
+	from oracle import c_rhs, ensemble
+	n, B = 40, 150
+	system = W.kuramoto(n)
+	Y0 = W.kuramoto_ensemble(B, n)
+	times = [0.5, 0.51, 0.52, 1.0, 5.0]
+	results, counts = {}, {}
+	for storage in ("dense", "global"):
+		ODE = jitcode(system["f_sym"], n=n, verbose=False)
+		ODE.set_integrator(name, interpolate=interpolate, rtol=RTOL, atol=ATOL, storage=storage)
+		assert (type(ODE.integrator).__name__ == "CudaDenseSineIntegrator") == (storage == "dense")
+		ODE.set_initial_value(Y0, 0.0)
+		results[storage] = np.stack([ODE.integrate(T) for T in times])
+		counts[storage] = ODE.step_counts()
+		if interpolate:
+			# IVP_wrapper.integrate reads an earlier time off the last step's interpolant (no step, no error)
+			earlier = ODE.integrate(4.9999)
+			assert ODE.step_counts() == counts[storage] and np.abs(earlier - results[storage][-1]).max() < 1e-2
+		else:
+			with pytest.raises(ValueError):
+				ODE.integrate(0.5)
+	within_tolerance(results["dense"], results["global"])
+	# the same stepper: the same number of attempts, up to decisions that fall differently by round-off (GEMM against term by term)
+	assert abs(sum(counts["dense"]) - sum(counts["global"])) <= 0.01 * sum(counts["global"])
+	handle = c_rhs.build_rhs(system["f_sym"], n=n)
+	ref = ensemble.run_ensemble(handle, name, Y0[:24], times, interpolate=interpolate, rtol=RTOL, atol=ATOL)
+	within_tolerance(results["dense"][:, :24], ref["y"])
+	# all sample times in one call; a second initial value re-creates the steppers
+	ODE = jitcode(system["f_sym"], n=n, verbose=False)
+	ODE.set_integrator(name, interpolate=interpolate, rtol=RTOL, atol=ATOL, storage="dense")
+	ODE.set_initial_value(Y0[:70], 0.0)
+	ODE.integrate(0.3)
+	ODE.set_initial_value(Y0, 0.0)
+	many = ODE.integrate_many(times)
+	assert_allclose(many, results["dense"], rtol=0, atol=0)
+	assert ODE.step_counts()[0] >= counts["dense"][0]
+
+
+def test_dense_dop853_dense_output_is_refused():
+	system = W.kuramoto(40)
+	ODE = jitcode(system["f_sym"], n=40, verbose=False)
+	with pytest.raises(NotImplementedError):
+		ODE.set_integrator("DOP853", interpolate=True, storage="dense")
+	ODE.set_integrator("DOP853", interpolate=True)           # … and by default such a system takes the generic kernels then
+	assert type(ODE.integrator).__name__ == "CudaEnsembleIntegrator"
+
+
 def test_dense_example_settings():
 	"""the example's own integrator settings (examples/kuramoto_network.py:29): dop853, atol 1e-6, rtol 0"""
 	from oracle import c_rhs, ensemble
