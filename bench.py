@@ -43,6 +43,7 @@ Keys of every record
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -378,7 +379,9 @@ class Bench:
 
 	# ---- one workload
 
-	def record(self, name, steps, warmup, B, cpu=True, parity=True, integrator=None):
+	def record(self, name, steps, warmup, B, cpu=True, parity=True, integrator=None, min_seconds=0.0):
+		"""min_seconds: the `configs` records time at least that long (more steps than asked for if a step is short):
+		nvidia-smi delivers its first clock sample a few hundred milliseconds after it was started"""
 		torch = self.torch
 		args, world, rank, device = self.args, self.world, self.rank, self.device
 		wl = workload(name, B, seed_offset=1000 * rank)      # every rank integrates its own shard
@@ -435,6 +438,16 @@ class Bench:
 		for _ in range(warmup):
 			device_step()
 		self.barrier()
+		if min_seconds > 0.0:
+			probe_start, probe_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+			probe_start.record()
+			device_step()
+			probe_end.record()
+			torch.cuda.synchronize()
+			wanted = torch.tensor([min_seconds / max(probe_start.elapsed_time(probe_end) * 1e-3, 1e-4)], device=device)
+			if world > 1:
+				self.dist.all_reduce(wanted, op=self.dist.ReduceOp.MAX)      # every rank times the same number of steps
+			steps = max(steps, min(400, int(math.ceil(wanted.item()))))
 		solver.reset_step_counts()
 		solver.kernel_events = []
 		launches_before = module.launch_count()
@@ -648,7 +661,7 @@ def run_ours(args):
 		for other in CONFIGS:
 			torch.cuda.empty_cache()
 			try:
-				configs[other] = bench.record(other, args.config_steps, 3, DEFAULT_TRAJECTORIES[other])
+				configs[other] = bench.record(other, args.config_steps, 3, DEFAULT_TRAJECTORIES[other], min_seconds=2.0)
 			except Exception as error:      # one failing config must not cost the headline line
 				configs[other] = {"error": f"{type(error).__name__}: {error}"}
 		line["configs"] = configs

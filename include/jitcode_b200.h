@@ -160,7 +160,7 @@ int64_t jb_launch_count(void);
  * tensor-core GEMM per right-hand-side evaluation for the whole ensemble.  Replaces, for such systems, the same
  * reference entry points as jb_eval_f / jb_integrate: driver JB_DRV_ODE ("dopri5" / "dop853", ODE_wrapper.integrate,
  * integrator_tools.py:134-144) and SciPy's solve_ivp stepper with the same pairs — JB_DRV_IVP_LAND ("RK45" / "DOP853"
- * without interpolation, IVP_wrapper_no_interpolation.integrate :110-128) and JB_DRV_IVP_DENSE ("RK45" with dense
+ * without interpolation, IVP_wrapper_no_interpolation.integrate :110-128) and JB_DRV_IVP_DENSE (the same with dense
  * output, IVP_wrapper.integrate :98-105).  Layout: plain structure of arrays, X[i*ld + b], ld a multiple of 64.
  */
 typedef struct jb_dense_args {
@@ -184,7 +184,7 @@ typedef struct jb_dense_args {
 	int32_t *scratch;          /* [ld/32 + 8] device scratch */
 	int32_t *host_flag;        /* four int32 in (pinned) host memory: the host polls the number of unfinished trajectories (of each of the interleaved sub-ensembles) */
 	int32_t  rounds_per_check; /* lock-step rounds between two polls; 0 = default (1: a round takes milliseconds, a poll microseconds) */
-	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1); bits 9-11: number of interleaved sub-ensembles (0: default, up to four of >= 1024 trajectories each; 1: none); bits 12-13: the driver, enum jb_driver — with the solve_ivp drivers work and ctrl persist between calls, and JB_DRV_IVP_DENSE exists for JB_DP5 only; bit 14: a new state was set, steppers have to be created */
+	int32_t  method_flags;     /* bits 0-7: enum jb_method; bit 8: dop853 shrinks by dfactor on rejection (SciPy 1.18.1); bits 9-11: number of interleaved sub-ensembles (0: default, up to four of >= 1024 trajectories each; 1: none); bits 12-13: the driver, enum jb_driver — with the solve_ivp drivers work and ctrl persist between calls; bit 14: a new state was set, steppers have to be created */
 	int64_t *rounds_out;       /* host: number of lock-step rounds of this call, or NULL */
 	void    *stream;
 } jb_dense_args;

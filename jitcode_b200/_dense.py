@@ -145,8 +145,8 @@ class CudaDenseSineIntegrator:
 	"""B trajectories of dy_i/dt = ω_i + Σ_j W_ij sin(y_j − y_i) on one GPU; Hairer's DOPRI5 ("dopri5") or DOP853 ("dop853")
 	(driver 0: every `integrate` call is a fresh start that lands on the target time, ODE_wrapper), or SciPy's solve_ivp
 	stepper with the same pairs ("RK45", "DOP853"): persistent between calls, driver 1 = the sample is the dense output
-	of the step that passed the target time (IVP_wrapper; the 5(4) pair only), driver 2 = the last step is clipped to the
-	target time (IVP_wrapper_no_interpolation)."""
+	of the step that passed the target time (IVP_wrapper), driver 2 = the last step is clipped to the target time
+	(IVP_wrapper_no_interpolation)."""
 
 	def __init__(self, W, omega, *, method=0, driver=0, device=None, rtol=1e-6, atol=1e-12, max_step=0.0, first_step=0.0, nsteps=10**6,
 			safety=0.0, ifactor=0.0, dfactor=0.0, beta=0.0, verbatim_dop853_reject=True, rounds_per_check=0, coupling_parameter=False,
@@ -176,8 +176,6 @@ class CudaDenseSineIntegrator:
 		# interleave: number of sub-ensembles whose launch sequences overlap on separate streams (0: default — up to
 		# four of ≥ 1024 trajectories each; 1: none; csrc/jb_dense.cu, integrate)
 		self.driver = int(driver)
-		if self.driver == 1 and int(method) != 0:
-			raise NotImplementedError("The dense engine has dense output for RK45 only; use DOP853 with interpolate=False.")
 		self.method_flags = int(method) | (256 if verbatim_dop853_reject else 0) | ((int(interleave) & 7) << 9) | (self.driver << 12)
 		self._fresh = True      # the solve_ivp stepper has to be created by the next call (a new state was set)
 		self.B = None

@@ -597,12 +597,12 @@ class jitcode:
 			storage = STORAGE_BY_NAME[storage]
 		old_integrator = self.integrator
 		dense = storage == "dense"
-		dense_capable = method in (_codegen.JB_DP5, _codegen.JB_DOP853) and not (method == _codegen.JB_DOP853 and driver == _codegen.JB_DRV_IVP_DENSE)
+		dense_capable = method in (_codegen.JB_DP5, _codegen.JB_DOP853)
 		if storage is None and dense_capable and self.n >= DENSE_MINIMUM_N and self._dense_coupling() is not None:
 			dense = np.count_nonzero(self._dense_coupling()[0]) >= DENSE_MINIMUM_DENSITY * self.n**2
 		if dense:
 			if not dense_capable or self._dense_coupling() is None:
-				raise NotImplementedError("The dense engine integrates sine-coupled phase oscillators with \"dopri5\", \"dop853\", \"RK45\", or \"DOP853\" without interpolation only.")
+				raise NotImplementedError("The dense engine integrates sine-coupled phase oscillators with \"dopri5\", \"dop853\", \"RK45\", or \"DOP853\" only.")
 			_dense.dense_library()                                       # compiling needs no GPU …
 			require_cuda(device)                                         # … running does
 			integrator_params.pop("verbosity", None)

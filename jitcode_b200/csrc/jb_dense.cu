@@ -276,8 +276,11 @@ enum { IVP_EXISTS = 1 /* the stepper exists: K[0] = f(t, Y), C_HABS valid */, IV
 // C_FLAGS is stored as a double holding a small int
 // work vectors, work[k*n*ld + i*ld + b]
 enum { W_Z = 0, W_K0 = 1 /* … W_K0+12 */, W_XS = 14 /* sin | cos: 2 vectors */, W_G = 16 /* G_s | G_c: 2 vectors */,
-		W_YOLD = 18 /* solve_ivp with dense output: start of the last step */, W_Q0 = 19 /* … W_Q0+3: its quartic interpolant */,
-		W_RES = 23 /* … and the sample at the target time */, W_COUNT = 24 };
+		W_YOLD = 18 /* solve_ivp with dense output: start of the last step */, W_Q0 = 19 /* … W_Q0+6: its interpolant (4 vectors for the 5(4) pair, 7 for the 8th-order pair) */,
+		W_KX = 26 /* … W_KX+2: K[13 … 15], the extra stages of the 8th-order pair's dense output */,
+		W_RES = 29 /* … and the sample at the target time */, W_COUNT = 30 };
+// work vector of stage derivative K[J]
+__host__ __device__ constexpr int krow(int j) { return j < 13 ? W_K0 + j : W_KX + (j - 13); }
 
 // coefficient access as constant expressions (both pairs; jb_tableaux.cuh)
 template <class Tab> struct Coef;
@@ -366,7 +369,7 @@ __device__ __forceinline__ double finish_rhs(const Dense &d, int i, int64_t b, i
 {
 	const double sum = xs_cos(d, i, b) * g_sin(d, i, b) - xs_sin(d, i, b) * g_cos(d, i, b);
 	const double value = d.coupling ? fma(d.coupling[b], sum, d.omega[i]) : d.omega[i] + sum;
-	vec(d, W_K0 + J)[at] = value;
+	vec(d, krow(J))[at] = value;
 	return value;
 }
 
@@ -839,6 +842,38 @@ __global__ void __launch_bounds__(256) control_ivp_kernel(const Dense d)
 	publish_activity(d, b, active);
 }
 
+// The 8th-order pair's dense output needs three more stages of the step just made (DOP853._dense_output_impl,
+// rk.py:693-701): stage s = 13, 14, 15 from (t_old, y_old) with the step's own h, for the trajectories that stepped.
+// The GEMMs in between run over the tiles that hold such trajectories.
+__global__ void __launch_bounds__(256) mark_accepted_tiles_kernel(const Dense d)
+{
+	const int64_t b = d.b0 + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned any = __ballot_sync(0xffffffffu, b < d.B && (flags_of(d, b) & F_ACCEPTED));
+	if ((threadIdx.x & 31) == 0 && b < d.b1) d.tile_skip[b / 32] = any == 0;
+}
+
+template <int ROW>
+__global__ void __launch_bounds__(256) extra_stage_kernel(const Dense d)
+{
+	for_rows(d, [&](int i, int64_t b, int64_t at) {
+		if (!(flags_of(d, b) & F_ACCEPTED)) return;
+		double k[ROW];
+		static_for<0, ROW - 1>([&](auto j) {
+			constexpr double a = jb::dop853::A[ROW][j];
+			if constexpr (a != 0.0) k[j] = vec(d, krow(j))[at];
+		});
+		if constexpr (ROW > 13) k[ROW - 1] = finish_rhs<ROW - 1>(d, i, b, at);
+		else k[ROW - 1] = vec(d, krow(ROW - 1))[at];
+		double acc = 0.0;
+		static_for<0, ROW>([&](auto j) {
+			constexpr double a = jb::dop853::A[ROW][j];
+			if constexpr (a != 0.0) acc = fma(a, k[j], acc);
+		});
+		const double z = fma(d.ctrl[C_HPREV * d.ld + b], acc, d.Y[at]);
+		sincos(z, &xs_sin(d, i, b), &xs_cos(d, i, b));
+	});
+}
+
 // End of a call of the solve_ivp drivers.  Trajectories whose last attempt was accepted still have y_old in Y, y_new in
 // Z and the stages of that step in K: with dense output the step's interpolant is formed first (Q = Kᵀ·P, rk.py:178-180
 // for the 5(4) pair), then Y ← Z and K[0] ← K[S] = f(t, Y) for the next call.  With dense output every trajectory then
@@ -847,10 +882,12 @@ template <class Tab>
 __global__ void __launch_bounds__(256) commit_ivp_kernel(const Dense d)
 {
 	constexpr int S = Tab::NSTAGE;
-	for_rows(d, [&](int, int64_t b, int64_t at) {
+	for_rows(d, [&](int i, int64_t b, int64_t at) {
+		(void) i;
 		if (flags_of(d, b) & F_ACCEPTED) {
-			if constexpr (Tab::ERR_NEEDS_FSAL) {
-				if (d.driver == JB_DRV_IVP_DENSE) {
+			if (d.driver == JB_DRV_IVP_DENSE) {
+				const double y_old = d.Y[at];
+				if constexpr (Tab::ERR_NEEDS_FSAL) {
 					double k[S + 1];
 					static_for<0, S + 1>([&](auto j) { k[j] = vec(d, W_K0 + j)[at]; });
 					static_for<0, 4>([&](auto p) {
@@ -861,8 +898,26 @@ __global__ void __launch_bounds__(256) commit_ivp_kernel(const Dense d)
 						});
 						vec(d, W_Q0 + p)[at] = q;
 					});
-					vec(d, W_YOLD)[at] = d.Y[at];
+				} else {
+					// F[0 … 6] of DOP853._dense_output_impl (rk.py:703-711); K[15] comes out of the last GEMM
+					double k[16];
+					static_for<0, 15>([&](auto j) { k[j] = vec(d, krow(j))[at]; });
+					k[15] = finish_rhs<15>(d, i, b, at);
+					const double h = d.ctrl[C_HPREV * d.ld + b];
+					const double delta = vec(d, W_Z)[at] - y_old;
+					vec(d, W_Q0)[at] = delta;
+					vec(d, W_Q0 + 1)[at] = h * k[0] - delta;
+					vec(d, W_Q0 + 2)[at] = 2.0 * delta - h * (k[S] + k[0]);
+					static_for<0, 4>([&](auto row) {
+						double q = 0.0;
+						static_for<0, 16>([&](auto j) {
+							constexpr double w = jb::dop853::D[row][j];
+							if constexpr (w != 0.0) q = fma(w, k[j], q);
+						});
+						vec(d, W_Q0 + 3 + row)[at] = h * q;
+					});
 				}
+				vec(d, W_YOLD)[at] = y_old;
 			}
 			d.Y[at] = vec(d, W_Z)[at];
 			vec(d, W_K0)[at] = vec(d, W_K0 + S)[at];
@@ -871,11 +926,21 @@ __global__ void __launch_bounds__(256) commit_ivp_kernel(const Dense d)
 			const double t_old = d.ctrl[C_TOLD * d.ld + b];
 			const double hh = d.t[b] - t_old;
 			const double x = (d.T - t_old) / hh;
-			double r = vec(d, W_Q0 + 3)[at];
-			r = fma(r, x, vec(d, W_Q0 + 2)[at]);
-			r = fma(r, x, vec(d, W_Q0 + 1)[at]);
-			r = fma(r, x, vec(d, W_Q0)[at]);
-			vec(d, W_RES)[at] = fma(hh * x, r, vec(d, W_YOLD)[at]);
+			if constexpr (Tab::ERR_NEEDS_FSAL) {
+				double r = vec(d, W_Q0 + 3)[at];
+				r = fma(r, x, vec(d, W_Q0 + 2)[at]);
+				r = fma(r, x, vec(d, W_Q0 + 1)[at]);
+				r = fma(r, x, vec(d, W_Q0)[at]);
+				vec(d, W_RES)[at] = fma(hh * x, r, vec(d, W_YOLD)[at]);
+			} else {
+				// Dop853DenseOutput._call_impl (rk.py:747-764)
+				double r = 0.0;
+				static_for<0, 7>([&](auto k) {
+					r += vec(d, W_Q0 + 6 - k)[at];
+					r *= (k % 2 == 0) ? x : 1.0 - x;
+				});
+				vec(d, W_RES)[at] = r + vec(d, W_YOLD)[at];
+			}
 		}
 	});
 }
@@ -1233,16 +1298,14 @@ static int integrate(const jb_dense_args *x)
 		});
 }
 
-// the same for SciPy's solve_ivp stepper (RK45 / DOP853): persistent between calls; with dense output (JB_DRV_IVP_DENSE,
-// the 5(4) pair only) the sample at T goes to work vector jb_dense_result_vector() and Y stays the solver's state
+// the same for SciPy's solve_ivp stepper (RK45 / DOP853): persistent between calls; with dense output (JB_DRV_IVP_DENSE)
+// the sample at T goes to work vector jb_dense_result_vector() and Y stays the solver's state
 template <class Tab>
 static int integrate_ivp(const jb_dense_args *x)
 {
 	jbd::Dense d{};
 	if (const int code = describe<Tab>(x, d)) return code;
 	if (x->B <= 0) return 0;
-	if (d.driver == JB_DRV_IVP_DENSE && !Tab::ERR_NEEDS_FSAL)
-		return jbd::fail(JB_E_BAD_ARGUMENT, "jb_dense_integrate: dense output exists for the 5(4) pair only (DOP853: interpolate=False)");
 	d.nmax = (int64_t) 1 << 26;       // solve_ivp has no step limit; a call must end nevertheless
 	const int have_probe = !(d.first_step > 0.0);
 	const int fresh = (x->method_flags >> 14) & 1;      // some stepper may have to be created (the caller set a new state)
@@ -1278,6 +1341,17 @@ static int integrate_ivp(const jb_dense_args *x)
 		[&](Chain &chain) {
 			const Dense &sub = chain.d;
 			cudaStream_t stream = chain.stream;
+			if constexpr (!Tab::ERR_NEEDS_FSAL) {
+				if (sub.driver == JB_DRV_IVP_DENSE && chain.rounds > 0) {
+					JBD_LAUNCH(jbd::mark_accepted_tiles_kernel, chain.tgrid, 256, sub);
+					JBD_LAUNCH(jbd::extra_stage_kernel<13>, chain.egrid, eblock, sub);
+					jbd::gemm(sub, stream);
+					JBD_LAUNCH(jbd::extra_stage_kernel<14>, chain.egrid, eblock, sub);
+					jbd::gemm(sub, stream);
+					JBD_LAUNCH(jbd::extra_stage_kernel<15>, chain.egrid, eblock, sub);
+					jbd::gemm(sub, stream);
+				}
+			}
 			JBD_LAUNCH(jbd::commit_ivp_kernel<Tab>, chain.egrid, eblock, sub);
 			JBD_LAUNCH(jbd::clear_accepted_kernel, chain.tgrid, 256, sub);
 		});

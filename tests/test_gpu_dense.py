@@ -126,7 +126,7 @@ def test_dense_integration_matches_generic_kernels_and_oracle(name):
 	within_tolerance(results["dense"][:, :24], ref["y"])
 
 
-@pytest.mark.parametrize("name,interpolate", [("RK45", True), ("RK45", False), ("DOP853", False)])
+@pytest.mark.parametrize("name,interpolate", [("RK45", True), ("RK45", False), ("DOP853", True), ("DOP853", False)])
 def test_dense_solve_ivp_drivers(name, interpolate):
 	"""SciPy's solve_ivp stepper inside the dense engine (IVP_wrapper / IVP_wrapper_no_interpolation,
 	integrator_tools.py:98-128): persistent between calls, dense output of the step that passed the target time or last
@@ -168,15 +168,6 @@ def test_dense_solve_ivp_drivers(name, interpolate):
 	many = ODE.integrate_many(times)
 	assert_allclose(many, results["dense"], rtol=0, atol=0)
 	assert ODE.step_counts()[0] >= counts["dense"][0]
-
-
-def test_dense_dop853_dense_output_is_refused():
-	system = W.kuramoto(40)
-	ODE = jitcode(system["f_sym"], n=40, verbose=False)
-	with pytest.raises(NotImplementedError):
-		ODE.set_integrator("DOP853", interpolate=True, storage="dense")
-	ODE.set_integrator("DOP853", interpolate=True)           # … and by default such a system takes the generic kernels then
-	assert type(ODE.integrator).__name__ == "CudaEnsembleIntegrator"
 
 
 def test_dense_example_settings():

@@ -280,7 +280,7 @@ def test_module_builds_loads_and_exports_every_symbol():
 	dense = _dense.dense_library()                    # the dense sine-coupling library: built once, loaded without a GPU
 	for name in _dense.DENSE_EXPORTS:
 		assert hasattr(dense, name), name
-	assert dense.jb_dense_work_vectors() == 24 and dense.jb_dense_control_scalars() == 19 and dense.jb_dense_result_vector() == 23
+	assert dense.jb_dense_work_vectors() == 30 and dense.jb_dense_control_scalars() == 19 and dense.jb_dense_result_vector() == 29
 	declared -= set(_dense.DENSE_EXPORTS)
 	ODE = jitcode(W.lotka_volterra(gamma_as_parameter=True)["f_sym"], n=2, control_pars=W.lotka_volterra(gamma_as_parameter=True)["control_pars"], verbose=False)
 	module = ODE.compile_cuda()
