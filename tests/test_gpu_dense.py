@@ -170,6 +170,31 @@ def test_dense_solve_ivp_drivers(name, interpolate):
 	assert ODE.step_counts()[0] >= counts["dense"][0]
 
 
+def test_dense_solve_ivp_with_coupling_parameter_vector_atol_and_first_step():
+	"""the solve_ivp drivers of the dense engine with everything the Hairer drivers have: the coupling strength as a
+	per-trajectory control parameter, one atol per component, a given first step — against the generic kernels"""
+	import sympy
+	from jitcode_b200 import y
+	n, B = 40, 96
+	data = W.kuramoto_data(n)
+	kappa = sympy.Symbol("c")
+	f = [data["omega"][i] + kappa / (n - 1) * sympy.Add(*[sympy.sin(y(j) - y(i)) for j in range(n) if data["A"][j, i]]) for i in range(n)]
+	Y0 = W.kuramoto_ensemble(B, n, seed=8)
+	strengths = np.random.default_rng(2).uniform(0.5, 4.0, B)
+	atol = np.geomspace(1e-12, 1e-9, n)
+	results, counts = {}, {}
+	for storage in ("dense", "global"):
+		ODE = jitcode(f, n=n, control_pars=[kappa], verbose=False)
+		ODE.set_integrator("RK45", rtol=1e-7, atol=atol, first_step=1e-3, storage=storage)
+		ODE.set_parameters(strengths)
+		ODE.set_initial_value(Y0, 0.0)
+		results[storage] = np.stack([ODE.integrate(T) for T in (0.7, 2.0)])
+		counts[storage] = ODE.step_counts()
+	excess = np.abs(results["dense"] - results["global"]) - 10 * (atol + 1e-7 * np.abs(results["global"]))
+	assert np.all(excess <= 0), f"max excess {excess.max():.3e}"
+	assert abs(sum(counts["dense"]) - sum(counts["global"])) <= 0.01 * sum(counts["global"])
+
+
 def test_dense_example_settings():
 	"""the example's own integrator settings (examples/kuramoto_network.py:29): dop853, atol 1e-6, rtol 0"""
 	from oracle import c_rhs, ensemble
