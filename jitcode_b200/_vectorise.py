@@ -97,8 +97,9 @@ def _role(node, own):
 	return (0 if index is None else 1, 0 if index is None else (index - own if own is not None else index), 0.0 if constant is None else constant)
 
 
-def analyse(expr, allow_loops=True, own=None):
-	"""canonical tree of a SymPy expression (`own`: index of the component whose equation this is)."""
+def analyse(expr, allow_loops=True, own=None, force=()):
+	"""canonical tree of a SymPy expression (`own`: index of the component whose equation this is; `force`: keys of
+	terms that form a loop however few of them there are — see make_plan)."""
 	if expr.is_Number:
 		return Node("const", float(expr))
 	if _is_dynvar(expr):
@@ -106,9 +107,9 @@ def analyse(expr, allow_loops=True, own=None):
 	if expr.is_Symbol:
 		return Node("sym", expr)
 	if expr.is_Pow and expr.exp.is_Number:
-		return Node("pow", expr.exp, [analyse(expr.base, allow_loops, own)])
+		return Node("pow", expr.exp, [analyse(expr.base, allow_loops, own, force)])
 	if expr.is_Add or expr.is_Mul:
-		children = sorted((analyse(arg, allow_loops, own) for arg in expr.args), key=lambda node: (node.key, _role(node, own)))
+		children = sorted((analyse(arg, allow_loops, own, force) for arg in expr.args), key=lambda node: (node.key, _role(node, own)))
 		if expr.is_Add and allow_loops:
 			runs = OrderedDict()
 			for child in children:
@@ -116,14 +117,14 @@ def analyse(expr, allow_loops=True, own=None):
 			children = []
 			for key, members in runs.items():
 				varying = "C" in key or "Y" in key
-				if len(members) >= LOOP_MIN and varying and not any(member.has_loop for member in members):
+				if (len(members) >= LOOP_MIN or key in force) and varying and not any(member.has_loop for member in members):
 					children.append(Node("loop", None, members))
 				else:
 					children.extend(members)
 			children.sort(key=lambda node: (node.key, _role(node, own) if node.kind != "loop" else ()))
 		return Node("op", expr.func, children)
 	if isinstance(expr, sympy.Function) or isinstance(expr, AppliedUndef):
-		return Node("op", expr.func, [analyse(arg, allow_loops, own) for arg in expr.args])
+		return Node("op", expr.func, [analyse(arg, allow_loops, own, force) for arg in expr.args])
 	raise NotImplementedError(f"cannot vectorise {expr!r}")
 
 
@@ -296,9 +297,32 @@ def make_plan(f, helpers, control_pars):
 		group = Group(node.key, node, f"jb_h{k}_")
 		group.add(-1, node)
 		plan.helpers.append((sympy.Symbol(f"jb_helper_{k}"), group))
+	nodes = [analyse(sympy.sympify(entry), own=i) for i, entry in enumerate(f)]
+	# Stragglers: a node of a network with only one or two neighbours has no "run of equally shaped terms", so its equation
+	# would be a group of its own (and keep its siblings' groups from being fused).  Where reading its few terms as a
+	# (short) loop gives it the shape of a large group, it joins that group.
+	census = {}
+	for node in nodes:
+		census[node.key] = census.get(node.key, 0) + 1
+	large = {key for key, count in census.items() if count >= 8}
+	def loop_terms(node, found):
+		if node.kind == "loop":
+			found.add(node.children[0].key)
+		for child in node.children:
+			loop_terms(child, found)
+		return found
+	force = set()
+	for node in nodes:
+		if node.key in large:
+			loop_terms(node, force)
+	if force:
+		for i, node in enumerate(nodes):
+			if node.key not in large:
+				again = analyse(sympy.sympify(f[i]), own=i, force=force)
+				if again.key in large:
+					nodes[i] = again
 	groups = OrderedDict()
-	for i, entry in enumerate(f):
-		node = analyse(sympy.sympify(entry), own=i)
+	for i, node in enumerate(nodes):
 		if node.key not in groups:
 			groups[node.key] = Group(node.key, node, f"jb_g{len(groups)}_")
 		groups[node.key].add(i, node)

@@ -188,6 +188,30 @@ def test_printed_vectorised_code_on_host_lanes(name, team_warps, tmp_path):
 		np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-14)
 
 
+def test_stragglers_join_the_large_groups(tmp_path):
+	"""a node with one or two neighbours has no run of equally shaped terms; read as a short loop its equation has the
+	shape of all the others and joins their group (the random graph of bench.py: 98 + 2 statements became 100)"""
+	from jitcode_b200 import _vectorise
+	from host_lanes import evaluate_printed
+	system = W.roessler_network(100, topology="random")
+	f, n = _symbolic.handle_input(system["f_sym"], system["n"])
+	helpers = _symbolic.sort_helpers(system["helpers"])
+	plan = _vectorise.make_plan(f, helpers, system["control_pars"])
+	assert [group.size for group in plan.groups] == [100, 100, 100]
+	lengths = [plan.groups[0].loops[0].start[m+1] - plan.groups[0].loops[0].start[m] for m in range(100)]
+	assert min(lengths) < _vectorise.LOOP_MIN <= max(lengths)
+	state = np.random.default_rng(6).random(n)
+	subs = dict(zip(system["control_pars"], [0.013]))
+	expected = evaluate_large([entry.xreplace(subs) for entry in f], [(s, d.xreplace(subs)) for s, d in helpers], state, time=0.4)
+	np.testing.assert_allclose(_vectorise.evaluate_plan(plan, 0.4, state, [0.013]), expected, rtol=1e-12, atol=1e-14)
+	lines, tables, component_of = _vectorise.warp_statements(plan)
+	got = evaluate_printed(lines, tables, component_of, 1, 0.4, state, [0.013], 32, 2, tmp_path)
+	np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-14)
+	# a tiny system in which nothing is "large" stays as it was
+	small = _vectorise.make_plan([y(1) + y(2), y(0) * 2.0, y(0) + y(1) + y(2) + y(0)**2], [], [])
+	assert len(small.groups) == 3
+
+
 @pytest.mark.parametrize("rewiring,expected", [(0.0, "complete"), (0.1, "subtract"), (0.3, "masks")])
 def test_printed_ring_variants_on_host_lanes(rewiring, expected, tmp_path):
 	"""the three ways a blocked ring is summed: complete ring (no masks, no corrections), nearly complete (all
