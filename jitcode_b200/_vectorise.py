@@ -828,6 +828,19 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 	lines = []
 	blockings = ring_blockings(plan, team) if blocked_rings else {}
 	groups = [group.reordered(_blocked_order(group.size, *blockings[group.size])) if group.size in blockings else group for group in plan.groups]
+	# Round-robin groups of several passes: a pass is padded to ITS longest sum, so the statements are dealt to the passes
+	# by length — the longest sums share the first pass, the shortest the last (Erdős–Rényi graph of mean degree 20:
+	# 32 + 23 + 20 + 14 padded gather slots per lane instead of 4 × ≈ 30).  All groups of one size take the same order,
+	# so that the equations of one unit stay at the same place of their groups (and are fused as before).
+	orders = {}
+	for group in groups:
+		if group.size in blockings or group.size in orders or group.size <= team or not group.loops or min(group.outs) < 0:
+			continue
+		weight = [sum(loop.start[m+1] - loop.start[m] for loop in group.loops) for m in range(group.size)]
+		order = sorted(range(group.size), key=lambda m: (-weight[m], m))
+		if order != list(range(group.size)):
+			orders[group.size] = order
+	groups = [group.reordered(orders[group.size]) if group.size in orders else group for group in groups]
 	position = component_positions(plan, groups)
 	zero_slot = plan.n
 	spans = [(position[group.outs[0]], group.size) for group in groups]
