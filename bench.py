@@ -475,8 +475,12 @@ class Bench:
 		del result
 
 		# ---- end-to-end arm: pinned host buffers in and out through the public API
-		for _ in range(warmup):      # (also lets torch's caching allocator for page-locked memory settle: results rotate through three blocks)
-			host_step()
+		# (the warm-up also lets torch's caching allocator for page-locked memory settle; it keeps its result until the next
+		# one exists, like the timed loop and like a caller does, so that both blocks the steady state needs get allocated
+		# here: page-locking 1.6 GB of samples of config 5 takes a second)
+		returned = None
+		for _ in range(warmup):
+			returned = host_step()
 		self.barrier()
 		solver.reset_step_counts()
 		t0 = time.perf_counter()

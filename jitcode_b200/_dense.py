@@ -377,17 +377,39 @@ class CudaDenseSineIntegrator:
 		if any(later < earlier for earlier, later in zip(([] if self.driver == 1 else [self.time]) + times, times)):
 			raise ValueError("Target time smaller than current time. Cannot integrate backwards in time")
 		out = torch.empty((len(times) if record_states else 1, self.B, self.n), dtype=torch.float64, device=self.device)
+		# results for the host: every sample starts its way there as soon as it exists, on a second stream, while the
+		# ensemble integrates towards the next one (config 5: 1.6 GB of samples, a fifth of the call if copied at the end)
+		stream_out = self._out_kind != "cuda" and out.numel() >= 1 << 20
+		if stream_out:
+			host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+			main, side = torch.cuda.current_stream(self.device), self._copy_stream()
 		for i, T in enumerate(times):
-			slot = out[i if record_states else 0]
+			k = i if record_states else 0
+			slot = out[k]
 			if T == self.time and (self.driver != 1 or not self._fresh):
 				slot.copy_(self._rows)
 			else:
 				self._advance(T, slot)
+			if stream_out and (record_states or i == len(times) - 1):
+				side.wait_stream(main)
+				with torch.cuda.stream(side):
+					host[k].copy_(slot, non_blocking=True)
 		self._rows = out[-1]
 		self._check_failures()
+		if stream_out:
+			side.synchronize()
+			out.record_stream(side)
+			if self._single:
+				host = host[:, 0]
+			return host if self._out_kind == "torch" else host.numpy()
 		if self._single:
 			out = out[:, 0]
 		return out if self._out_kind == "cuda" else self._to_host(out)
+
+	def _copy_stream(self):
+		if getattr(self, "_side_stream", None) is None:
+			self._side_stream = torch.cuda.Stream(self.device)
+		return self._side_stream
 
 	def eval_f(self, state):
 		rows, kind, single = self._to_device_rows(state)

@@ -195,6 +195,26 @@ def test_dense_solve_ivp_with_coupling_parameter_vector_atol_and_first_step():
 	assert abs(sum(counts["dense"]) - sum(counts["global"])) <= 0.01 * sum(counts["global"])
 
 
+def test_dense_samples_streamed_to_the_host():
+	"""integrate_many with a host-resident ensemble copies every sample to page-locked memory on a second stream while the
+	next one is integrated (large outputs only): the same numbers as the device-resident call"""
+	n, B = 40, 4096
+	system = W.kuramoto(n)
+	Y0 = W.kuramoto_ensemble(B, n, seed=12)
+	times = [0.25 * k for k in range(1, 9)]
+	ODE = jitcode(system["f_sym"], n=n, verbose=False)
+	ODE.set_integrator("dop853", atol=1e-6, rtol=0, storage="dense")
+	ODE.set_initial_value(torch.as_tensor(Y0).cuda(), 0.0)
+	on_device = ODE.integrate_many(times).cpu().numpy()
+	ODE.set_initial_value(Y0, 0.0)
+	on_host = ODE.integrate_many(times)
+	assert isinstance(on_host, np.ndarray) and on_host.shape == (8, B, n)
+	assert_allclose(on_host, on_device, rtol=0, atol=0)
+	ODE.set_initial_value(Y0, 0.0)
+	last = ODE.integrate_many(times, record_states=False)
+	assert_allclose(last[0], on_device[-1], rtol=0, atol=0)
+
+
 def test_dense_example_settings():
 	"""the example's own integrator settings (examples/kuramoto_network.py:29): dop853, atol 1e-6, rtol 0"""
 	from oracle import c_rhs, ensemble
