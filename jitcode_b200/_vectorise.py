@@ -38,6 +38,7 @@ tested on a machine without a GPU.
 vectoriser against direct evaluation of the symbolic input.
 """
 
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -391,6 +392,7 @@ class Tables:
 	"""two flat tables (doubles, unsigned integers) that the kernel stages in shared memory."""
 	def __init__(self):
 		self.f64, self.u = [], []
+		self.helper_lanes = None      # set while a batch is printed whose idle lanes help with the gathers (_print_loop)
 
 	def add_f64(self, values):
 		offset = len(self.f64)
@@ -513,6 +515,39 @@ def _paddable(loop):
 		return body == 0 or sympy.simplify(body) == 0
 	except Exception:
 		return False
+
+
+HELPER_LANES = not os.environ.get("JITCODE_B200_NO_HELPER_LANES")
+
+
+def team_is_warp(team):
+	"""a single warp whose idle lanes can shadow working lanes of the second half-warp"""
+	return 24 <= team < 32
+
+
+def _helper_plan(lists, team, n_pass, size):
+	"""per pass (cap, owners): every statement keeps `cap` (even) gather slots, the statements in `owners` hand the rest to
+	one idle lane each; None if no pass gets narrower that way.  The smallest cap is taken for which the idle lanes
+	(but one, whose empty row serves everybody else) suffice and the rest of a statement fits a helper's row."""
+	if size != team * n_pass:
+		return None
+	helpers = min(32 - team, 8) - 1
+	if helpers < 1:
+		return None
+	plan, gain = [], 0
+	for p in range(n_pass):
+		counts = {m: len(lists[m]) for m in range(team * p, team * p + team)}
+		widest = max(counts.values())
+		widest += widest % 2
+		cap = widest
+		for candidate in range(2, widest, 2):
+			owners = [m for m, count in counts.items() if count > candidate]
+			if len(owners) <= helpers and all(counts[m] - candidate <= candidate for m in owners):
+				cap = candidate
+				break
+		plan.append((max(cap, 2), [m for m, count in counts.items() if count > cap]))
+		gain += widest - cap
+	return plan if gain > 0 else None
 
 
 def _ell(values, start, size, width, pad):
@@ -672,14 +707,25 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 				rotation = 0        # the ring is too short for a wavefront without wrap-around either way
 		who = "jb_lane" if blocked else "lane"
 		physical = (lambda lane: (lane - rotation) % team) if blocked else (lambda lane: lane)
-		if blocked and prologue is not None and not any("const int jb_lane" in line for line in prologue):
-			shifted = f"lane + {rotation}"
-			prologue.insert(0, f"\tconst int jb_lane = {f'{shifted} >= {team} ? {shifted} - {team} : {shifted}' if rotation else 'lane'};")
 		signed_pairs = bool(missing) and 8 * zero_slot < 32768 and SIGNED_PAIRS
 		negative = [set(terms) for terms in missing] if signed_pairs else [set()] * size
 		if signed_pairs:
 			per_statement = [list(plus) + list(minus) for plus, minus in zip(per_statement, missing)]
 			missing = None
+		# Idle lanes as helpers (blocked order of a single warp that leaves lanes idle): a pass is padded to its longest
+		# statement, but few statements are long (Rössler benchmark: 3.7 entries per statement on average, 8 at most).  The
+		# lanes beyond `team` run the same gather loop on rows of their own that hold what did NOT fit `cap` slots of an
+		# over-long statement (one such statement per helper lane and pass); its owner fetches the helper's sum with one
+		# shuffle.  For the warp these gathers are free: an LDS.64 of 32 lanes takes the two wavefronts that one of 25 takes.
+		helper_plan = _helper_plan(per_statement, team, n_pass, size) if (signed_pairs and HELPER_LANES and blocked and team_is_warp(team) and 8 * (zero_slot + ZERO_WORDS) <= 4096) else None
+		if helper_plan:
+			tables.helper_lanes = team
+		if blocked and prologue is not None and not any("const int jb_lane" in line for line in prologue):
+			# (helper lanes shadow a working lane of their own half-warp in everything but the gathers: the same addresses,
+			# hence no additional shared-memory wavefronts, and nothing out of range)
+			source = f"(lane >= {team} ? lane - {team - 16} : lane)" if helper_plan else "lane"
+			shifted = f"{source} + {rotation}"
+			prologue.insert(0, f"\tconst int jb_lane = {f'{shifted} >= {team} ? {shifted} - {team} : {shifted}' if rotation else source};")
 
 		def pair_table(lists):
 			"""padded table of 16-bit byte offsets, two per 32-bit word, pass after pass → (offset, bases, pairs per pass)"""
@@ -698,6 +744,53 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 							words.append(8 * (zero_slot if where is None else where) | (0x8000 if where in negative[min(team*p + lane, size - 1)] else 0))
 			return (tables.add_u(words, align=2), bases, widths) if words else None
 
+		def helper_table(lists):
+			"""the same table with 32 rows per pass, indexed by the lane of the warp: rows of the working lanes hold the first
+			`cap` entries of their statement and, in bits 12-14 of the first entry, which lane beyond `team` has summed the
+			rest (the last one holds no entries at all: its sum is the 0.0 of statements that fit) → (offset, bases, widths)"""
+			words, bases, widths = [], [], []
+			spare = 32 - team
+			for p in range(n_pass):
+				cap, owners = helper_plan[p]
+				rows, owner_of_row, code = [[] for _ in range(32)], [None] * 32, [spare - 1] * 32
+				for lane in range(team):
+					m = team * p + (lane + rotation) % team       # the statement lane `lane` of the warp works on
+					rows[lane], owner_of_row[lane] = lists[m][:cap], m
+					if m in owners:
+						helper = owners.index(m)
+						rows[team + helper], owner_of_row[team + helper], code[lane] = lists[m][cap:], m, helper
+				bases.append(len(words) // 2)
+				widths.append(cap // 2)
+				placed = _spread_over_banks(rows, cap, zero_slot) if SPREAD_OVER_BANKS else [row + [None] * (cap - len(row)) for row in rows]
+				for kp in range(cap // 2):
+					for lane in range(32):
+						for k in (2*kp, 2*kp + 1):
+							where = placed[lane][k]
+							entry = 8 * (zero_slot if where is None else where)
+							if owner_of_row[lane] is not None and where in negative[owner_of_row[lane]]:
+								entry |= 0x8000
+							if k == 0 and lane < team:
+								entry |= code[lane] << 12
+							words.append(entry)
+			return tables.add_u(words, align=2), bases, widths
+
+		def print_helped_pairs(table, first, second):
+			offset, bases, widths = table
+			lines.append("\t{")
+			lines.append(f"\t\tconstexpr int pass_base[{n_pass}] = {{ {', '.join(map(str, bases))} }}, pass_pairs[{n_pass}] = {{ {', '.join(map(str, widths))} }};")
+			lines.append(f"\t\tconst unsigned *const pairs = reinterpret_cast<const unsigned *>(JB_TU + {offset}) + pass_base[pass] + lane;")
+			lines.append("\t\tconst unsigned jb_first = pairs[0];")
+			lines.append("#pragma unroll")
+			lines.append("\t\tfor (int k = 0; k < pass_pairs[pass]; ++k) {")
+			lines.append("\t\t\tconst unsigned pair = k ? pairs[k * 32] : jb_first;")
+			lines.append(f"\t\t\t{first} += jb::flip_sign({term.replace(reads, 'y.at(pair & 0x0fffu)')}, pair << 16);")
+			lines.append(f"\t\t\t{second} += jb::flip_sign({term.replace(reads, 'y.at((pair >> 16) & 0x0fffu)')}, pair);")
+			lines.append("\t\t}")
+			lines.append("\t\t// what did not fit the lane's own slots was summed by one of the idle lanes")
+			lines.append(f"\t\t{first} += {second};")
+			lines.append(f"\t\t{second} = jb::shfl({first}, {team} + ((jb_first >> 12) & 7u));")
+			lines.append("\t}")
+
 		def print_pairs(table, first, second, sign):
 			offset, bases, widths = table
 			lines.append("\t{")
@@ -715,7 +808,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 			lines.append("\t\t}")
 			lines.append("\t}")
 
-		extra_table = pair_table(per_statement)
+		extra_table = (helper_table if helper_plan else pair_table)(per_statement)
 		missing_table = pair_table(missing) if missing else None
 		for c, values in enumerate(consts):
 			lines.append(f"\tconst double {loop.prefix}c{c} = {printer.doprint(sympy.Float(values[0]))};")
@@ -783,7 +876,9 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 				else:
 					lines.append(f"\t\tif (present & {1 << k}u) {accumulator} += {value};")
 			lines.append("\t}")
-		if extra_table:
+		if extra_table and helper_plan:
+			print_helped_pairs(extra_table, f"{name}_c", f"{name}_d")
+		elif extra_table:
 			print_pairs(extra_table, f"{name}_c", f"{name}_d", "+")
 		if missing_table:
 			# absent ring neighbours were summed with all the others: taken out again
@@ -918,6 +1013,7 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 	for ((size, (lanes, blocked)), _), members in batches.items():
 		n_pass = (size + lanes - 1) // lanes
 		header, prologue, stores = [], [], []
+		tables.helper_lanes = None
 		if blocked:
 			header.append(f"if (lane < {lanes}) {{")
 		if any(group.loops for _, group in members) and n_pass <= 16:
@@ -940,6 +1036,10 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 			slot_preamble(group.prefix, group.consts, group.indices, "m", "\t")
 			lines.append(f"\tconst double {group.prefix}value = {printer.doprint(group.body)};")
 			stores.append(f"\tdy.set({base} + m, {group.prefix}value);")
+		if blocked and tables.helper_lanes:
+			# the idle lanes take part (gathers, shuffles); they shadow working lanes everywhere else and store nothing
+			header[0] = "{"
+			stores = [f"\tif (lane < {lanes}) " + store.strip() for store in stores]
 		lines.extend(stores)
 		lines.append("}")
 		if blocked:

@@ -102,6 +102,9 @@ __device__ __forceinline__ double flip_sign(double v, unsigned word)
 	return __hiloint2double(__double2hiint(v) ^ (int) (word & 0x80000000u), __double2loint(v));
 }
 
+// value of `v` in lane `source` of the warp (all lanes take part)
+__device__ __forceinline__ double shfl(double v, unsigned source) { return __shfl_sync(0xffffffffu, v, source); }
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

@@ -19,6 +19,16 @@ static std::vector<double> totals, partial;
 static int call_index;
 namespace jb {{
 static inline double flip_sign(double v, unsigned word) {{ return (word & 0x80000000u) ? -v : v; }}
+// a shuffle between lanes that run one after the other: the value the source lane offered in the previous round
+static std::vector<std::vector<double>> offered, offered_before;
+static int shuffle_index, current_lane_index;
+static inline double shfl(double v, unsigned source)
+{{
+	const int c = shuffle_index++;
+	if (c >= (int) offered.size()) {{ offered.resize(c + 1, std::vector<double>(256, NAN)); offered_before.resize(c + 1, std::vector<double>(256, NAN)); }}
+	offered[c][current_lane_index] = v;
+	return offered_before[c][source];
+}}
 template <int W> struct Team {{
 	static double sum(double v, double *)
 	{{
@@ -55,9 +65,12 @@ extern "C" void evaluate(double t, double *row, double *out, const double *pars,
 		partial.assign(partial.size(), 0.0);
 		for (int lane = 0; lane < lanes; ++lane) {{
 			call_index = 0;
+			jb::shuffle_index = 0;
+			jb::current_lane_index = lane;
 			rhs_lane(t, y, dy, par, lane, nullptr);
 		}}
 		totals = partial;
+		jb::offered_before = jb::offered;
 	}}
 }}
 """
@@ -84,6 +97,8 @@ def evaluate_printed(lines, tables, component_of, n_par, t, state, pars, lanes, 
 	out = np.full_like(row, np.nan)
 	parameters = np.asarray(list(pars) + [0.0], dtype=float)
 	as_pointer = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+	if any("jb::shfl" in line for line in lines):
+		rounds += 1          # (what a lane fetches from another lane is there one round later)
 	lib.evaluate(ctypes.c_double(t), as_pointer(row), as_pointer(out), as_pointer(parameters), ctypes.c_int(lanes), ctypes.c_int(rounds))
 	result = np.empty(n)
 	result[component_of] = out[:n]
