@@ -11,6 +11,9 @@ stage loop (register storage) or call out of line (global storage).  The vector 
 accessor macros play in jitced_template.c:38-55.
 """
 
+import os
+import struct
+
 import sympy
 from sympy.core.function import AppliedUndef
 from sympy.printing.c import C99CodePrinter
@@ -31,8 +34,27 @@ class CudaPrinter(C99CodePrinter):
 
 	MAX_PRODUCT_POWER = 8
 
-	def __init__(self):
+	def __init__(self, literals=None):
 		super().__init__({"allow_unknown_functions": True})
+		# numbers that do not fit an instruction's 32-bit immediate (the upper half of a double) are read from the constant
+		# bank as JB_LIT[k] if the caller keeps a table: as a literal each costs two UMOV per use — 16 % of the instructions
+		# of the FitzHugh–Nagumo Lyapunov kernel were UMOV (profiles/r2_fhn_quad_summary.txt)
+		self.literals = literals
+
+	def _constant(self, value, text):
+		if self.literals is None or os.environ.get("JITCODE_B200_INLINE_LITERALS"):
+			return text
+		if struct.unpack("<Q", struct.pack("<d", value))[0] & 0xffffffff == 0:
+			return text
+		if value not in self.literals:
+			self.literals.append(value)
+		return f"JB_LIT[{self.literals.index(value)}]"
+
+	def _print_Float(self, expr):
+		return self._constant(float(expr), super()._print_Float(expr))
+
+	def _print_Rational(self, expr):
+		return self._constant(float(expr), super()._print_Rational(expr))
 
 	def _print_Pow(self, expr):
 		base, exponent = expr.base, expr.exp
@@ -70,6 +92,13 @@ def _repeated_function_calls(expressions):
 	return repeated
 
 
+class Statements(list):
+	"""lines of code, and the table of numbers they refer to as JB_LIT[k]"""
+	def __init__(self, *args):
+		super().__init__(*args)
+		self.literals = []
+
+
 def rhs_statements(f, helpers, control_pars, do_cse=False):
 	"""
 	f            : list of expressions in y(i), t, helper symbols, control parameters
@@ -83,8 +112,8 @@ def rhs_statements(f, helpers, control_pars, do_cse=False):
 	helper_defs = [definition.xreplace(subs) for _, definition in helpers]
 	f = [entry.xreplace(subs) for entry in f]
 
-	printer = CudaPrinter()
-	lines = []
+	lines = Statements()
+	printer = CudaPrinter(lines.literals)
 
 	# shared temporaries: repeated function calls always; full common-subexpression elimination on request
 	everything = helper_defs + f
@@ -158,6 +187,7 @@ def module_source(statements, n, n_params, n_basic, n_lyap, tangent_indices, met
 	warp = storage == JB_STORE_WARP
 	tf = [repr(float(v)) for v in tables.f64] if warp else []
 	tu = [str(int(v)) for v in tables.u] if warp else []
+	literals = [repr(float(v)) for v in getattr(statements, "literals", [])]
 	tu_type = "unsigned short" if (not tu or max(max(int(v) for v in tu), n) < 65536) else "unsigned int"
 	components = [str(int(c)) for c in (component_of if warp else range(n))]
 	n_row = _vectorise_row_length(n) if warp else n
@@ -189,6 +219,11 @@ __device__ const double jb_tf[{max(1, len(tf))}] = {{
 __device__ const {tu_type} jb_tu[{max(1, len(tu))}] = {{
 	{_c_array(tu, 24)}
 }};
+// numbers of the right-hand side that do not fit an instruction's immediate: operands from the constant bank
+__constant__ double jb_lit[{max(1, len(literals))}] = {{
+	{_c_array(literals, 4)}
+}};
+#define JB_LIT jb_generated::jb_lit
 // component stored at each position of the kernel's vectors (identity unless the vectoriser regrouped them)
 __device__ const {tu_type} jb_component[{n}] = {{
 	{_c_array(components, 24)}
