@@ -518,6 +518,7 @@ def _paddable(loop):
 
 
 HELPER_LANES = not os.environ.get("JITCODE_B200_NO_HELPER_LANES")
+SPLIT_REDUCTIONS = not os.environ.get("JITCODE_B200_NO_SPLIT_REDUCTIONS")
 
 
 def team_is_warp(team):
@@ -978,7 +979,16 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 				lines.append(f"{indent}const int {prefix}i{j} = JB_TU[{tables.add_u(values)} + {where}];")
 
 	# helpers: loops spread over the lanes and reduced, the rest redundantly on every lane
+	# Split reduction (one helper with one sum, a single warp per trajectory): the five shuffle steps of the sum over the
+	# warp are a chain of dependent shuffles and additions — 9 % of the stall samples of the Rössler network's kernel for
+	# 4.5 % of its instructions.  Its steps are handed to the first batch, which spreads them over the loads and additions
+	# of its register window (every shuffle sits in a basic block of its own, so the printed order is the executed order).
+	split_steps, split_tail = [], []
+	can_split = SPLIT_REDUCTIONS and team_warps == 1 and len(plan.helpers) == 1 and len(plan.helpers[0][1].loops) == 1 and not pending
 	for symbol, group in plan.helpers:
+		if can_split:
+			loop = group.loops[0]
+			lines.append(f"double {loop.symbol.name}_v;")
 		lines.append("{")
 		for loop in group.loops:
 			count = loop.start[1]
@@ -994,10 +1004,18 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 			slot_preamble(loop.prefix, loop.consts, loop.indices, "k", "\t\t")
 			lines.append(f"\t\t{loop.symbol.name}_acc += {printer.doprint(loop.body)};")
 			lines.append("\t}")
-			lines.append(f"\tconst double {loop.symbol.name} = jb::Team<{team_warps}>::sum({loop.symbol.name}_acc, jb_scratch);")
+			if can_split:
+				lines.append(f"\t{loop.symbol.name}_v = {loop.symbol.name}_acc;")
+				lines.append("}")
+				split_steps = [f"{loop.symbol.name}_v = jb::Team<1>::butterfly<{k}>({loop.symbol.name}_v, jb_scratch);" for k in range(5)]
+				saved, lines = lines, ["{", f"\tconst double {loop.symbol.name} = {loop.symbol.name}_v;"]
+			else:
+				lines.append(f"\tconst double {loop.symbol.name} = jb::Team<{team_warps}>::sum({loop.symbol.name}_acc, jb_scratch);")
 		slot_preamble(group.prefix, group.consts, group.indices, "0", "\t")
 		lines.append(f"\t{symbol.name} = {printer.doprint(group.body)};")
 		lines.append("}")
+		if can_split:
+			split_tail, lines = lines, saved
 		emitted.add(symbol)
 		flush()
 	assert not pending, "unresolvable temporaries"
@@ -1046,7 +1064,20 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 			lines.append("}")
 		if blocked and not any("const int jb_lane" in line for line in prologue):
 			prologue.insert(0, "\tconst int jb_lane = lane;")
+		if split_steps:
+			# the pending reduction: its steps between the blocks of this batch's window if all lanes of the warp get there
+			# (no `if (lane < …)` around the batch) and the window is long enough, otherwise in one piece in front of it
+			closing = [k for k, line in enumerate(prologue) if line == "\t}"]
+			if blocked and header[0] == "{" and len(closing) >= 2 * len(split_steps):
+				for step in reversed(range(len(split_steps))):
+					where = closing[(step + 1) * len(closing) // (len(split_steps) + 1) - 1] + 1
+					prologue.insert(where, "\t" + split_steps[step])
+				prologue.extend("\t" + line for line in split_tail)
+			else:
+				body.extend(split_steps + split_tail)
+			split_steps, split_tail = [], []
 		lines = body + (header[:1] + prologue + header[1:] if blocked else header) + lines
+	lines.extend(split_steps + split_tail)      # (no batch at all)
 	helper_declarations = [f"double {symbol.name};" for symbol, _ in plan.helpers]
 	component_of = [None] * plan.n
 	for component, where in position.items():

@@ -149,6 +149,13 @@ struct Team {
 		if constexpr (W == 1) __syncwarp();
 		else asm volatile("bar.sync %0, %1;" :: "r"(1 + index()), "r"(SIZE) : "memory");   // named barrier per team
 	}
+	// the same sum in five steps that the caller may spread over other work (a single warp: step K of the butterfly;
+	// the additions are those of sum(), in the same order)
+	template <int K> static __device__ __forceinline__ double butterfly(double v, double *scratch)
+	{
+		if constexpr (W == 1) return v + __shfl_xor_sync(0xffffffffu, v, 16 >> K);
+		else return K == 0 ? sum(v, scratch) : v;
+	}
 	// Σ over the team, known to all its threads; `scratch`: W doubles of shared memory owned by the team
 	static __device__ __forceinline__ double sum(double v, double *scratch)
 	{

@@ -37,6 +37,7 @@ template <int W> struct Team {{
 		partial[c] += v;
 		return totals[c];
 	}}
+	template <int K> static double butterfly(double v, double *scratch) {{ return K == 0 ? sum(v, scratch) : v; }}
 }};
 }}
 struct Vec {{
