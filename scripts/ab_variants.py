@@ -3,7 +3,10 @@
     python scripts/ab_variants.py fhn_lyap 100000 threads=64,min_blocks=4 threads=128,min_blocks=3 …
 every argument after the batch size is one variant: extra nvcc flags, or key=value pairs handed to set_integrator.
 Switches the kernels understand: -DJB_NO_STIFFNESS (Hairer's stiffness test compiled out), -DJB_LITERAL_COEF (Runge–Kutta
-coefficients as 64-bit literals instead of constant-bank operands), -DJB_REFILL_LANES=k (lanes that change trajectories together)."""
+coefficients as 64-bit literals instead of constant-bank operands), -DJB_REFILL_LANES=k (lanes that change trajectories together).
+Switches of the generators (environment): JITCODE_B200_NO_HELPER_LANES (idle lanes of a blocked ring do not help with the
+gathers), JITCODE_B200_NO_SPLIT_REDUCTIONS (the mean field's warp sum in one piece), JITCODE_B200_INLINE_LITERALS (numbers of
+the right-hand side as literals instead of constant-bank operands)."""
 import sys
 import time
 import torch
