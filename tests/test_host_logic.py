@@ -258,6 +258,34 @@ def test_printed_code_on_varied_networks(n, neighbours, rewiring, team_warps, se
 	np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-13)
 
 
+@pytest.mark.parametrize("n,neighbours,rewiring,idle", [(100, 20, 0.1, 7), (104, 20, 0.1, 6), (112, 16, 0.12, 4), (120, 20, 0.1, 2), (124, 20, 0.1, 1)])
+def test_idle_lanes_help_with_the_gathers(n, neighbours, rewiring, idle, tmp_path):
+	"""blocked rings that leave lanes of the warp idle: what does not fit the first slots of an over-long statement is
+	gathered by an idle lane and fetched with a shuffle (_helper_plan); with a single idle lane there is nobody to help
+	(its empty row serves the statements that fit).  Printed code on host lanes (shuffles emulated round by round) ≡ the
+	plan's interpreter; the mean field's sum is printed as butterfly steps inside the window when all lanes get there."""
+	from jitcode_b200 import _vectorise
+	from host_lanes import evaluate_printed
+	A = W.small_world_network(np.random.default_rng(n), n, neighbours, rewiring)
+	kappa, mean = sympy.symbols("kappa mean")
+	helpers = [(mean, sympy.Add(*[y(2*j + 1) for j in range(n)]) / n)]
+	f = []
+	for i in range(n):
+		f.append(-0.3 * y(2*i) + y(2*i + 1) + kappa * sympy.Add(*[y(2*j) - y(2*i) for j in range(n) if A[i, j]]))
+		f.append(0.1 * y(2*i) - 0.2 * y(2*i + 1) * mean)
+	f, dimension = _symbolic.handle_input(f, 2 * n)
+	plan = _vectorise.make_plan(f, _symbolic.sort_helpers(helpers), [kappa])
+	assert _vectorise.ring_blockings(plan, 32) == {n: (32 - idle, 4)}
+	lines, tables, component_of = _vectorise.warp_statements(plan)
+	text = "\n".join(lines)
+	assert ("jb::shfl(" in text) == (idle > 1), "helpers where there are idle lanes to spare"
+	assert ("butterfly<4>" in text) and (("if (lane < " + str(32 - idle) + ") {") in text) == (idle <= 1)
+	state = np.random.default_rng(n + 1).random(dimension)
+	expected = _vectorise.evaluate_plan(plan, 0.3, state, [0.7])
+	got = evaluate_printed(lines, tables, component_of, 1, 0.3, state, [0.7], 32, 2, tmp_path)
+	np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-13)
+
+
 def test_warp_configuration_rule():
 	"""cached rows / threads / team size of a warp-storage module follow the measured rule"""
 	from jitcode_b200._jitcode import _warp_configuration
