@@ -393,6 +393,7 @@ class Tables:
 	def __init__(self):
 		self.f64, self.u = [], []
 		self.helper_lanes = None      # set while a batch is printed whose idle lanes help with the gathers (_print_loop)
+		self.single_warp = True       # one warp per trajectory (the helpers' shuffles are warp-wide)
 
 	def add_f64(self, values):
 		offset = len(self.f64)
@@ -718,7 +719,7 @@ def _print_loop(printer, loop, group, position, tables, lines, zero_slot, team, 
 		# lanes beyond `team` run the same gather loop on rows of their own that hold what did NOT fit `cap` slots of an
 		# over-long statement (one such statement per helper lane and pass); its owner fetches the helper's sum with one
 		# shuffle.  For the warp these gathers are free: an LDS.64 of 32 lanes takes the two wavefronts that one of 25 takes.
-		helper_plan = _helper_plan(per_statement, team, n_pass, size) if (signed_pairs and HELPER_LANES and blocked and team_is_warp(team) and 8 * (zero_slot + ZERO_WORDS) <= 4096) else None
+		helper_plan = _helper_plan(per_statement, team, n_pass, size) if (signed_pairs and HELPER_LANES and blocked and tables.single_warp and team_is_warp(team) and 8 * (zero_slot + ZERO_WORDS) <= 4096) else None
 		if helper_plan:
 			tables.helper_lanes = team
 		if blocked and prologue is not None and not any("const int jb_lane" in line for line in prologue):
@@ -921,6 +922,7 @@ def warp_statements(plan, team_warps=1, blocked_rings=True, fuse_groups=True):
 	team = 32 * team_warps
 	printer = CudaPrinter()
 	tables = Tables()
+	tables.single_warp = team_warps == 1
 	lines = []
 	blockings = ring_blockings(plan, team) if blocked_rings else {}
 	groups = [group.reordered(_blocked_order(group.size, *blockings[group.size])) if group.size in blockings else group for group in plan.groups]
