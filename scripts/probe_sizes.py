@@ -7,7 +7,7 @@ from jitcode_b200 import jitcode
 for N, B in [(50, 131072), (200, 65536), (500, 16384)]:
 	system = W.roessler_network(N)
 	Y0, pars = W.roessler_ensemble(B, N=N)
-	for storage in (None, "global"):
+	for storage in ((None,) if "warp-only" in sys.argv else (None, "global")):
 		t0 = time.time()
 		ODE = jitcode(system["f_sym"], helpers=system["helpers"], n=system["n"], control_pars=system["control_pars"], verbose=False)
 		ODE.set_integrator("dopri5", rtol=1e-6, atol=1e-12, storage=storage)
